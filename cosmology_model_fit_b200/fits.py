@@ -1,0 +1,184 @@
+"""Model specs for the reference's fit scripts (one function per script, same name as the script).
+
+Each function takes the tuples the reference's own loaders return (`yXXXX*/data.py: get_data()`) and does
+what the script's import-time section does — Cholesky/inverse of the covariance, the 4000-point z-grid, the
+step-template weights — then describes the model as a `LikelihoodSpec` whose theta column order is the
+script's own.
+
+SN data tuple  : (z_cmb, z_hel, obs, cov)         e.g. y2022pantheonSHOES/data.py:28-35 without the legend
+BAO data tuple : (z, value, quantity, cov)        quantity = strings or CL_BAO_* codes (y2025BAO/data.py)
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.linalg import block_diag, cho_factor
+
+from . import spec as S
+from .spec import LikelihoodSpec
+
+BBN_SCHONEBERG = (0.02218, 0.00055)  # y2024BBN/prior_lcdm_schoneberg.py:2-3
+H0_TRGB = (70.39, 1.80)              # sn/pantheon.py:85
+DES_Y6_BAO = (np.array([0.85]), np.array([19.74]), np.array([S.BAO_DM]), np.array([[0.60**2]]))  # y2024DESBAO/data.py
+SIXDF_BAO = (np.array([0.106]), np.array([2.9761904762]), np.array([S.BAO_DV]), np.array([[0.0176517796]]))  # y20116dFBAO/data.py
+
+
+def _qty_codes(q):
+    q = np.asarray(q)
+    if q.dtype.kind in "US":
+        return np.array([S.BAO_QTY_MAP[str(x)] for x in q], dtype=np.int32)
+    return q.astype(np.int32)
+
+
+def concat_bao(*sets):
+    """np.concatenate of the tables + block_diag of the covariances (bao/desi_cmb_union3.py:20-21)."""
+    z = np.concatenate([np.asarray(s[0], dtype=np.float64) for s in sets])
+    v = np.concatenate([np.asarray(s[1], dtype=np.float64) for s in sets])
+    q = np.concatenate([_qty_codes(s[2]) for s in sets])
+    cov = block_diag(*[np.asarray(s[3], dtype=np.float64) for s in sets])
+    return z, v, q, cov
+
+
+def _cho_lower(cov):
+    """cho_factor(cov, lower=True)[0] with the (garbage) upper triangle cleared (sn/pantheon.py:14)."""
+    return np.tril(cho_factor(np.asarray(cov, dtype=np.float64), lower=True)[0])
+
+
+def _grid(*zs):
+    return LikelihoodSpec.make_grid(max(float(np.max(z)) for z in zs))
+
+
+def _sn_block(sp, sn, form, z_turn, col_offset, col_v):
+    z_cmb, z_hel, obs, cov = sn
+    sp.sn_zcmb, sp.sn_zhel, sp.sn_obs = z_cmb, z_hel, obs
+    sp.sn_cov_form = form
+    sp.sn_mat = _cho_lower(cov) if form == S.SN_CHOLESKY else np.linalg.inv(cov)
+    sp.col_offset = col_offset
+    if col_v is not None:
+        sp.col_vel = (col_v,)
+        sp.sn_vel_weight = LikelihoodSpec.step_weight(z_cmb, z_turn)
+    return sp
+
+
+def _bao_block(sp, bao, dh_mode, rd_mode, rd_fixed=147.09, col_rd=-1):
+    z, v, q, cov = bao
+    sp.bao_z, sp.bao_value, sp.bao_qty = z, v, _qty_codes(q)
+    sp.bao_inv_cov = np.linalg.inv(cov)
+    sp.bao_dh_mode, sp.rd_mode, sp.rd_fixed, sp.col_rd = dh_mode, rd_mode, rd_fixed, col_rd
+    return sp
+
+
+# ---------------------------------------------------------------------------------------------- sn/*
+def sn_pantheon(sn, z_turn=0.15):
+    """sn/pantheon.py (config 0): theta = (M, H0, Om, v); late LCDM; Cholesky chi2; TRGB H0 prior."""
+    bounds = np.array([(-20.0, -19.0), (50.0, 90.0), (0.0, 0.7), (-3.0, 3.0)])  # sn/pantheon.py:68-75
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=1, col_Om=2,
+                        z_grid=_grid(sn[0]), bounds=bounds, gauss_prior=((1, *H0_TRGB),))
+    return _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 3)
+
+
+def sn_des5y(sn, z_turn=0.11):
+    """sn/des5y.py: theta = (dM, H0, Om, v); late LCDM; step at z_cmb <= 0.11 (sn/des5y.py:44-45)."""
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=1, col_Om=2, z_grid=_grid(sn[0]))
+    return _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 3)
+
+
+def sn_union3_1(sn, z_turn=0.2):
+    """sn/union3_1.py: theta = (dM, Om, v); H0 fixed at 70; chi2 = d @ inv_cov @ d."""
+    sp = LikelihoodSpec(ndim=3, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=-1, H0_fixed=70.0, col_Om=1,
+                        z_grid=_grid(sn[0]))
+    return _sn_block(sp, sn, S.SN_INVCOV, z_turn, 0, 2)
+
+
+# --------------------------------------------------------------------------------------------- cmb/*
+def cmb_cmb(consts=None):
+    """cmb/cmb.py: theta = (H0, obh2, och2); compressed CMB only."""
+    consts = consts or S.cmb_planck_act()
+    bounds = np.array([(60.0, 75.0), (0.020, 0.025), (0.05, 0.25)])  # cmb/cmb.py:30-36
+    return LikelihoodSpec(ndim=3, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=0, col_obh2=1, col_och2=2,
+                          cmb_consts=consts, cmb_mode=consts.mode, bounds=bounds,
+                          z_grid=LikelihoodSpec.make_grid(2.33))
+
+
+# --------------------------------------------------------------------------------------------- bao/*
+def bao_desi(desi, des_y6=DES_Y6_BAO):
+    """bao/desi.py: theta = (h, Om, w0); thawing; r_d = 147.09 fixed; pchip D_H; emcee vectorize=True."""
+    bao = concat_bao(desi, des_y6)
+    bounds = np.array([(0.50, 0.80), (0.1, 0.5), (-1.0, 0.0)])  # bao/desi.py:67-73
+    sp = LikelihoodSpec(ndim=3, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=0, H0_scale=100.0, col_Om=1,
+                        col_w0=2, z_grid=_grid(bao[0]), bounds=bounds)
+    return _bao_block(sp, bao, S.DH_PCHIP, S.RD_FIXED, 147.09)
+
+
+def bao_desi_cmb_union3(sn, desi_fs_lya, consts=None, des_y6=DES_Y6_BAO, sixdf=SIXDF_BAO, de_model=S.DE_LCDM):
+    """bao/desi_cmb_union3.py (config 2): theta = (dM, H0, obh2, och2, v [, w0, wa])."""
+    consts = consts or S.cmb_planck_act()
+    bao = concat_bao(desi_fs_lya, des_y6, sixdf)
+    ndim = 5 + (2 if de_model == S.DE_CPL else 1 if de_model in (S.DE_WCDM, S.DE_THAWING) else 0)
+    sp = LikelihoodSpec(ndim=ndim, family=S.FAMILY_FULL, de_model=de_model, col_H0=1, col_obh2=2, col_och2=3,
+                        col_w0=5 if ndim > 5 else -1, col_wa=6 if ndim > 6 else -1, guard_cpl=de_model == S.DE_CPL,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0], bao[0]))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 0, 4)
+    return _bao_block(sp, bao, S.DH_PCHIP, S.RD_FIT)
+
+
+def bao_desi_fs_lya_cmb(desi_fs_lya, consts=None):
+    """bao/desi_fs_lya_cmb.py: theta = (H0, obh2, och2, w0, wa); CPL with the w0+wa>=0 -> -1e8 guard."""
+    consts = consts or S.cmb_planck_act()
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_CPL, col_H0=0, col_obh2=1, col_och2=2,
+                        col_w0=3, col_wa=4, cmb_consts=consts, cmb_mode=consts.mode, guard_cpl=True,
+                        z_grid=_grid(desi_fs_lya[0]))
+    return _bao_block(sp, (desi_fs_lya[0], desi_fs_lya[1], _qty_codes(desi_fs_lya[2]), desi_fs_lya[3]), S.DH_PCHIP, S.RD_FIT)
+
+
+def bao_desi_des5y_bbn_theta_star(sn, desi, consts=None, with_v=False, z_turn=0.10563):
+    """bao/desi_des5y_bbn_theta_star.py (config 1): theta = (dM, H0, obh2, och2, w0 [, v]); thawing; l_A-only CMB
+    term d^2/cov[1,1]; BBN Gaussian in the prior.  `with_v=True` adds the z_turn=0.10563 step of the sibling DES
+    scripts (bao/desi_cmb_des5y.py:103-111) as BASELINE.json's config text asks."""
+    consts = consts or S.cmb_planck_act()
+    bounds = [(-0.5, 0.5), (50.0, 90.0), (0.010, 0.030), (0.05, 0.30), (-1.0, -1 / 3)]  # :122-130
+    if with_v:
+        bounds.append((-4.5, 4.5))
+    w = np.zeros((3, 3))
+    w[1, 1] = 1.0 / consts.covariance[1, 1]  # :110-111
+    sp = LikelihoodSpec(ndim=len(bounds), family=S.FAMILY_FULL, de_model=S.DE_THAWING, col_H0=1, col_obh2=2, col_och2=3,
+                        col_w0=4, cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=w,
+                        z_grid=_grid(sn[0], desi[0]), bounds=np.array(bounds), gauss_prior=((2, *BBN_SCHONEBERG),))
+    _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 5 if with_v else None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_cmb_pantheon(sn, desi, consts=None, z_turn=0.15):
+    """bao/desi_cmb_pantheon.py (config 3): theta = (M, H0, obh2, och2, v); LCDM as checked in."""
+    consts = consts or S.cmb_planck_act()
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0], desi[0]))
+    _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 4)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_cmb_des5y(sn, desi_fs_lya, consts=None, z_turn=0.10563):
+    """bao/desi_cmb_des5y.py: theta = (dM, H0, obh2, och2, v); pchip D_H; F_AP rows; step at 0.10563."""
+    consts = consts or S.cmb_planck_act()
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0], desi_fs_lya[0]))
+    _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 4)
+    return _bao_block(sp, desi_fs_lya, S.DH_PCHIP, S.RD_FIT)
+
+
+def bao_desi_bbn(desi, consts=None):
+    """bao/desi_bbn.py: theta = (H0, Om, obh2, w0); late thawing; r_d = r_drag(obh2, Om h^2); pchip D_H."""
+    consts = consts or S.cmb_planck()
+    bounds = np.array([(55.0, 75.0), (0.17, 0.50), (0.016, 0.030), (-1.0, -1 / 3)])  # bao/desi_bbn.py:70-77
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=0, col_Om=1, col_obh2=2, col_w0=3,
+                        cmb_consts=consts, z_grid=_grid(desi[0]), bounds=bounds)
+    return _bao_block(sp, desi, S.DH_PCHIP, S.RD_FIT)
+
+
+# --------------------------------------------------------------------------------------------- ohd/*
+def ohd_cc(cc):
+    """ohd/cc.py: theta = (H0, Om, f); chi2 = f^2 d^T C^-1 d; log L adds N ln 2pi + logdet - 2N ln f."""
+    z, H, cov = cc
+    return LikelihoodSpec(ndim=3, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=0, col_Om=1,
+                          cc_z=z, cc_H=H, cc_inv_cov=np.linalg.inv(cov), col_fcc=2,
+                          cc_logdet=float(np.linalg.slogdet(cov)[1]), cc_norm_sign=1.0,
+                          z_grid=LikelihoodSpec.make_grid(float(np.max(z))))
