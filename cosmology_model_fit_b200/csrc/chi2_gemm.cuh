@@ -1,0 +1,243 @@
+// chi2_gemm.cuh — stage 3: chi2_sn[b] = | W r_b |^2 for a whole batch, W = L^-1 lower triangular.
+//
+// Replaces the reference's per-theta forward substitution (solve_triangular.py:5-14: y = L^-1 delta, return
+// y.y) by one batched contraction Y[B,N] = R[B,N] . W^T restricted to the lower triangle, on the FP64 tensor
+// pipe (mma.sync f64 -> DMMA.8x8x4 on sm_100a), with a fused row-dot epilogue: Y is never written, only the
+// per-row sum of squares of each 128-column tile.
+//
+// Data movement: TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) brings [128 rows x 16 k] boxes of R and of W
+// into a 6-stage shared-memory ring guarded by full/empty mbarriers; one producer warp, eight consumer warps
+// (2 along M x 4 along N, warp tile 64x32, accumulators in registers).  Fragments are read with conflict-free
+// 128-bit shared loads: the k index inside a k16 step is permuted (lane t owns k = 4t..4t+3) identically for
+// both operands, which leaves the product unchanged.
+//
+// Work decomposition: items (row block, column tile) ordered by decreasing k-extent of the column tile and
+// dealt round-robin to a persistent grid; the k loop of column tile j stops at the diagonal, so only
+// ~N^2/2 (1 + 128/N) MACs per row are executed instead of N^2.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cosmolike {
+
+constexpr int kBM = 128, kBN = 128, kBK = 16;
+constexpr int kStages = 6;
+constexpr int kConsumerWarps = 8;
+constexpr int kGemmThreads = (kConsumerWarps + 1) * 32;
+constexpr int kBoxBytes = kBM * kBK * 8;       // 16 KB, A and B boxes have the same shape
+constexpr int kStageBytes = 2 * kBoxBytes;     // 32 KB
+constexpr int kGemmSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 4 * kBM * 8 /*epilogue*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+  int64_t B;       // rows of R in this pass
+  int N;           // SN count
+  int T;           // column tiles = ceil(N / 128)
+  int n_rb;        // row blocks = ceil(B / 128)
+  double* part;    // [T][B] partial sums of squares
+  double* part_u;  // nullable [T][B]: partial sums of y_j * u_j (moments mode)
+  const double* u; // [N] u = W 1 (moments mode)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mma_f64_16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+        "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+template <bool MOMENTS>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+  extern __shared__ unsigned char gsm_raw[];
+  const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
+  unsigned char* base_ptr = gsm_raw + (base - smem_u32(gsm_raw));
+  const uint32_t sA = base;                                   // [stage][128 rows][128 B]
+  const uint32_t sB = base + kStages * kBoxBytes;
+  double* s_epi = reinterpret_cast<double*>(base_ptr + kStages * kStageBytes);  // [2][4][128]
+  const uint32_t bars = base + kStages * kStageBytes + 2 * 4 * kBM * 8;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t total = (int64_t)g.n_rb * g.T;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == kConsumerWarps) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int jt = g.T - 1 - (int)(item / g.n_rb);
+        const int rb = (int)(item % g.n_rb);
+        const int kmax = min(g.N, (jt + 1) * kBN);
+        const int nk = (kmax + kBK - 1) / kBK;
+        for (int ks = 0; ks < nk; ks++) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+          tma_load_2d(sA + stage * kBoxBytes, &tmR, ks * kBK, rb * kBM, full_bar(stage));
+          tma_load_2d(sB + stage * kBoxBytes, &tmW, ks * kBK, jt * kBN, full_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers: DMMA + fused row-dot epilogue =====================
+  const int gq = lane >> 2, t = lane & 3;   // mma "groupID" and "threadID_in_group"
+  const int warp_m = warp & 1, warp_n = warp >> 1;
+  // byte offsets of this lane's two 16-byte chunks inside a 128-byte row, after the 128B swizzle
+  const uint32_t ch0 = (uint32_t)(((2 * t) ^ gq) << 4), ch1 = (uint32_t)(((2 * t + 1) ^ gq) << 4);
+  const uint32_t a_row0 = (uint32_t)(warp_m * 64 + gq) * 128u;  // + mt*16*128 (+8 rows = +1024)
+  const uint32_t b_row0 = (uint32_t)(warp_n * 32 + gq) * 128u;  // + nt*8*128
+  int epi_buf = 0;
+
+  for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const int jt = g.T - 1 - (int)(item / g.n_rb);
+    const int rb = (int)(item % g.n_rb);
+    const int kmax = min(g.N, (jt + 1) * kBN);
+    const int nk = (kmax + kBK - 1) / kBK;
+
+    double acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[i][j][q] = 0.0;
+
+    for (int ks = 0; ks < nk; ks++) {
+      mbar_wait(full_bar(stage), phase);
+      const uint32_t aS = sA + stage * kBoxBytes + a_row0;
+      const uint32_t bS = sB + stage * kBoxBytes + b_row0;
+      double bf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        double2 lo = lds128(bS + nt * 1024 + ch0), hi = lds128(bS + nt * 1024 + ch1);
+        bf[nt][0] = lo.x; bf[nt][1] = lo.y; bf[nt][2] = hi.x; bf[nt][3] = hi.y;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) {
+        const uint32_t ar = aS + mt * 2048;
+        double2 r0lo = lds128(ar + ch0), r0hi = lds128(ar + ch1);
+        double2 r1lo = lds128(ar + 1024 + ch0), r1hi = lds128(ar + 1024 + ch1);
+        // a_i: row = g + 8*(i&1), logical k = t + 4*(i>>1) -> physical k = 4t + (i>>1)
+        double af[8] = {r0lo.x, r1lo.x, r0lo.y, r1lo.y, r0hi.x, r1hi.x, r0hi.y, r1hi.y};
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) mma_f64_16816(acc[mt][nt], af, bf[nt]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+
+    // ---- epilogue: per-row sum over this warp's 32 columns of y^2 (and y*u) ----
+    double* epi = s_epi + epi_buf * (4 * kBM);
+    double* epi_u = nullptr;
+    (void)epi_u;
+    double uu[4][2];
+    if (MOMENTS) {
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        int col = jt * kBN + warp_n * 32 + nt * 8 + 2 * t;
+        uu[nt][0] = col < g.N ? g.u[col] : 0.0;
+        uu[nt][1] = col + 1 < g.N ? g.u[col + 1] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+      double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        s0 += acc[mt][nt][0] * acc[mt][nt][0] + acc[mt][nt][1] * acc[mt][nt][1];
+        s1 += acc[mt][nt][2] * acc[mt][nt][2] + acc[mt][nt][3] * acc[mt][nt][3];
+        if (MOMENTS) {
+          u0 += acc[mt][nt][0] * uu[nt][0] + acc[mt][nt][1] * uu[nt][1];
+          u1 += acc[mt][nt][2] * uu[nt][0] + acc[mt][nt][3] * uu[nt][1];
+        }
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      if (MOMENTS) {
+        u0 += __shfl_xor_sync(0xffffffffu, u0, 1); u0 += __shfl_xor_sync(0xffffffffu, u0, 2);
+        u1 += __shfl_xor_sync(0xffffffffu, u1, 1); u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
+      }
+      const int r = warp_m * 64 + mt * 16 + gq;
+      if (t == 0) { epi[warp_n * kBM + r] = s0; epi[warp_n * kBM + r + 8] = s1; }
+      if (MOMENTS && t == 1) {
+        // the y.u partials share the epilogue buffer of the other parity: written after the barrier below
+        acc[mt][0][0] = u0; acc[mt][0][1] = u1;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+    if (tid < kBM) {
+      const int64_t row = (int64_t)rb * kBM + tid;
+      if (row < g.B) g.part[(int64_t)jt * g.B + row] = (epi[tid] + epi[kBM + tid]) + (epi[2 * kBM + tid] + epi[3 * kBM + tid]);
+    }
+    if (MOMENTS) {
+      // second pass through the same buffer for y.u
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+      if (t == 1) {
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          const int r = warp_m * 64 + mt * 16 + gq;
+          epi[warp_n * kBM + r] = acc[mt][0][0]; epi[warp_n * kBM + r + 8] = acc[mt][0][1];
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+      if (tid < kBM) {
+        const int64_t row = (int64_t)rb * kBM + tid;
+        if (row < g.B) g.part_u[(int64_t)jt * g.B + row] = (epi[tid] + epi[kBM + tid]) + (epi[2 * kBM + tid] + epi[3 * kBM + tid]);
+      }
+    }
+    epi_buf ^= 1;
+  }
+}
+
+}  // namespace cosmolike

@@ -1,0 +1,678 @@
+// cosmolike.cu — C ABI of libcosmolike_b200.so (see include/cosmolike.h).
+// Host side: context, device copies of the static operands, W = L^-1 in extended precision, TMA descriptors,
+// pinned staging and the three-stage launch sequence.  No torch, no Python; plain CUDA runtime + one driver
+// entry point (cuTensorMapEncodeTiled) resolved at run time.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/cosmolike.h"
+#include "chi2_gemm.cuh"
+#include "devspec.h"
+#include "friedmann.cuh"
+
+using namespace cosmolike;
+
+static thread_local std::string g_create_error;
+
+struct cl_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  bool timing_valid = false;
+  DevSpec ds{};
+  std::vector<void*> dev_allocs;
+  // stage 3 operands
+  double* d_W = nullptr;  // [n_sn][ldW] = L^-1
+  double* d_u = nullptr;  // [n_sn] u = W 1
+  double uu = 0.0;        // u.u
+  int64_t ldW = 0;
+  int T = 0;
+  CUtensorMap tmW{};
+  // workspace
+  int64_t cap_rows = 0, max_rows = 65536;
+  int64_t ldR = 0;
+  double *d_theta = nullptr, *d_out = nullptr, *d_R = nullptr, *d_aux = nullptr, *d_part = nullptr, *d_part_u = nullptr;
+  double *d_scratch = nullptr;  // helper outputs
+  int64_t scratch_bytes = 0;
+  double *h_theta = nullptr, *h_out = nullptr;  // pinned
+  int64_t h_theta_cap = 0, h_out_cap = 0;
+  int64_t launches = 0;
+  int opt_gemm_ctas = 0, opt_s12_ctas = 0;
+  std::string err, desc;
+  std::mutex mu;
+};
+
+static int fail(cl_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                            \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) return fail(ctx, CL_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D f64 tensor [rows][cols] with row stride ld (elements), box = [kBM rows][kBK cols], 128-byte swizzle
+static int make_tmap(cl_ctx* c, CUtensorMap* tm, const double* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(c, CL_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CL_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return CL_OK;
+}
+
+template <typename T>
+static int upload(cl_ctx* c, const T* src, size_t n, const T** dst) {
+  *dst = nullptr;
+  if (!src || n == 0) return CL_OK;
+  void* p = nullptr;
+  CUDA_TRY(c, cudaMalloc(&p, n * sizeof(T)));
+  c->dev_allocs.push_back(p);
+  CUDA_TRY(c, cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = (const T*)p;
+  return CL_OK;
+}
+
+// ---- W = L^-1 (lower triangular, row-major) in long double, column blocks in parallel ----
+static bool invert_lower(const double* L, int n, int64_t ldL, std::vector<double>& W, int64_t ldW) {
+  for (int i = 0; i < n; i++)
+    if (!(L[(size_t)i * ldL + i] > 0.0) || !std::isfinite(L[(size_t)i * ldL + i])) return false;
+  W.assign((size_t)n * ldW, 0.0);
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  int nthreads = (int)std::min<unsigned>(hw, 32u);
+  if (n < 256) nthreads = 1;
+  const int cb = 32;  // column block
+  std::vector<std::thread> pool;
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    std::vector<long double> X((size_t)n * cb);
+    for (;;) {
+      int blk = next.fetch_add(1);
+      int j0 = blk * cb;
+      if (j0 >= n) break;
+      int jw = std::min(cb, n - j0);
+      // solve L X = E[:, j0:j0+jw]; rows < j0 of X are zero
+      for (int i = j0; i < n; i++) {
+        long double* xi = &X[(size_t)i * cb];
+        for (int q = 0; q < jw; q++) xi[q] = (i == j0 + q) ? 1.0L : 0.0L;
+        const double* Li = L + (size_t)i * ldL;
+        for (int k = j0; k < i; k++) {
+          long double lik = Li[k];
+          const long double* xk = &X[(size_t)k * cb];
+          for (int q = 0; q < jw; q++) xi[q] -= lik * xk[q];
+        }
+        long double inv = 1.0L / (long double)Li[i];
+        for (int q = 0; q < jw; q++) xi[q] *= inv;
+        for (int q = 0; q < jw; q++) W[(size_t)i * ldW + j0 + q] = (j0 + q <= i) ? (double)xi[q] : 0.0;
+      }
+    }
+  };
+  for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return true;
+}
+
+// Cholesky of a symmetric positive definite matrix given by its INVERSE (CL_SN_INVCOV with a large block):
+// C = inv(Cinv) by Gauss-Jordan-free route: factor Cinv = G G^T, then C = G^-T G^-1 and chol(C) is formed anew.
+static bool cholesky_lower_ld(std::vector<long double>& A, int n) {
+  for (int j = 0; j < n; j++) {
+    long double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(d > 0.0L)) return false;
+    d = sqrtl(d);
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      long double s = A[(size_t)i * n + j];
+      for (int k = 0; k < j; k++) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      A[(size_t)i * n + j] = s / d;
+    }
+    for (int i = 0; i < j; i++) A[(size_t)i * n + j] = 0.0L;
+  }
+  return true;
+}
+
+static bool lower_factor_from_invcov(const double* Cinv, int n, std::vector<double>& L) {
+  // Cinv = G G^T ; C = G^-T G^-1 ; L = chol(C)
+  std::vector<long double> G((size_t)n * n);
+  for (size_t i = 0; i < (size_t)n * n; i++) G[i] = Cinv[i];
+  if (!cholesky_lower_ld(G, n)) return false;
+  std::vector<double> Gd((size_t)n * n), Ginv;
+  for (size_t i = 0; i < (size_t)n * n; i++) Gd[i] = (double)G[i];
+  if (!invert_lower(Gd.data(), n, n, Ginv, n)) return false;
+  std::vector<long double> Cm((size_t)n * n, 0.0L);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      long double s = 0.0L;
+      for (int k = i; k < n; k++) s += (long double)Ginv[(size_t)k * n + i] * Ginv[(size_t)k * n + j];
+      Cm[(size_t)i * n + j] = s;
+      Cm[(size_t)j * n + i] = s;
+    }
+  if (!cholesky_lower_ld(Cm, n)) return false;
+  L.resize((size_t)n * n);
+  for (size_t i = 0; i < (size_t)n * n; i++) L[i] = (double)Cm[i];
+  return true;
+}
+
+// ---- kernel dispatch over the (family, dark-energy) instantiations ----
+typedef void (*S12Kernel)(const DevSpec, const Stage12Args);
+static S12Kernel pick_s12(int fam, int de) {
+#define CASE(F, D) if (fam == F && de == D) return k_friedmann_residuals<F, D>;
+  CASE(CL_FAMILY_LATE, CL_DE_LCDM) CASE(CL_FAMILY_LATE, CL_DE_WCDM) CASE(CL_FAMILY_LATE, CL_DE_CPL) CASE(CL_FAMILY_LATE, CL_DE_THAWING)
+  CASE(CL_FAMILY_FULL, CL_DE_LCDM) CASE(CL_FAMILY_FULL, CL_DE_WCDM) CASE(CL_FAMILY_FULL, CL_DE_CPL) CASE(CL_FAMILY_FULL, CL_DE_THAWING)
+#undef CASE
+  return nullptr;
+}
+
+static int validate(const cl_spec* s) {
+  if (!s) return fail(nullptr, CL_E_INVALID, "spec is NULL");
+  if (s->abi_version != CL_ABI_VERSION) return fail(nullptr, CL_E_INVALID, "abi_version %u != %u", s->abi_version, CL_ABI_VERSION);
+  if (s->ndim < 1 || s->ndim > CL_MAX_DIM) return fail(nullptr, CL_E_INVALID, "ndim out of range");
+  auto col_ok = [&](int c, bool required) { return required ? (c >= 0 && c < s->ndim) : (c >= -1 && c < s->ndim); };
+  if (s->family != CL_FAMILY_LATE && s->family != CL_FAMILY_FULL) return fail(nullptr, CL_E_INVALID, "bad family");
+  if (s->de_model < CL_DE_LCDM || s->de_model > CL_DE_THAWING) return fail(nullptr, CL_E_INVALID, "bad de_model");
+  if (!col_ok(s->col_H0, false)) return fail(nullptr, CL_E_INVALID, "col_H0 out of range");
+  if (s->family == CL_FAMILY_LATE && !col_ok(s->col_Om, true)) return fail(nullptr, CL_E_INVALID, "LATE family needs col_Om");
+  if (s->family == CL_FAMILY_FULL && (!col_ok(s->col_obh2, true) || !col_ok(s->col_och2, true)))
+    return fail(nullptr, CL_E_INVALID, "FULL family needs col_obh2 and col_och2");
+  if (s->de_model != CL_DE_LCDM && !col_ok(s->col_w0, true)) return fail(nullptr, CL_E_INVALID, "dark-energy model needs col_w0");
+  if (s->de_model == CL_DE_CPL && !col_ok(s->col_wa, true)) return fail(nullptr, CL_E_INVALID, "CPL needs col_wa");
+  const bool need_grid = s->n_sn > 0 || s->n_bao > 0;
+  if (need_grid || s->z_grid) {
+    if (!s->z_grid || s->n_grid < 16 || s->n_grid > kS12Threads * kPPT) return fail(nullptr, CL_E_INVALID, "z_grid must have 16..4096 points");
+    for (int i = 1; i < s->n_grid; i++)
+      if (!(s->z_grid[i] > s->z_grid[i - 1])) return fail(nullptr, CL_E_INVALID, "z_grid must be strictly increasing");
+  }
+  if (s->n_sn < 0 || s->n_bao < 0 || s->n_bao > CL_MAX_BAO || s->n_cc < 0 || s->n_cc > CL_MAX_CC) return fail(nullptr, CL_E_INVALID, "block size out of range");
+  if (s->n_sn > 0) {
+    if (!s->sn_zcmb || !s->sn_zhel || !s->sn_obs || !s->sn_mat) return fail(nullptr, CL_E_INVALID, "SN block has NULL arrays");
+    if (!col_ok(s->col_offset, false)) return fail(nullptr, CL_E_INVALID, "col_offset out of range");
+    if (s->n_vel < 0 || s->n_vel > CL_MAX_VEL || (s->n_vel > 0 && !s->sn_vel_weight)) return fail(nullptr, CL_E_INVALID, "bad velocity templates");
+    for (int k = 0; k < s->n_vel; k++) if (!col_ok(s->col_vel[k], true)) return fail(nullptr, CL_E_INVALID, "col_vel out of range");
+  }
+  if (s->n_bao > 0) {
+    if (!s->bao_z || !s->bao_value || !s->bao_qty || !s->bao_inv_cov) return fail(nullptr, CL_E_INVALID, "BAO block has NULL arrays");
+    if (s->rd_mode == CL_RD_PARAM && !col_ok(s->col_rd, true)) return fail(nullptr, CL_E_INVALID, "col_rd out of range");
+    if (s->rd_mode == CL_RD_FIT && s->family == CL_FAMILY_LATE && !col_ok(s->col_obh2, true)) return fail(nullptr, CL_E_INVALID, "r_drag fit needs col_obh2");
+    for (int k = 0; k < s->n_bao; k++) if (s->bao_qty[k] < 0 || s->bao_qty[k] > 3) return fail(nullptr, CL_E_INVALID, "bad BAO quantity code");
+  }
+  if (s->cmb_mode != CL_CMB_NONE && s->family != CL_FAMILY_FULL) return fail(nullptr, CL_E_INVALID, "CMB block needs the FULL family");
+  if (s->n_gl < 0 || s->n_gl > CL_MAX_GL) return fail(nullptr, CL_E_INVALID, "n_gl out of range");
+  if (s->n_cc > 0 && (!s->cc_z || !s->cc_H || !s->cc_inv_cov || !col_ok(s->col_fcc, false))) return fail(nullptr, CL_E_INVALID, "bad CC block");
+  if (s->n_gauss_chi2 < 0 || s->n_gauss_chi2 > CL_MAX_GAUSS || s->n_gauss_prior < 0 || s->n_gauss_prior > CL_MAX_GAUSS)
+    return fail(nullptr, CL_E_INVALID, "too many Gaussian terms");
+  for (int g = 0; g < s->n_gauss_chi2; g++) if (!col_ok(s->gauss_chi2_col[g], true)) return fail(nullptr, CL_E_INVALID, "gauss_chi2_col out of range");
+  for (int g = 0; g < s->n_gauss_prior; g++) if (!col_ok(s->gauss_prior_col[g], true)) return fail(nullptr, CL_E_INVALID, "gauss_prior_col out of range");
+  return CL_OK;
+}
+
+static void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w) {
+  x.resize(n); w.resize(n);
+  for (int i = 0; i < n; i++) {
+    double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; it++) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; j++) { double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1); }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      double dz = p1 / pp;
+      z -= dz;
+      if (fabs(dz) < 1e-16) break;
+    }
+    x[n - 1 - i] = z;
+    w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
+extern "C" int cl_destroy(cl_ctx* c) {
+  if (!c) return CL_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void* p : c->dev_allocs) cudaFree(p);
+  for (double* p : {c->d_theta, c->d_out, c->d_R, c->d_aux, c->d_part, c->d_part_u, c->d_scratch, c->d_W, c->d_u}) if (p) cudaFree(p);
+  if (c->h_theta) cudaFreeHost(c->h_theta);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return CL_OK;
+}
+
+extern "C" const char* cl_last_error(const cl_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+extern "C" const char* cl_describe(const cl_ctx* c) { return c ? c->desc.c_str() : "cosmolike_b200 (no context)"; }
+extern "C" int64_t cl_launch_count(const cl_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
+  if (!out) return fail(nullptr, CL_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate(spec);
+  if (rc != CL_OK) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, CL_E_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, CL_E_NO_DEVICE, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, CL_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, CL_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+  cl_ctx* c = new cl_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  auto bail = [&](int code) { g_create_error = c->err; cl_destroy(c); return code; };
+#define TRY(expr) do { int r_ = (expr); if (r_ != CL_OK) return bail(r_); } while (0)
+#define CTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(c, CL_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CL_E_CUDA); } } while (0)
+  CTRY(cudaSetDevice(device));
+  CTRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) CTRY(cudaEventCreate(&e));
+
+  DevSpec& d = c->ds;
+  const cl_spec& s = *spec;
+  d.ndim = s.ndim; d.family = s.family; d.de_model = s.de_model;
+  d.col_H0 = s.col_H0; d.col_Om = s.col_Om; d.Om_is_physical = s.Om_is_physical; d.col_obh2 = s.col_obh2; d.col_och2 = s.col_och2;
+  d.col_w0 = s.de_model == CL_DE_LCDM ? -1 : s.col_w0; d.col_wa = s.de_model == CL_DE_CPL ? s.col_wa : -1;
+  d.H0_fixed = s.H0_fixed; d.H0_scale = s.H0_scale; d.k = s.cmbc;
+  // grid
+  d.G = s.z_grid ? s.n_grid : 0;
+  if (s.z_grid) {
+    TRY(upload(c, s.z_grid, (size_t)s.n_grid, &d.z_grid));
+    // np.linspace(0, stop, n): y = arange(n) * step with step = stop/(n-1), last element := stop
+    double step = s.z_grid[1];
+    bool uni = s.z_grid[0] == 0.0 && step > 0.0;
+    for (int i = 0; uni && i < s.n_grid - 1; i++) uni = (s.z_grid[i] == (double)i * step);
+    d.grid_uniform = uni ? 1 : 0;
+    d.step = step; d.inv_step = 1.0 / step; d.z_last = s.z_grid[s.n_grid - 1];
+  }
+  // SN
+  d.n_sn = s.n_sn;
+  if (s.n_sn > 0) {
+    const int n = s.n_sn;
+    d.sn_small = n <= CL_SN_SMALL_MAX ? 1 : 0;
+    d.sn_form = s.sn_cov_form; d.col_offset = s.col_offset; d.n_vel = s.n_vel; d.vel_mode = s.vel_mode; d.vel_scale = s.vel_scale;
+    for (int k = 0; k < CL_MAX_VEL; k++) d.col_vel[k] = k < s.n_vel ? s.col_vel[k] : 0;
+    std::vector<double> zhelp1(n);
+    for (int i = 0; i < n; i++) zhelp1[i] = 1.0 + s.sn_zhel[i];  // (1.0 + z_hel), sn/pantheon.py:54
+    TRY(upload(c, s.sn_zcmb, (size_t)n, &d.sn_zcmb));
+    TRY(upload(c, zhelp1.data(), (size_t)n, &d.sn_zhelp1));
+    TRY(upload(c, s.sn_obs, (size_t)n, &d.sn_obs));
+    if (s.n_vel > 0) TRY(upload(c, s.sn_vel_weight, (size_t)n * s.n_vel, &d.sn_vel_w));
+    // factor handling
+    std::vector<double> Lbuf;
+    const double* L = s.sn_mat;
+    if (s.sn_cov_form == CL_SN_INVCOV && !d.sn_small) {
+      if (!lower_factor_from_invcov(s.sn_mat, n, Lbuf)) { fail(c, CL_E_NUMERIC, "inverse covariance is not positive definite"); return bail(CL_E_NUMERIC); }
+      L = Lbuf.data();
+    }
+    if (d.sn_small && s.sn_cov_form == CL_SN_INVCOV) {
+      TRY(upload(c, s.sn_mat, (size_t)n * n, &d.sn_mat_small));
+    } else {
+      c->ldW = ((int64_t)n + 1) & ~1LL;  // 16-byte row stride for TMA
+      std::vector<double> W;
+      if (!invert_lower(L, n, n, W, c->ldW)) { fail(c, CL_E_NUMERIC, "Cholesky factor has a non-positive diagonal"); return bail(CL_E_NUMERIC); }
+      std::vector<double> u(n);
+      long double uu = 0.0L;
+      for (int i = 0; i < n; i++) {
+        long double acc = 0.0L;
+        for (int j = 0; j <= i; j++) acc += W[(size_t)i * c->ldW + j];
+        u[i] = (double)acc; uu += acc * acc;
+      }
+      c->uu = (double)uu;
+      if (d.sn_small) {
+        std::vector<double> Wc((size_t)n * n);
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Wc[(size_t)i * n + j] = W[(size_t)i * c->ldW + j];
+        TRY(upload(c, Wc.data(), Wc.size(), &d.sn_mat_small));
+      } else {
+        CTRY(cudaMalloc(&c->d_W, W.size() * sizeof(double)));
+        CTRY(cudaMemcpy(c->d_W, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CTRY(cudaMalloc(&c->d_u, n * sizeof(double)));
+        CTRY(cudaMemcpy(c->d_u, u.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+        c->T = (n + kBN - 1) / kBN;
+        c->ldR = ((int64_t)n + 15) & ~15LL;
+        TRY(make_tmap(c, &c->tmW, c->d_W, n, n, c->ldW));
+      }
+    }
+  }
+  // BAO
+  d.n_bao = s.n_bao;
+  if (s.n_bao > 0) {
+    d.dh_mode = s.bao_dh_mode; d.rd_mode = s.rd_mode; d.col_rd = s.col_rd; d.rd_fixed = s.rd_fixed;
+    TRY(upload(c, s.bao_z, (size_t)s.n_bao, &d.bao_z));
+    TRY(upload(c, s.bao_value, (size_t)s.n_bao, &d.bao_val));
+    TRY(upload(c, s.bao_qty, (size_t)s.n_bao, &d.bao_qty));
+    TRY(upload(c, s.bao_inv_cov, (size_t)s.n_bao * s.n_bao, &d.bao_W));
+  } else {
+    d.rd_mode = s.rd_mode; d.col_rd = s.col_rd; d.rd_fixed = s.rd_fixed;
+  }
+  // CMB + GL nodes
+  d.cmb_mode = s.cmb_mode;
+  for (int i = 0; i < 3; i++) d.cmb_prior[i] = s.cmb_prior[i];
+  for (int i = 0; i < 9; i++) d.cmb_W[i] = s.cmb_weight[i];
+  if (s.family == CL_FAMILY_FULL) {
+    std::vector<double> gx, gw;
+    const double *px = s.gl_x, *pw = s.gl_w;
+    int ngl = s.n_gl;
+    if (!px || !pw || ngl <= 0) { ngl = 100; gauss_legendre(ngl, gx, gw); px = gx.data(); pw = gw.data(); }
+    d.n_gl = ngl;
+    TRY(upload(c, px, (size_t)ngl, &d.gl_x));
+    TRY(upload(c, pw, (size_t)ngl, &d.gl_w));
+  }
+  // CC
+  d.n_cc = s.n_cc; d.col_fcc = s.n_cc > 0 ? s.col_fcc : -1; d.cc_logdet = s.cc_logdet; d.cc_norm_sign = s.cc_norm_sign;
+  if (s.n_cc > 0) {
+    TRY(upload(c, s.cc_z, (size_t)s.n_cc, &d.cc_z));
+    TRY(upload(c, s.cc_H, (size_t)s.n_cc, &d.cc_H));
+    TRY(upload(c, s.cc_inv_cov, (size_t)s.n_cc * s.n_cc, &d.cc_W));
+  }
+  // Gaussian terms, prior, guard
+  d.n_gc = s.n_gauss_chi2; d.n_gp = s.n_gauss_prior; d.has_bounds = s.has_bounds; d.guard_cpl = s.guard_cpl;
+  for (int g = 0; g < CL_MAX_GAUSS; g++) {
+    d.gc_col[g] = s.gauss_chi2_col[g]; d.gc_mean[g] = s.gauss_chi2_mean[g]; d.gc_sigma[g] = s.gauss_chi2_sigma[g];
+    d.gp_col[g] = s.gauss_prior_col[g]; d.gp_mean[g] = s.gauss_prior_mean[g]; d.gp_sigma[g] = s.gauss_prior_sigma[g];
+  }
+  for (int j = 0; j < CL_MAX_DIM; j++) { d.lo[j] = s.lo[j]; d.hi[j] = s.hi[j]; }
+  d.lp_norm = s.log_prior_norm; d.guard_value = s.guard_value;
+
+  // kernel attributes
+  S12Kernel k12 = pick_s12(d.family, d.de_model);
+  CTRY(cudaFuncSetAttribute(k12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
+  CTRY(cudaFuncSetAttribute(k_chi2_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  CTRY(cudaFuncSetAttribute(k_chi2_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+
+  char buf[256];
+  snprintf(buf, sizeof buf, "cosmolike_b200 abi %u, sm_100a, %s (%d SMs), n_sn=%d n_bao=%d cmb=%d n_cc=%d grid=%d%s", CL_ABI_VERSION, prop.name,
+           prop.multiProcessorCount, d.n_sn, d.n_bao, d.cmb_mode, d.n_cc, d.G, d.grid_uniform ? " uniform" : "");
+  c->desc = buf;
+  *out = c;
+  return CL_OK;
+#undef TRY
+#undef CTRY
+}
+
+extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) return CL_E_INVALID;
+  std::string n(name);
+  if (n == "max_rows_per_pass") { if (value < 128) return fail(c, CL_E_INVALID, "max_rows_per_pass must be >= 128"); c->max_rows = value; return CL_OK; }
+  if (n == "gemm_ctas") { c->opt_gemm_ctas = (int)value; return CL_OK; }
+  if (n == "stage12_ctas") { c->opt_s12_ctas = (int)value; return CL_OK; }
+  return fail(c, CL_E_INVALID, "unknown option %s", name);
+}
+
+// ---- workspace ----
+static int ensure_rows(cl_ctx* c, int64_t rows) {
+  if (rows <= c->cap_rows) return CL_OK;
+  int64_t cap = std::max<int64_t>(rows, std::min<int64_t>(c->max_rows, std::max<int64_t>(1024, c->cap_rows * 2)));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (double** p : {&c->d_theta, &c->d_out, &c->d_R, &c->d_aux, &c->d_part, &c->d_part_u}) { if (*p) cudaFree(*p); *p = nullptr; }
+  c->cap_rows = 0;
+  CUDA_TRY(c, cudaMalloc(&c->d_theta, cap * CL_MAX_DIM * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_out, cap * 4 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_aux, cap * AUX_COUNT * sizeof(double)));
+  if (c->d_W) {
+    CUDA_TRY(c, cudaMalloc(&c->d_R, cap * c->ldR * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_part, cap * c->T * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_part_u, cap * c->T * sizeof(double)));
+  }
+  c->cap_rows = cap;
+  return CL_OK;
+}
+
+static int ensure_pinned(cl_ctx* c, int64_t theta_elems, int64_t out_elems) {
+  if (theta_elems > c->h_theta_cap) {
+    if (c->h_theta) cudaFreeHost(c->h_theta);
+    c->h_theta = nullptr; c->h_theta_cap = 0;
+    CUDA_TRY(c, cudaMallocHost(&c->h_theta, theta_elems * sizeof(double)));
+    c->h_theta_cap = theta_elems;
+  }
+  if (out_elems > c->h_out_cap) {
+    if (c->h_out) cudaFreeHost(c->h_out);
+    c->h_out = nullptr; c->h_out_cap = 0;
+    CUDA_TRY(c, cudaMallocHost(&c->h_out, out_elems * sizeof(double)));
+    c->h_out_cap = out_elems;
+  }
+  return CL_OK;
+}
+
+static int ensure_scratch(cl_ctx* c, int64_t bytes) {
+  if (bytes <= c->scratch_bytes) return CL_OK;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  c->d_scratch = nullptr; c->scratch_bytes = 0;
+  CUDA_TRY(c, cudaMalloc(&c->d_scratch, bytes));
+  c->scratch_bytes = bytes;
+  return CL_OK;
+}
+
+static int launch_s12(cl_ctx* c, const Stage12Args& a, cudaStream_t st) {
+  S12Kernel k = pick_s12(c->ds.family, c->ds.de_model);
+  int64_t want = c->opt_s12_ctas > 0 ? c->opt_s12_ctas : (int64_t)c->sm_count * 3 * 8;
+  int grid = (int)std::min<int64_t>(a.B, want);
+  k<<<grid, kS12Threads, sizeof(S12Smem), st>>>(c->ds, a);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  return CL_OK;
+}
+
+// one pass over `rows` device-resident parameter vectors: stage 1+2 -> stage 3 -> finalize
+static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, int what, double* d_out, double* d_comps,
+                    bool moments, cudaStream_t st, bool record) {
+  int rc = ensure_rows(c, rows);
+  if (rc != CL_OK) return rc;
+  const bool large = c->d_W != nullptr;
+  Stage12Args a{};
+  a.theta = d_theta; a.B = rows; a.ld = ld; a.mode = MODE_EVAL; a.what = moments ? CL_OUT_CHI2 : what;
+  a.R = c->d_R; a.ldR = c->ldR; a.aux = c->d_aux; a.zero_offset = moments ? 1 : 0;
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
+  rc = launch_s12(c, a, st);
+  if (rc != CL_OK) return rc;
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+  if (large) {
+    CUtensorMap tmR;
+    rc = make_tmap(c, &tmR, c->d_R, rows, c->ds.n_sn, c->ldR);
+    if (rc != CL_OK) return rc;
+    GemmArgs g{};
+    g.B = rows; g.N = c->ds.n_sn; g.T = c->T; g.n_rb = (int)((rows + kBM - 1) / kBM);
+    g.part = c->d_part; g.part_u = c->d_part_u; g.u = c->d_u;
+    int64_t items = (int64_t)g.n_rb * g.T;
+    int grid = (int)std::min<int64_t>(items, c->opt_gemm_ctas > 0 ? c->opt_gemm_ctas : c->sm_count);
+    if (moments) k_chi2_gemm<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
+    else k_chi2_gemm<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+  FinalizeArgs f{};
+  f.B = rows; f.what = what; f.n_part = c->T; f.sn_large = large ? 1 : 0;
+  f.part = c->d_part; f.aux = c->d_aux; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value;
+  k_finalize<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(f);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
+  return CL_OK;
+}
+
+static int check_eval_args(cl_ctx* c, const double* theta, int64_t B, int64_t ld, const void* out) {
+  if (!c) return CL_E_INVALID;
+  if (B < 0 || (B > 0 && (!theta || !out))) return fail(c, CL_E_INVALID, "NULL buffer");
+  if (ld < c->ds.ndim) return fail(c, CL_E_INVALID, "ld (%lld) < ndim (%d)", (long long)ld, c->ds.ndim);
+  return CL_OK;
+}
+
+extern "C" int cl_eval_device(cl_ctx* c, const double* d_theta, int64_t B, int64_t ld, int what, double* d_out, void* stream) {
+  int rc = check_eval_args(c, d_theta, B, ld, d_out);
+  if (rc != CL_OK || B == 0) return rc;
+  if (what < CL_OUT_CHI2 || what > CL_OUT_LOGPROB) return fail(c, CL_E_INVALID, "bad output selector");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
+    int64_t rows = std::min(c->max_rows, B - r0);
+    rc = run_pass(c, d_theta + r0 * ld, rows, ld, what, d_out + r0, nullptr, false, st, r0 == 0);
+    if (rc != CL_OK) return rc;
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+  c->timing_valid = true;
+  return CL_OK;
+}
+
+// host-memory evaluation with `width` outputs per row (1: out, 4: components, 3: moments)
+static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int what, double* out, int width, bool moments) {
+  int rc = check_eval_args(c, theta, B, ld, out);
+  if (rc != CL_OK || B == 0) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int nd = c->ds.ndim;
+  cudaStream_t st = c->stream;
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
+    int64_t rows = std::min(c->max_rows, B - r0);
+    rc = ensure_rows(c, rows);
+    if (rc != CL_OK) return rc;
+    rc = ensure_pinned(c, rows * nd, rows * 4);
+    if (rc != CL_OK) return rc;
+    if (r0 > 0) CUDA_TRY(c, cudaStreamSynchronize(st));  // staging buffers are reused
+    for (int64_t i = 0; i < rows; i++) memcpy(c->h_theta + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_theta, c->h_theta, rows * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* d_res = c->d_out;
+    if (width == 1) rc = run_pass(c, c->d_theta, rows, nd, what, d_res, nullptr, false, st, r0 == 0);
+    else if (width == 4) rc = run_pass(c, c->d_theta, rows, nd, CL_OUT_CHI2, nullptr, d_res, false, st, r0 == 0);
+    else rc = run_pass(c, c->d_theta, rows, nd, CL_OUT_CHI2, nullptr, nullptr, true, st, r0 == 0);
+    if (rc != CL_OK) return rc;
+    if (moments) {
+      // out[b] = (yy, yu, uu): reduce the partial planes on the host side of the ABI is avoided: reuse finalize
+      // (yy, yu, uu) from the SN partial planes alone
+      k_sum_parts<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(c->d_part, c->d_part_u, c->T, rows, c->uu, d_res);
+      c->launches++;
+      CUDA_TRY(c, cudaGetLastError());
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_out, d_res, rows * width * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    memcpy(out + r0 * width, c->h_out, rows * width * sizeof(double));
+  }
+  c->timing_valid = true;
+  return CL_OK;
+}
+
+extern "C" int cl_eval(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int what, double* out) {
+  if (what < CL_OUT_CHI2 || what > CL_OUT_LOGPROB) return fail(c, CL_E_INVALID, "bad output selector");
+  return eval_host(c, theta, B, ld, what, out, 1, false);
+}
+
+extern "C" int cl_eval_components(cl_ctx* c, const double* theta, int64_t B, int64_t ld, double* out) {
+  return eval_host(c, theta, B, ld, CL_OUT_CHI2, out, 4, false);
+}
+
+extern "C" int cl_eval_sn_moments(cl_ctx* c, const double* theta, int64_t B, int64_t ld, double* out) {
+  if (!c) return CL_E_INVALID;
+  if (!c->d_W || c->ds.col_offset < 0) return fail(c, CL_E_INVALID, "sn moments need a large SN block with an offset column");
+  return eval_host(c, theta, B, ld, CL_OUT_CHI2, out, 3, true);
+}
+
+// ---- helper exports: one stage-1/2 launch in a non-EVAL mode, results through pinned staging ----
+static int helper(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int mode, const double* zq, int64_t nq, double* o1, double* o2, int64_t width) {
+  int rc = check_eval_args(c, theta, B, ld, o1 ? o1 : o2);
+  if (rc != CL_OK || B == 0) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int nd = c->ds.ndim;
+  cudaStream_t st = c->stream;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, (64LL << 20) / std::max<int64_t>(8, width * 16)));
+  std::vector<double> hbuf;
+  for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+    int64_t rows = std::min(chunk, B - r0);
+    int64_t per = rows * width;
+    rc = ensure_scratch(c, (rows * nd + 2 * per + nq) * (int64_t)sizeof(double));
+    if (rc != CL_OK) return rc;
+    double* d_th = c->d_scratch;
+    double* d_o1 = d_th + rows * nd;
+    double* d_o2 = d_o1 + per;
+    double* d_zq = d_o2 + per;
+    hbuf.resize(rows * nd);
+    for (int64_t i = 0; i < rows; i++) memcpy(hbuf.data() + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
+    CUDA_TRY(c, cudaMemcpyAsync(d_th, hbuf.data(), rows * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nq > 0) CUDA_TRY(c, cudaMemcpyAsync(d_zq, zq, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+    Stage12Args a{};
+    a.theta = d_th; a.B = rows; a.ld = nd; a.mode = mode; a.what = CL_OUT_CHI2;
+    a.zq = d_zq; a.nq = (int)nq;
+    if (mode == MODE_DIST) { a.outDM = o1 ? d_o1 : nullptr; a.outDH = o2 ? d_o2 : nullptr; }
+    else if (mode == MODE_RESID) { a.R = d_o1; }
+    else a.out = d_o1;
+    rc = launch_s12(c, a, st);
+    if (rc != CL_OK) return rc;
+    if (o1) CUDA_TRY(c, cudaMemcpyAsync(o1 + r0 * width, d_o1, per * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (o2) CUDA_TRY(c, cudaMemcpyAsync(o2 + r0 * width, d_o2, per * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+  }
+  return CL_OK;
+}
+
+extern "C" int cl_distances(cl_ctx* c, const double* theta, int64_t B, int64_t ld, const double* zq, int64_t nq, double* DM, double* DH) {
+  if (!c) return CL_E_INVALID;
+  if (!c->ds.z_grid) return fail(c, CL_E_INVALID, "spec has no z_grid");
+  if (nq <= 0 || !zq || (!DM && !DH)) return fail(c, CL_E_INVALID, "bad query arguments");
+  return helper(c, theta, B, ld, MODE_DIST, zq, nq, DM, DH, nq);
+}
+extern "C" int cl_bao_theory(cl_ctx* c, const double* theta, int64_t B, int64_t ld, double* out) {
+  if (!c) return CL_E_INVALID;
+  if (c->ds.n_bao <= 0) return fail(c, CL_E_INVALID, "spec has no BAO block");
+  return helper(c, theta, B, ld, MODE_BAO, nullptr, 0, out, nullptr, c->ds.n_bao);
+}
+extern "C" int cl_cmb(cl_ctx* c, const double* theta, int64_t B, int64_t ld, double* out) {
+  if (!c) return CL_E_INVALID;
+  if (c->ds.family != CL_FAMILY_FULL) return fail(c, CL_E_INVALID, "CMB quantities need the FULL family");
+  return helper(c, theta, B, ld, MODE_CMB, nullptr, 0, out, nullptr, 8);
+}
+extern "C" int cl_sn_residuals(cl_ctx* c, const double* theta, int64_t B, int64_t ld, double* out) {
+  if (!c) return CL_E_INVALID;
+  if (c->ds.n_sn <= 0) return fail(c, CL_E_INVALID, "spec has no SN block");
+  return helper(c, theta, B, ld, MODE_RESID, nullptr, 0, out, nullptr, c->ds.n_sn);
+}
+
+extern "C" int cl_last_timing(cl_ctx* c, double ms[4]) {
+  if (!c || !ms) return CL_E_INVALID;
+  if (!c->timing_valid) return fail(c, CL_E_INVALID, "no evaluation has been timed yet");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaEventSynchronize(c->ev[5]));
+  float t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[1], c->ev[2])); ms[0] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[2], c->ev[3])); ms[1] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); ms[2] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[0], c->ev[5])); ms[3] = t;
+  return CL_OK;
+}

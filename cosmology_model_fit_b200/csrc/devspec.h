@@ -1,0 +1,70 @@
+// devspec.h — device-side view of one likelihood (a flattened cl_spec whose pointers are device pointers).
+// Passed to the kernels by value as a __grid_constant__ parameter.
+#pragma once
+#include <stdint.h>
+#include "../../include/cosmolike.h"
+
+namespace cosmolike {
+
+constexpr double kC_KMS = 299792.458;  // scipy.constants.c / 1000 (sn/pantheon.py:12)
+
+// aux planes written by the stage-1/2 kernel, [AUX_COUNT][B] (structure of arrays)
+enum { AUX_BAO = 0, AUX_CMB = 1, AUX_EXTRA = 2, AUX_CCNORM = 3, AUX_LOGPRIOR = 4, AUX_FLAGS = 5, AUX_SN_SMALL = 6, AUX_COUNT = 7 };
+enum { FLAG_GUARD = 1, FLAG_OUTSIDE = 2 };
+
+// what the stage-1/2 kernel produces
+enum { MODE_EVAL = 0, MODE_DIST = 1, MODE_BAO = 2, MODE_CMB = 3, MODE_RESID = 4 };
+
+struct DevSpec {
+  int ndim, family, de_model;
+  int col_H0, col_Om, Om_is_physical, col_obh2, col_och2, col_w0, col_wa;
+  double H0_fixed, H0_scale;
+  cl_cmb_consts k;
+  // z grid
+  const double* z_grid;
+  int G, grid_uniform;
+  double step;      // z_grid[i] == i*step bit-for-bit when grid_uniform (np.linspace from 0), except the last node
+  double z_last;    // z_grid[G-1] (np.linspace stores `stop` there exactly)
+  double inv_step;
+  // SN block
+  int n_sn, sn_small, sn_form, col_offset, n_vel, vel_mode, vel_pm1;
+  int col_vel[CL_MAX_VEL];
+  const double *sn_zcmb, *sn_zhelp1, *sn_obs, *sn_vel_w, *sn_mat_small;
+  double vel_scale;
+  // BAO block
+  int n_bao, dh_mode, rd_mode, col_rd;
+  const double *bao_z, *bao_val, *bao_W;
+  const int32_t* bao_qty;
+  double rd_fixed;
+  // CMB block
+  int cmb_mode, n_gl;
+  double cmb_prior[3], cmb_W[9];
+  const double *gl_x, *gl_w;
+  // CC block
+  int n_cc, col_fcc;
+  const double *cc_z, *cc_H, *cc_W;
+  double cc_logdet, cc_norm_sign;
+  // Gaussian terms, prior, guard
+  int n_gc, n_gp, has_bounds, guard_cpl;
+  int gc_col[CL_MAX_GAUSS], gp_col[CL_MAX_GAUSS];
+  double gc_mean[CL_MAX_GAUSS], gc_sigma[CL_MAX_GAUSS], gp_mean[CL_MAX_GAUSS], gp_sigma[CL_MAX_GAUSS];
+  double lo[CL_MAX_DIM], hi[CL_MAX_DIM];
+  double lp_norm, guard_value;
+};
+
+// arguments of one stage-1/2 launch
+struct Stage12Args {
+  const double* theta;  // [B][ld]
+  int64_t B, ld;
+  int mode, what;
+  int zero_offset;      // moments mode: residuals with the magnitude offset set to 0
+  double* R;            // MODE_EVAL: residual rows [B][ldR]; MODE_RESID: [B][n_sn]
+  int64_t ldR;
+  double* aux;          // [AUX_COUNT][B]
+  const double* zq;     // MODE_DIST query redshifts
+  int nq;
+  double *outDM, *outDH;  // MODE_DIST
+  double* out;            // MODE_BAO [B][n_bao], MODE_CMB [B][8]
+};
+
+}  // namespace cosmolike

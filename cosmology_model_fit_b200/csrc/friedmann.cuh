@@ -1,0 +1,525 @@
+// friedmann.cuh — stages 1 and 2 of the likelihood path, one CTA per parameter vector.
+//
+// Stage 1 (Friedmann distances): E(z) on the caller's z-grid, dh = c/H, cumulative trapezoid D_M with a
+//   block-wide scan, both kept in shared memory (reference: sn/pantheon.py:28-40, bao/desi_cmb_des5y.py:60-66);
+//   Gauss-Legendre D_M(z*) and r_s(z*) for the compressed CMB (cmb/data_planck_act_compression.py:160-197).
+// Stage 2 (residuals): Hermite / PCHIP interpolation to every SN and BAO redshift (interpolator.py:71-119),
+//   mu with the z_pec step correction (sn/pantheon.py:43-60), BAO ratios (bao/desi_cmb_union3.py:76-94),
+//   (R, l_A, omega_b), the small quadratic forms, priors and guards.  The SN residual row goes to HBM for the
+//   stage-3 chi-squared GEMM; everything else is reduced to a handful of scalars per theta.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "devspec.h"
+
+namespace cosmolike {
+
+constexpr int kS12Threads = 256;
+constexpr int kPPT = 16;  // grid points per thread: 256*16 = 4096 >= n_grid
+
+__host__ __device__ __forceinline__ int pad_idx(int i) { return i + ((i >> 4) << 1); }
+constexpr int kPaddedGrid = 4096 + (4096 / 16) * 2;
+
+struct Cosmo {
+  double H0, h, Om, Or, Obc, Onu, Ode, obh2, och2, w0, wa;
+};
+
+__device__ __forceinline__ void unpack(const DevSpec& s, const double* __restrict__ th, Cosmo& c) {
+  c.H0 = s.col_H0 >= 0 ? s.H0_scale * th[s.col_H0] : s.H0_fixed;
+  c.h = c.H0 / 100;
+  c.w0 = s.col_w0 >= 0 ? th[s.col_w0] : -1.0;
+  c.wa = s.col_wa >= 0 ? th[s.col_wa] : 0.0;
+  c.Om = c.Or = c.Obc = c.Onu = c.Ode = c.obh2 = c.och2 = 0.0;
+  if (s.family == CL_FAMILY_LATE) {
+    c.Om = th[s.col_Om];
+    if (s.Om_is_physical) c.Om = c.Om / (c.h * c.h);
+    if (s.col_obh2 >= 0) c.obh2 = th[s.col_obh2];
+  } else {
+    double h2 = c.h * c.h;
+    c.obh2 = th[s.col_obh2];
+    c.och2 = th[s.col_och2];
+    c.Onu = s.k.Omnu_h2 / h2;
+    c.Or = s.k.Or_h2 / h2;
+    c.Obc = (c.obh2 + c.och2) / h2;
+    c.Ode = 1.0 - c.Obc - c.Or - c.Onu;
+  }
+}
+
+// 5-node massive-neutrino density (cmb/data_planck_act_compression.py:53-66)
+__device__ __forceinline__ double omnu_z(const cl_cmb_consts& k, double zp1) {
+  double r = k.nu_m0 / zp1;
+  double mz = r * r;
+  double f0 = sqrt(k.nu_q2[0] + mz), f1 = sqrt(k.nu_q2[1] + mz), f2 = sqrt(k.nu_q2[2] + mz);
+  double f3 = sqrt(k.nu_q2[3] + mz), f4 = sqrt(k.nu_q2[4] + mz);
+  double ws = f0 * k.nu_w[0] + f1 * k.nu_w[1] + f2 * k.nu_w[2] + f3 * k.nu_w[3] + f4 * k.nu_w[4];
+  double z2 = zp1 * zp1;
+  return z2 * z2 * ws / k.nu_rho0;
+}
+
+template <int DE>
+__device__ __forceinline__ double fde(const Cosmo& c, double z, double zp1, double cubed) {
+  if (DE == CL_DE_WCDM) return pow(zp1, 3 * (1.0 + c.w0));
+  if (DE == CL_DE_CPL) return pow(zp1, 3 * (1 + c.w0 + c.wa)) * exp(-3 * c.wa * z / zp1);
+  if (DE == CL_DE_THAWING) {
+    double q = 2 * cubed / ((1.0 + c.w0) + (1.0 - c.w0) * cubed);
+    return q * q;
+  }
+  return 1.0;
+}
+
+// H(z) (sn/pantheon.py:28-31 late family, bao/desi_cmb_union3.py:37-57 full family)
+template <int FAM, int DE>
+__device__ __forceinline__ double H_of_z(const DevSpec& s, const Cosmo& c, double z) {
+  double zp1 = 1.0 + z;
+  double cubed = zp1 * zp1 * zp1;
+  if (FAM == CL_FAMILY_LATE) {
+    double de = (DE == CL_DE_LCDM) ? (1.0 - c.Om) : (1.0 - c.Om) * fde<DE>(c, z, zp1, cubed);
+    return c.H0 * sqrt(c.Om * cubed + de);
+  }
+  double radiation = c.Or * (cubed * zp1);
+  double matter = c.Obc * cubed;
+  double neutrino = c.Onu * omnu_z(s.k, zp1);
+  double de = (DE == CL_DE_LCDM) ? c.Ode : c.Ode * fde<DE>(c, z, zp1, cubed);
+  return c.H0 * sqrt(radiation + matter + de + neutrino);
+}
+
+__device__ __forceinline__ double grid_z(const DevSpec& s, int i) {
+  if (s.grid_uniform) return i == s.G - 1 ? s.z_last : (double)i * s.step;
+  return __ldg(s.z_grid + i);
+}
+
+// index i with x[i] < xq <= x[i+1]  (np.searchsorted(x, xq) - 1, interpolator.py:94); caller excluded the ends
+__device__ __forceinline__ int find_interval(const DevSpec& s, double xq) {
+  const int G = s.G;
+  if (s.grid_uniform) {
+    int i = (int)(xq * s.inv_step);
+    i = max(0, min(i, G - 2));
+    while (i > 0 && grid_z(s, i) >= xq) --i;
+    while (i < G - 2 && grid_z(s, i + 1) < xq) ++i;
+    return i;
+  }
+  int lo = 0, hi = G;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(s.z_grid + mid) < xq) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+// cubic Hermite with analytic node derivatives y' = dh (interp_hermite, interpolator.py:71-108,117-119)
+__device__ __forceinline__ double hermite_dm(const DevSpec& s, const double* __restrict__ s_cum,
+                                             const double* __restrict__ s_dh, double xq) {
+  const int G = s.G;
+  double x0 = grid_z(s, 0), xn = grid_z(s, G - 1);
+  if (xq <= x0) return s_cum[0] + s_dh[0] * (xq - x0);
+  if (xq >= xn) return s_cum[pad_idx(G - 1)] + s_dh[pad_idx(G - 1)] * (xq - xn);
+  int i = find_interval(s, xq);
+  double xi = grid_z(s, i);
+  double h_i = grid_z(s, i + 1) - xi;
+  double t = (xq - xi) / h_i;
+  double t2 = t * t, t3 = t2 * t;
+  double h00 = 2 * t3 - 3 * t2 + 1;
+  double h10 = t3 - 2 * t2 + t;
+  double h01 = -2 * t3 + 3 * t2;
+  double h11 = t3 - t2;
+  int p0 = pad_idx(i), p1 = pad_idx(i + 1);
+  return h00 * s_cum[p0] + h10 * h_i * s_dh[p0] + h01 * s_cum[p1] + h11 * h_i * s_dh[p1];
+}
+
+__device__ __forceinline__ double sgn(double v) { return (double)((v > 0) - (v < 0)); }
+
+// Fritsch-Carlson slope at node j of (z_grid, dh_grid) (_pchip_slopes, interpolator.py:5-68); local stencil
+__device__ double pchip_slope(const DevSpec& s, const double* __restrict__ y, int j) {
+  const int n = s.G;
+  auto H = [&](int i) { return grid_z(s, i + 1) - grid_z(s, i); };
+  auto D = [&](int i) { return (y[pad_idx(i + 1)] - y[pad_idx(i)]) / H(i); };
+  if (j == 0) {
+    double h0 = H(0), h1 = H(1), d0 = D(0), d1 = D(1);
+    double v = ((2 * h0 + h1) * d0 - h0 * d1) / (h0 + h1);
+    if (d0 == 0.0 || sgn(v) != sgn(d0)) return 0.0;
+    if (sgn(d0) != sgn(d1) && fabs(v) > fabs(3 * d0)) return 3 * d0;
+    return v;
+  }
+  if (j == n - 1) {
+    double h2 = H(n - 2), h3 = H(n - 3), d2 = D(n - 2), d3 = D(n - 3);
+    double v = ((2 * h2 + h3) * d2 - h2 * d3) / (h2 + h3);
+    if (d2 == 0.0 || sgn(v) != sgn(d2)) return 0.0;
+    if (sgn(d2) != sgn(d3) && fabs(v) > fabs(3 * d2)) return 3 * d2;
+    return v;
+  }
+  double dm1 = D(j - 1), di = D(j), hm1 = H(j - 1), hi = H(j);
+  if (dm1 != 0.0 && di != 0.0 && dm1 * di > 0.0) {
+    double w1 = 2.0 * hi + hm1, w2 = hi + 2.0 * hm1;
+    return (w1 + w2) / (w1 / dm1 + w2 / di);
+  }
+  return 0.0;
+}
+
+// interp_pchip(xq, z_grid, dh_grid) (interpolator.py:111-114): clamps outside the grid
+__device__ double pchip_dh(const DevSpec& s, const double* __restrict__ s_dh, double xq) {
+  const int G = s.G;
+  if (xq <= grid_z(s, 0)) return s_dh[0];
+  if (xq >= grid_z(s, G - 1)) return s_dh[pad_idx(G - 1)];
+  int i = find_interval(s, xq);
+  double xi = grid_z(s, i);
+  double h_i = grid_z(s, i + 1) - xi;
+  double t = (xq - xi) / h_i;
+  double t2 = t * t, t3 = t2 * t;
+  double h00 = 2 * t3 - 3 * t2 + 1, h10 = t3 - 2 * t2 + t, h01 = -2 * t3 + 3 * t2, h11 = t3 - t2;
+  double d0 = pchip_slope(s, s_dh, i), d1 = pchip_slope(s, s_dh, i + 1);
+  return h00 * s_dh[pad_idx(i)] + h10 * h_i * d0 + h01 * s_dh[pad_idx(i + 1)] + h11 * h_i * d1;
+}
+
+// closed-form fits (cmb/data_planck_act_compression.py:86-124)
+__device__ double z_star_fit(const cl_cmb_consts& k, double wb, double wm) {
+  wb = pow(wb, k.zstar_b);
+  wm = pow(wm, k.zstar_m);
+  return pow(wm, -0.7316314841257655) +
+         k.zstar_s1 * 391.6723594873167 * pow(wb, 0.9368102670600895) * pow(wm, -0.35300106475765136) +
+         k.zstar_s2 * 937.4224935298015 * pow(wm, 0.0192950634264157) * pow(wb, -0.04285000485853785);
+}
+__device__ double r_drag_fit(const cl_cmb_consts& k, double wb, double wm) {
+  wb = pow(wb, k.rdrag_b);
+  wm = pow(wm, k.rdrag_m);
+  const double a1 = 0.00257366, a2 = 0.05032, a3 = 0.013, a4 = 0.7720642, a5 = 0.24346362, a6 = 0.00641072,
+               a7 = 0.5350899, a8 = 32.7525, a9 = 0.315473;
+  double den = (a1 * pow(wb, a2)) + (a3 * pow(wb, a4) * pow(wm, a5)) + (a6 * pow(wm, a7));
+  return 1.0 / den - a8 / pow(wm, a9);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sums of NV values (fixed order -> deterministic); result valid in every thread
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*8] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    double w = warp_sum(v[q]);
+    if (lane == 0) s_red[q * 8 + warp] = w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < kS12Threads / 32; w++) a += s_red[q * 8 + w];
+    v[q] = a;
+  }
+  __syncthreads();
+}
+
+struct S12Smem {
+  double cum[kPaddedGrid];
+  double dh[kPaddedGrid];
+  double wsum[8];
+  double red[5 * 8];
+  double vec[CL_MAX_BAO + CL_MAX_CC + CL_SN_SMALL_MAX];
+  double scal[4];  // z*, r_drag
+};
+
+template <int FAM, int DE>
+__global__ void __launch_bounds__(kS12Threads, 3)
+k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__ Stage12Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = s.G;
+
+  for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const double* __restrict__ th = a.theta + b * a.ld;
+    Cosmo c;
+    unpack(s, th, c);
+
+    // ---- prior box / guard: rows that the reference never evaluates (sn/pantheon.py:80-92) ----
+    double lp = 0.0;
+    int flags = 0;
+    if (a.mode == MODE_EVAL) {
+      if (a.what == CL_OUT_LOGPROB) {
+        if (s.has_bounds)
+          for (int j = 0; j < s.ndim; j++)
+            if (!(s.lo[j] < th[j] && th[j] < s.hi[j])) flags |= FLAG_OUTSIDE;
+        lp = s.lp_norm;
+        for (int g = 0; g < s.n_gp; g++) {
+          double r = th[s.gp_col[g]] - s.gp_mean[g];
+          lp += -0.5 * (r * r) / (s.gp_sigma[g] * s.gp_sigma[g]);
+        }
+      }
+      if (s.guard_cpl && DE == CL_DE_CPL && c.w0 + c.wa >= 0.0 && a.what != CL_OUT_CHI2) flags |= FLAG_GUARD;
+      if (flags) {  // uniform across the CTA
+        if (tid == 0) {
+          a.aux[AUX_FLAGS * a.B + b] = (double)flags;
+          a.aux[AUX_LOGPRIOR * a.B + b] = lp;
+        }
+        continue;
+      }
+    }
+
+    const bool need_grid = (a.mode == MODE_EVAL && (s.n_sn > 0 || s.n_bao > 0)) || a.mode == MODE_DIST ||
+                           a.mode == MODE_BAO || a.mode == MODE_RESID;
+    const bool need_cmb = (a.mode == MODE_EVAL && s.cmb_mode != CL_CMB_NONE) || a.mode == MODE_CMB;
+    const bool need_rd = s.rd_mode == CL_RD_FIT && ((a.mode == MODE_EVAL && s.n_bao > 0) || a.mode == MODE_BAO || a.mode == MODE_CMB);
+
+    // ================= stage 1: dh = c/H on the grid, cumulative trapezoid =================
+    double dh[kPPT];
+    const int i0 = tid * kPPT;
+    if (need_grid) {
+#pragma unroll
+      for (int k = 0; k < kPPT; k++) {
+        int i = i0 + k;
+        dh[k] = (i < G) ? kC_KMS / H_of_z<FAM, DE>(s, c, grid_z(s, i)) : 0.0;
+      }
+      if (i0 < G) {
+        double2* dst = reinterpret_cast<double2*>(&sm.dh[pad_idx(i0)]);
+#pragma unroll
+        for (int k = 0; k < kPPT / 2; k++) dst[k] = make_double2(dh[2 * k], dh[2 * k + 1]);
+      }
+    }
+    // scalar fits run on the last thread while the others finish their grid points
+    if (tid == kS12Threads - 1 && (need_cmb || need_rd)) {
+      double obh2 = c.obh2;
+      double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
+      sm.scal[0] = need_cmb ? z_star_fit(s.k, obh2, wm) : 0.0;
+      sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
+    }
+    __syncthreads();
+
+    if (need_grid) {
+      double nxt = (i0 + kPPT < G) ? sm.dh[pad_idx(i0 + kPPT)] : 0.0;
+      double pre[kPPT];
+      double run = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPPT; k++) {
+        int i = i0 + k;
+        pre[k] = run;
+        double d1 = (k + 1 < kPPT) ? dh[(k + 1) % kPPT] : nxt;
+        if (i + 1 < G) {
+          double dz = grid_z(s, i + 1) - grid_z(s, i);
+          run += ((dh[k] + d1) / 2) * dz;
+        }
+      }
+      // block-exclusive scan of the per-thread totals
+      double inc = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) sm.wsum[warp] = inc;
+      __syncthreads();
+      double off = inc - run;
+      for (int w = 0; w < warp; w++) off += sm.wsum[w];
+      if (i0 < G) {
+        double2* dst = reinterpret_cast<double2*>(&sm.cum[pad_idx(i0)]);
+#pragma unroll
+        for (int k = 0; k < kPPT / 2; k++) dst[k] = make_double2(off + pre[2 * k], off + pre[2 * k + 1]);
+      }
+      __syncthreads();
+    }
+
+    // ================= helper outputs =================
+    if (a.mode == MODE_DIST) {
+      for (int q = tid; q < a.nq; q += kS12Threads) {
+        double z = a.zq[q];
+        if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.cum, sm.dh, z);
+        if (a.outDH) a.outDH[b * a.nq + q] = kC_KMS / H_of_z<FAM, DE>(s, c, z);
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ================= stage 2: residuals =================
+    const int n_sn = s.n_sn;
+    if ((a.mode == MODE_EVAL || a.mode == MODE_RESID) && n_sn > 0) {
+      const double offset = (s.col_offset >= 0 && !a.zero_offset) ? th[s.col_offset] : 0.0;
+      double vamp[CL_MAX_VEL];
+#pragma unroll
+      for (int k = 0; k < CL_MAX_VEL; k++) vamp[k] = k < s.n_vel ? s.vel_scale * th[s.col_vel[k]] : 0.0;
+      const int64_t ld = a.mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
+      double* __restrict__ Rrow = a.R + b * ld;
+      for (int i = tid; i < n_sn; i += kS12Threads) {
+        double zq = __ldg(s.sn_zcmb + i);
+        if (s.n_vel > 0) {
+          // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)): D_M(z_cmb) cancels
+          double v_km_s = 0.0;
+          for (int k = 0; k < s.n_vel; k++) v_km_s += vamp[k] * __ldg(s.sn_vel_w + (size_t)k * n_sn + i);
+          double z_pec = v_km_s / kC_KMS;
+          if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + zq) / (1.0 + z_pec);
+          else zq = fmax((1.0 + zq) * (1.0 + z_pec) - 1.0, 1e-8);
+        }
+        double DM = hermite_dm(s, sm.cum, sm.dh, zq);
+        double mu = 25.0 + 5 * log10(__ldg(s.sn_zhelp1 + i) * DM);
+        double d = __ldg(s.sn_obs + i) - offset - mu;
+        if (s.sn_small && a.mode == MODE_EVAL) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d;
+        else Rrow[i] = d;
+      }
+    }
+    if (a.mode == MODE_RESID) { __syncthreads(); continue; }
+
+    // BAO theory (bao_theory, bao/desi_cmb_union3.py:76-94 / bao/desi_cmb_pantheon.py:85-99)
+    const bool do_bao = (a.mode == MODE_EVAL || a.mode == MODE_BAO) && s.n_bao > 0;
+    if (do_bao && tid < s.n_bao) {
+      double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : sm.scal[1]);
+      double z = __ldg(s.bao_z + tid);
+      double DM = hermite_dm(s, sm.cum, sm.dh, z);
+      double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.dh, z) : kC_KMS / H_of_z<FAM, DE>(s, c, z);
+      int q = __ldg(s.bao_qty + tid);
+      double v;
+      if (q == CL_BAO_DV_OVER_RS) v = pow(z * DH * (DM * DM), 1.0 / 3) / rd;
+      else if (q == CL_BAO_DM_OVER_RS) v = DM / rd;
+      else if (q == CL_BAO_DH_OVER_RS) v = DH / rd;
+      else v = DM / DH;
+      if (a.mode == MODE_BAO) a.out[b * s.n_bao + tid] = v;
+      else sm.vec[tid] = __ldg(s.bao_val + tid) - v;
+    }
+    if (a.mode == MODE_BAO) { __syncthreads(); continue; }
+
+    // cosmic chronometers (ohd/cc.py:22-26)
+    if (a.mode == MODE_EVAL && tid < s.n_cc)
+      sm.vec[CL_MAX_BAO + tid] = __ldg(s.cc_H + tid) - H_of_z<FAM, DE>(s, c, __ldg(s.cc_z + tid));
+
+    // Gauss-Legendre integrands (cmb/data_planck_act_compression.py:160-197): thread q < n_gl -> D_M node,
+    // n_gl <= q < 2 n_gl -> r_s node (in scale factor)
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double zstar = 0.0;
+    if (need_cmb) {
+      zstar = sm.scal[0];
+      if (tid < s.n_gl) {
+        double hw = zstar / 2.0;
+        double z = hw * __ldg(s.gl_x + tid) + hw;
+        v[0] = __ldg(s.gl_w + tid) * (kC_KMS / H_of_z<FAM, DE>(s, c, z));
+      } else if (tid < 2 * s.n_gl) {
+        int q = tid - s.n_gl;
+        double a_lim = 1.0 / (1.0 + zstar);
+        double hw = a_lim / 2.0;
+        double av = hw * __ldg(s.gl_x + q) + hw;
+        double z = (1.0 / av) - 1.0;
+        double Rb = (3.0 / 4.0) * (c.obh2 / s.k.Ogamma_h2) * av;
+        v[1] = __ldg(s.gl_w + q) * (kC_KMS / (av * av * H_of_z<FAM, DE>(s, c, z) * sqrt(3.0 * (1.0 + Rb))));
+      }
+    }
+    __syncthreads();  // sm.vec complete
+
+    if (a.mode == MODE_EVAL) {
+      if (tid < s.n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
+        double t = 0.0;
+        for (int i = 0; i < s.n_bao; i++) t += sm.vec[i] * __ldg(s.bao_W + i * s.n_bao + tid);
+        v[2] = t * sm.vec[tid];
+      }
+      if (tid < s.n_cc) {
+        const double* d = sm.vec + CL_MAX_BAO;
+        double t = 0.0;
+        for (int i = 0; i < s.n_cc; i++) t += d[i] * __ldg(s.cc_W + i * s.n_cc + tid);
+        v[3] = t * d[tid];
+      }
+      if (s.sn_small && tid < n_sn) {
+        const double* d = sm.vec + CL_MAX_BAO + CL_MAX_CC;
+        double t = 0.0;
+        if (s.sn_form == CL_SN_INVCOV) {  // delta @ inv_cov @ delta (sn/union3_1.py:57)
+          for (int i = 0; i < n_sn; i++) t += d[i] * __ldg(s.sn_mat_small + i * n_sn + tid);
+          v[4] = t * d[tid];
+        } else {  // |L^-1 delta|^2 with W = L^-1 (solve_triangular.py:5-14)
+          for (int i = 0; i <= tid; i++) t += __ldg(s.sn_mat_small + tid * n_sn + i) * d[i];
+          v[4] = t * t;
+        }
+      }
+    }
+    block_sum<5>(v, sm.red);
+
+    if (tid == 0) {
+      double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
+      if (need_cmb) {
+        dm = (zstar / 2.0) * v[0];
+        rs = ((1.0 / (1.0 + zstar)) / 2.0) * v[1];
+        double Om_h2 = c.och2 + c.obh2 + s.k.Omnu_h2;
+        if (s.cmb_mode == CL_CMB_THETA_WB_WM) { cmbv[0] = rs / dm; cmbv[1] = c.obh2; cmbv[2] = Om_h2; }
+        else { cmbv[0] = 100 * sqrt(Om_h2) * dm / kC_KMS; cmbv[1] = M_PI * dm / rs; cmbv[2] = c.obh2; }
+      }
+      if (a.mode == MODE_CMB) {
+        double* r = a.out + b * 8;
+        r[0] = cmbv[0]; r[1] = cmbv[1]; r[2] = cmbv[2]; r[3] = zstar; r[4] = rs; r[5] = dm;
+        r[6] = need_rd ? sm.scal[1] : 0.0; r[7] = 100 * (rs / dm);
+      } else {
+        double chi2_cmb = 0.0;
+        if (s.cmb_mode != CL_CMB_NONE) {
+          double d[3] = {s.cmb_prior[0] - cmbv[0], s.cmb_prior[1] - cmbv[1], s.cmb_prior[2] - cmbv[2]};
+          for (int j = 0; j < 3; j++) {
+            double t = 0.0;
+            for (int i = 0; i < 3; i++) t += d[i] * s.cmb_W[i * 3 + j];
+            chi2_cmb += t * d[j];
+          }
+        }
+        double extra = 0.0, ccnorm = 0.0;
+        if (s.n_cc > 0) {
+          double f = s.col_fcc >= 0 ? th[s.col_fcc] : 1.0;
+          extra += f * f * v[3];
+          if (s.cc_norm_sign != 0.0) ccnorm = s.n_cc * log(2 * M_PI) + s.cc_logdet - s.cc_norm_sign * 2 * s.n_cc * log(f);
+        }
+        for (int g = 0; g < s.n_gc; g++) {
+          double r = (th[s.gc_col[g]] - s.gc_mean[g]) / s.gc_sigma[g];
+          extra += r * r;
+        }
+        a.aux[AUX_BAO * a.B + b] = v[2];
+        a.aux[AUX_CMB * a.B + b] = chi2_cmb;
+        a.aux[AUX_EXTRA * a.B + b] = extra;
+        a.aux[AUX_CCNORM * a.B + b] = ccnorm;
+        a.aux[AUX_LOGPRIOR * a.B + b] = lp;
+        a.aux[AUX_FLAGS * a.B + b] = 0.0;
+        a.aux[AUX_SN_SMALL * a.B + b] = v[4];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- finalize: combine the SN chi2 partials of stage 3 with the scalar terms ----
+struct FinalizeArgs {
+  int64_t B;
+  int what, n_part, sn_large;
+  const double* part;  // [n_part][B] per-column-tile partial sums of |W r|^2
+  const double* aux;   // [AUX_COUNT][B]
+  double* out;         // [B]
+  double* comps;       // nullable [B][4]
+  double guard_value;
+};
+
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FinalizeArgs f) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= f.B) return;
+  int flags = (int)f.aux[AUX_FLAGS * f.B + b];
+  double lp = f.aux[AUX_LOGPRIOR * f.B + b];
+  if (flags) {
+    double r = (flags & FLAG_OUTSIDE) ? -INFINITY : (f.what == CL_OUT_LOGPROB ? lp + f.guard_value : f.guard_value);
+    if (f.out) f.out[b] = r;
+    if (f.comps) for (int j = 0; j < 4; j++) f.comps[b * 4 + j] = NAN;
+    return;
+  }
+  double sn = 0.0;
+  if (f.sn_large) for (int t = 0; t < f.n_part; t++) sn += f.part[(int64_t)t * f.B + b];
+  else sn = f.aux[AUX_SN_SMALL * f.B + b];
+  double bao = f.aux[AUX_BAO * f.B + b], cmb = f.aux[AUX_CMB * f.B + b], extra = f.aux[AUX_EXTRA * f.B + b];
+  if (f.comps) { f.comps[b * 4] = sn; f.comps[b * 4 + 1] = bao; f.comps[b * 4 + 2] = cmb; f.comps[b * 4 + 3] = extra; }
+  if (!f.out) return;
+  double chi2 = sn + bao + cmb + extra;
+  if (f.what == CL_OUT_CHI2) f.out[b] = chi2;
+  else {
+    double ll = -0.5 * (chi2 + f.aux[AUX_CCNORM * f.B + b]);
+    f.out[b] = f.what == CL_OUT_LOGLIKE ? ll : lp + ll;
+  }
+}
+
+// moments mode: out[b] = (y.y, y.u, u.u)
+__global__ void __launch_bounds__(256) k_sum_parts(const double* __restrict__ part, const double* __restrict__ part_u, int T,
+                                                   int64_t B, double uu, double* __restrict__ out) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double yy = 0.0, yu = 0.0;
+  for (int t = 0; t < T; t++) { yy += part[(int64_t)t * B + b]; yu += part_u[(int64_t)t * B + b]; }
+  out[b * 3] = yy; out[b * 3 + 1] = yu; out[b * 3 + 2] = uu;
+}
+
+}  // namespace cosmolike

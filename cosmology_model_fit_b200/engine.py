@@ -1,7 +1,227 @@
-"""placeholder"""
+"""ctypes binding of libcosmolike_b200.so — the host-side mirror of the reference's per-script callables.
+
+`Engine(spec)` exposes, for one `LikelihoodSpec`, the names every reference fit script defines at module level:
+`chi_squared(theta)`, `log_likelihood(theta)`, `log_probability(theta)` (sn/pantheon.py:57-97) and the batch
+form `log_probs_vectorized(batch)` (bao/desi.py:100-106), plus the helper exports their `main()`s use
+(`DM_z`, `DH_z`, `bao_theory`, `cmb_distances`).  A 1-D theta returns a Python float like the reference's
+scalar functions; a 2-D batch returns an ndarray.
+
+There is no CPU fallback: if the shared library is missing or no sm_100 GPU is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .spec import ClSpec, LikelihoodSpec, OUT_CHI2, OUT_LOGLIKE, OUT_LOGPROB
+
+_dp = C.POINTER(C.c_double)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libcosmolike_b200.so"
+
+#: every symbol include/cosmolike.h declares
+ABI_SYMBOLS = (
+    "cl_create", "cl_destroy", "cl_last_error", "cl_eval", "cl_eval_device", "cl_eval_components",
+    "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
+    "cl_launch_count", "cl_set_option", "cl_describe",
+)
+
+
 class EngineError(RuntimeError):
     pass
-class Engine:
-    pass
+
+
 def library_path():
-    return None
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library (built by cosmology_model_fit_b200/build.py or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise EngineError(f"{path} not found: run `python -m cosmology_model_fit_b200.build` (needs nvcc); "
+                          "there is no CPU fallback")
+    lib = C.CDLL(path)
+    sp, ctxp, i64 = C.POINTER(ClSpec), C.c_void_p, C.c_int64
+    lib.cl_create.argtypes = [sp, C.c_int, C.POINTER(ctxp)]
+    lib.cl_destroy.argtypes = [ctxp]
+    lib.cl_last_error.argtypes = [ctxp]
+    lib.cl_last_error.restype = C.c_char_p
+    lib.cl_describe.argtypes = [ctxp]
+    lib.cl_describe.restype = C.c_char_p
+    lib.cl_eval.argtypes = [ctxp, _dp, i64, i64, C.c_int, _dp]
+    lib.cl_eval_device.argtypes = [ctxp, C.c_void_p, i64, i64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cl_eval_components.argtypes = [ctxp, _dp, i64, i64, _dp]
+    lib.cl_eval_sn_moments.argtypes = [ctxp, _dp, i64, i64, _dp]
+    lib.cl_distances.argtypes = [ctxp, _dp, i64, i64, _dp, i64, _dp, _dp]
+    lib.cl_bao_theory.argtypes = [ctxp, _dp, i64, i64, _dp]
+    lib.cl_cmb.argtypes = [ctxp, _dp, i64, i64, _dp]
+    lib.cl_sn_residuals.argtypes = [ctxp, _dp, i64, i64, _dp]
+    lib.cl_last_timing.argtypes = [ctxp, C.c_double * 4]
+    lib.cl_launch_count.argtypes = [ctxp]
+    lib.cl_launch_count.restype = i64
+    lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Engine:
+    """One likelihood on one GPU (one process per GPU; see parallel.py for the sharded form)."""
+
+    def __init__(self, spec: LikelihoodSpec, device: int = 0):
+        self.lib = load_library()
+        self.spec = spec
+        self._c_spec = spec.c_spec()
+        self._ctx = C.c_void_p()
+        rc = self.lib.cl_create(C.byref(self._c_spec), int(device), C.byref(self._ctx))
+        if rc != 0:
+            msg = self.lib.cl_last_error(None)
+            self._ctx = C.c_void_p()
+            raise EngineError(f"cl_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.ndim = spec.ndim
+        self.device = device
+
+    # -- lifetime ---------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.cl_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.cl_last_error(self._ctx)
+            raise EngineError(f"cosmolike error {rc}: {msg.decode() if msg else ''}")
+
+    def describe(self):
+        return self.lib.cl_describe(self._ctx).decode()
+
+    def set_option(self, name, value):
+        self._check(self.lib.cl_set_option(self._ctx, name.encode(), int(value)))
+
+    # -- evaluation -------------------------------------------------------------------------------------------
+    def _theta(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        scalar = t.ndim == 1
+        t = np.ascontiguousarray(np.atleast_2d(t))
+        if t.ndim != 2 or t.shape[1] != self.ndim:
+            raise ValueError(f"theta must have shape ({self.ndim},) or (B, {self.ndim})")
+        return t, scalar
+
+    def _eval(self, theta, what):
+        t, scalar = self._theta(theta)
+        out = np.empty(t.shape[0], dtype=np.float64)
+        self._check(self.lib.cl_eval(self._ctx, _p(t), t.shape[0], t.shape[1], what, _p(out)))
+        return float(out[0]) if scalar else out
+
+    def chi_squared(self, theta):
+        """chi_squared(params) (sn/pantheon.py:57-61)"""
+        return self._eval(theta, OUT_CHI2)
+
+    def log_likelihood(self, theta):
+        """log_likelihood(params) (sn/pantheon.py:64-65; guard of bao/desi_fs_lya_cmb.py:117-121)"""
+        return self._eval(theta, OUT_LOGLIKE)
+
+    def log_probability(self, theta):
+        """log_probability(params): -inf outside the prior box (sn/pantheon.py:88-97)"""
+        return self._eval(theta, OUT_LOGPROB)
+
+    def log_probs_vectorized(self, batch, dtype=np.float32):
+        """Batch log-probability for emcee(vectorize=True); float32 like bao/desi.py:100-106 unless dtype says
+        otherwise."""
+        return np.asarray(self._eval(np.atleast_2d(batch), OUT_LOGPROB)).astype(dtype, copy=False)
+
+    def log_likelihood_vectorized(self, batch, dtype=np.float32):
+        """Batch log-likelihood for nautilus(vectorized=True) (bao/desi_union3_cc_theta_star.py:142-147)."""
+        return np.asarray(self._eval(np.atleast_2d(batch), OUT_LOGLIKE)).astype(dtype, copy=False)
+
+    def components(self, theta):
+        """chi2 split as (sn, bao, cmb, cc+gaussian) (bao/desi_cmb_union3.py:97-135)"""
+        t, scalar = self._theta(theta)
+        out = np.empty((t.shape[0], 4))
+        self._check(self.lib.cl_eval_components(self._ctx, _p(t), t.shape[0], t.shape[1], _p(out)))
+        return out[0] if scalar else out
+
+    def sn_moments(self, theta):
+        """(y.y, y.u, u.u) for the analytic treatment of the magnitude offset."""
+        t, scalar = self._theta(theta)
+        out = np.empty((t.shape[0], 3))
+        self._check(self.lib.cl_eval_sn_moments(self._ctx, _p(t), t.shape[0], t.shape[1], _p(out)))
+        return out[0] if scalar else out
+
+    def eval_device(self, d_theta: int, B: int, ld: int, what: int, d_out: int, stream: int = 0):
+        """Asynchronous evaluation on raw device pointers (ints), e.g. torch tensors' data_ptr()."""
+        self._check(self.lib.cl_eval_device(self._ctx, C.c_void_p(d_theta), B, ld, what, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    # -- helper exports ---------------------------------------------------------------------------------------
+    def distances(self, theta, zq):
+        t, scalar = self._theta(theta)
+        zq = np.ascontiguousarray(np.atleast_1d(zq), dtype=np.float64)
+        dm = np.empty((t.shape[0], zq.size)); dh = np.empty((t.shape[0], zq.size))
+        self._check(self.lib.cl_distances(self._ctx, _p(t), t.shape[0], t.shape[1], _p(zq), zq.size, _p(dm), _p(dh)))
+        return (dm[0], dh[0]) if scalar else (dm, dh)
+
+    def DM_z(self, z, theta):
+        """DM_z(z, params): trapezoid grid + Hermite (bao/desi_cmb_pantheon.py:66-72)"""
+        return self.distances(theta, z)[0]
+
+    def DH_z(self, z, theta):
+        """DH_z(z, params) = c / H(z) (bao/desi_cmb_pantheon.py:61-63)"""
+        return self.distances(theta, z)[1]
+
+    def bao_theory(self, theta):
+        t, scalar = self._theta(theta)
+        out = np.empty((t.shape[0], self._c_spec.n_bao))
+        self._check(self.lib.cl_bao_theory(self._ctx, _p(t), t.shape[0], t.shape[1], _p(out)))
+        return out[0] if scalar else out
+
+    def cmb(self, theta):
+        """(v0, v1, v2, z*, r_s*, D_M*, r_drag, 100 theta*)"""
+        t, scalar = self._theta(theta)
+        out = np.empty((t.shape[0], 8))
+        self._check(self.lib.cl_cmb(self._ctx, _p(t), t.shape[0], t.shape[1], _p(out)))
+        return out[0] if scalar else out
+
+    def cmb_distances(self, theta):
+        """cmb.cmb_distances(...) -> (R, l_A, omega_b) (cmb/data_planck_act_compression.py:200-212)"""
+        r = self.cmb(theta)
+        return r[..., :3]
+
+    def sn_residuals(self, theta):
+        t, scalar = self._theta(theta)
+        out = np.empty((t.shape[0], self._c_spec.n_sn))
+        self._check(self.lib.cl_sn_residuals(self._ctx, _p(t), t.shape[0], t.shape[1], _p(out)))
+        return out[0] if scalar else out
+
+    # -- instrumentation --------------------------------------------------------------------------------------
+    def last_timing(self):
+        """dict of CUDA-event times (ms) of the last evaluation: stage12, stage3, finalize, total."""
+        ms = (C.c_double * 4)()
+        self._check(self.lib.cl_last_timing(self._ctx, ms))
+        return {"stage12_ms": ms[0], "stage3_ms": ms[1], "finalize_ms": ms[2], "total_ms": ms[3]}
+
+    def launch_count(self):
+        return int(self.lib.cl_launch_count(self._ctx))

@@ -1,0 +1,63 @@
+"""The golden cases: (spec builder, golden file) for every reference script the fixtures cover."""
+import os
+
+import numpy as np
+
+from cosmology_model_fit_b200 import datasets, fits
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_cache = {}
+
+
+def golden(name):
+    if name not in _cache:
+        _cache[name] = dict(np.load(os.path.join(GOLDEN, f"golden_{name}.npz")))
+    return _cache[name]
+
+
+def _memo(fn):
+    def wrapper():
+        key = "data:" + fn.__name__
+        if key not in _cache:
+            _cache[key] = fn()
+        return _cache[key]
+    return wrapper
+
+
+pantheon = _memo(lambda: datasets.pantheon_plus())
+pantheon.__name__ = "pantheon"
+pantheon = _memo(datasets.pantheon_plus)
+des = _memo(datasets.des_dovekie)
+union3 = _memo(datasets.union3_1)
+desi = _memo(datasets.desi_dr2)
+desi_fs = _memo(datasets.desi_fs_lya)
+
+SPECS = {
+    "sn_pantheon": lambda: fits.sn_pantheon(pantheon()),
+    "sn_union3_1": lambda: fits.sn_union3_1(union3()),
+    "sn_des5y": lambda: fits.sn_des5y(des()),
+    "bao_desi": lambda: fits.bao_desi(desi()),
+    "bao_desi_cmb_union3": lambda: fits.bao_desi_cmb_union3(union3(), desi_fs()),
+    "bao_desi_fs_lya_cmb": lambda: fits.bao_desi_fs_lya_cmb(desi_fs()),
+    "cmb_cmb": lambda: fits.cmb_cmb(),
+    "bao_desi_des5y_bbn_theta_star": lambda: fits.bao_desi_des5y_bbn_theta_star(des(), desi()),
+    "bao_desi_cmb_pantheon": lambda: fits.bao_desi_cmb_pantheon(pantheon(), desi()),
+    "bao_desi_cmb_des5y": lambda: fits.bao_desi_cmb_des5y(des(), desi_fs()),
+}
+
+#: cases whose golden file has a plain chi2[n] for theta[n]
+CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cmb_union3",
+              "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y"]
+
+
+def spec(name):
+    key = "spec:" + name
+    if key not in _cache:
+        _cache[key] = SPECS[name]()
+    return _cache[key]
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))

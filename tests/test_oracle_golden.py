@@ -1,0 +1,136 @@
+"""Pins the CPU oracle (oracle/cosmo_oracle.c) to golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  Tolerances: distances 1e-12 relative (north star asks 1e-9), chi2 1e-7 absolute
+(north star asks 1e-6) even where chi2 ~ 1e6."""
+import numpy as np
+import pytest
+
+import oracle.oracle as O
+from cases import CHI2_CASES, golden, rel_err, spec
+
+CHI2_ATOL = 1e-7
+DIST_RTOL = 1e-12
+
+
+@pytest.mark.parametrize("name", CHI2_CASES)
+def test_chi2_matches_reference(name):
+    g = golden(name)
+    got = O.Oracle(spec(name)).chi_squared(g["theta"])
+    assert np.max(np.abs(got - g["chi2"])) < CHI2_ATOL
+
+
+def test_grid_is_the_reference_grid():
+    for name in ("sn_pantheon", "sn_union3_1", "bao_desi", "bao_desi_cmb_union3", "bao_desi_des5y_bbn_theta_star"):
+        assert np.array_equal(spec(name).z_grid, golden(name)["z_grid"]), name
+
+
+def test_pantheon_distances_residuals_logprob():
+    g = golden("sn_pantheon")
+    o = O.Oracle(spec("sn_pantheon"))
+    dm, _ = o.distances(g["theta"][:8], g["zq"])
+    assert rel_err(dm, g["dm"]) < DIST_RTOL
+    assert np.max(np.abs(o.sn_residuals(g["theta"][:4]) - g["delta"])) < 1e-12
+    lp = o.log_probability(g["theta_logp"])
+    assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"]))
+    fin = np.isfinite(g["logp"])
+    assert np.max(np.abs(lp[fin] - g["logp"][fin])) < CHI2_ATOL
+
+
+def test_union3_distances_and_known_answers():
+    g = golden("sn_union3_1")
+    o = O.Oracle(spec("sn_union3_1"))
+    assert rel_err(o.distances(g["theta"][:8], g["zq"])[0], g["dm"]) < DIST_RTOL
+    # SURVEY.md G2 pins
+    chi2 = o.chi_squared([[-0.05, 0.3, -3.0], [-0.05, 0.3, 0.0], [0.027, 0.335, 0.0]])
+    assert np.allclose(chi2, [160.89519602172209, 178.67819338900432, 28.761102862275692], rtol=0, atol=1e-9)
+
+
+def test_bao_desi_theory_and_float32_batch():
+    g = golden("bao_desi")
+    o = O.Oracle(spec("bao_desi"))
+    assert rel_err(o.bao_theory(g["theta"]), g["theory"]) < DIST_RTOL
+    lp = o.log_probability(g["batch"])
+    assert np.array_equal(lp.astype(np.float32), g["logp32"])  # bao/desi.py:103 returns float32
+    assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp64"]))
+
+
+def test_config2_components_and_cmb():
+    g = golden("bao_desi_cmb_union3")
+    o = O.Oracle(spec("bao_desi_cmb_union3"))
+    c = o.components(g["theta"])
+    assert np.max(np.abs(c[:, 0] - g["chi2_sn"])) < CHI2_ATOL
+    assert np.max(np.abs(c[:, 1] - g["chi2_bao"])) < CHI2_ATOL
+    assert np.max(np.abs(c[:, 2] - g["chi2_cmb"])) < CHI2_ATOL
+    cm = o.cmb(g["theta"])
+    assert rel_err(cm[:, :3], g["cmb_distances"]) < DIST_RTOL
+    assert rel_err(cm[:, 3], g["z_star"]) < DIST_RTOL
+    assert rel_err(cm[:, 6], g["r_drag"]) < DIST_RTOL
+    assert rel_err(o.bao_theory(g["theta"]), g["bao_theory"]) < DIST_RTOL
+    # SURVEY.md G4 pin
+    assert abs(o.chi_squared([-0.0519, 68.42, 0.02257, 0.11738, -3.0])[0] - 39.686971513276205) < 1e-9
+
+
+def test_cmb_constants_match_reference_module():
+    g = golden("bao_desi_cmb_union3")
+    k = spec("bao_desi_cmb_union3").cmb_consts
+    assert k.Or_h2 == float(g["Or_h2"]) and k.Omnu_h2 == float(g["Omnu_h2"]) and k.Ogamma_h2 == float(g["O_GAMMA_H2"])
+    assert k.nu_m0 == float(g["m0"]) and k.nu_rho0 == float(g["rho0"])
+    assert np.array_equal(k.nu_q, g["qs"]) and np.array_equal(np.array(k.nu_w), g["ws"])
+    assert np.array_equal(k.priors, g["cmb_priors"]) and np.array_equal(k.covariance, g["cmb_cov"])
+    x, w = np.polynomial.legendre.leggauss(100)
+    assert np.array_equal(x, g["GL_X"]) and np.array_equal(w, g["GL_W"])
+
+
+def test_cpl_guard_and_loglike():
+    g = golden("bao_desi_fs_lya_cmb")
+    o = O.Oracle(spec("bao_desi_fs_lya_cmb"))
+    ll = o.log_likelihood(g["theta"])
+    guard = g["loglike"] == -1e8
+    assert guard.sum() > 0 and np.array_equal(ll == -1e8, guard)
+    assert np.max(np.abs(ll - g["loglike"])) < CHI2_ATOL
+    ok = ~guard
+    c = o.components(g["theta"][ok])
+    assert np.max(np.abs(c[:, 1] - g["chi2_bao"][ok])) < CHI2_ATOL
+    assert np.max(np.abs(c[:, 2] - g["chi2_cmb"][ok])) < CHI2_ATOL
+
+
+def test_cmb_only_blobs():
+    g = golden("cmb_cmb")
+    o = O.Oracle(spec("cmb_cmb"))
+    assert np.max(np.abs(o.log_likelihood(g["theta"]) - g["loglike"])) < CHI2_ATOL
+    cm = o.cmb(g["theta"])
+    blobs = np.c_[cm[:, 7], cm[:, 4], cm[:, 5] / 1000, cm[:, 3]]  # cmb/cmb.py:62-63
+    assert rel_err(blobs, g["blobs"]) < DIST_RTOL
+    lp = o.log_probability(g["theta_logp"])
+    assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"]))
+
+
+def test_config1_logprob_with_bbn_prior():
+    g = golden("bao_desi_des5y_bbn_theta_star")
+    o = O.Oracle(spec("bao_desi_des5y_bbn_theta_star"))
+    lp = o.log_probability(g["theta_logp"])
+    fin = np.isfinite(g["logp"])
+    assert np.array_equal(np.isneginf(lp), ~fin)
+    assert np.max(np.abs(lp[fin] - g["logp"][fin])) < CHI2_ATOL
+    assert rel_err(o.bao_theory(g["theta"][:8]), g["bao_theory"]) < DIST_RTOL
+
+
+def test_interpolator_known_answers():
+    g = golden("interpolator")
+    assert np.array_equal(O.interp_hermite(g["u_xq"], g["u_x"], g["u_y"], g["u_yp"]), g["u_herm"])
+    assert np.array_equal(O.interp_pchip(g["u_xq"], g["u_x"], g["u_y"]), g["u_pchip"])
+    assert np.array_equal(O.pchip_slopes(g["u_x"], g["u_y"]), g["u_slopes"])
+    assert np.array_equal(O.pchip_slopes(g["n_x"], g["n_y"]), g["n_slopes"])
+    assert np.array_equal(O.interp_pchip(g["n_xq"], g["n_x"], g["n_y"]), g["n_pchip"])
+    assert np.array_equal(O.interp_pchip(g["u_xq"], g["u_x"], g["d_y"]), g["d_pchip"])
+
+
+def test_solve_triangular_known_answers():
+    g = golden("solve_triangular")
+    for b, v in zip(g["b"], g["value"]):
+        assert abs(O.solve_triangular(g["L"], b) - v) < 1e-12 * abs(v)
+
+
+def test_threads_do_not_change_results():
+    g = golden("sn_pantheon")
+    o = O.Oracle(spec("sn_pantheon"))
+    assert np.array_equal(o.chi_squared(g["theta"], nthreads=1), o.chi_squared(g["theta"], nthreads=4))
