@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py — likelihood evals/sec on the headline workload of BASELINE.json.
+
+Workload W0: sn/pantheon.py-shaped likelihood — flat LCDM + z_turn=0.15 velocity step, theta =
+(M, H0, Om, v) — on the real Pantheon+ redshifts/magnitudes with the full N x N covariance (synthetic SPD
+stand-in: the real blob is not shipped with the reference), N = 1701 (all rows; `--n-sn 1590` gives the z>0.01
+cut the reference actually fits), batch B = 65536 parameter vectors per GPU per step.
+
+One "step" = one pass of the whole hot path (stage 1+2 Friedmann distances + residuals, stage 3 chi-squared
+DMMA GEMM, finalize) over one batch.  `value` is device-resident throughput (inputs already in HBM), `e2e` is
+the same through the C ABI with host buffers (H2D + D2H inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one process per GPU); rows are sharded across ranks (weak scaling, B per GPU
+fixed) and the per-rank log-likelihoods are all-gathered with NCCL every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "likelihood evals/sec (Pantheon+ full-cov, batch 65536)"
+UNIT = "evals/s"
+
+
+def build_spec(n_sn):
+    from cosmology_model_fit_b200 import datasets, fits
+    sn = datasets.pantheon_plus(cut=(n_sn == 1590))
+    assert sn[0].size == n_sn, sn[0].size
+    return fits.sn_pantheon(sn)
+
+
+def theta_batch(spec, B, seed):
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    return np.ascontiguousarray(uniform_theta(spec.bounds, B, seed=seed))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def dgemm_peak_tflops(torch, dev):
+    """FP64 tensor-pipe denominator: cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64
+    figure)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n**3 / (best * 1e-3) / 1e12
+
+
+def cpu_baseline(spec, theta, seconds=12.0):
+    """The oracle port (oracle/cosmo_oracle.c) on all host cores, on a bounded sample of the same batch."""
+    import oracle.oracle as O
+    orc = O.Oracle(spec, grid_builds=2)  # sn/pantheon.py rebuilds the z-grid twice per evaluation (:59-60,49)
+    cores = O.max_threads()
+    n0 = min(len(theta), 16 * cores)
+    t0 = time.perf_counter(); orc.chi_squared(theta[:n0], nthreads=0); dt = time.perf_counter() - t0
+    n = int(min(len(theta), max(n0, n0 * seconds / max(dt, 1e-3))))
+    t0 = time.perf_counter(); orc.chi_squared(theta[:n], nthreads=0); dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} rows of the step-0 batch, oracle/cosmo_oracle.c with {cores} threads, {dt:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is numba/Python and cannot
+    travel to the GPU box) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return 0
+    import oracle.oracle as O
+    spec = build_spec(args.n_sn)
+    orc = O.Oracle(spec, grid_builds=2)
+    cores = O.max_threads()
+    theta = theta_batch(spec, args.batch, 1000)
+    n = min(args.batch, max(256, 64 * cores))
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.chi_squared(theta[:n], nthreads=0)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        off = (k * n) % max(1, args.batch - n)
+        orc.chi_squared(theta[off:off + n], nthreads=0)
+    dt = time.perf_counter() - t0
+    val = args.steps * n / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, spec, world, sample_rows=n),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} rows per step of the same workload (bounded sample), {cores} threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, spec, world, sample_rows=None):
+    cfg = {"workload": f"W0 sn.pantheon shape: flat LCDM + v-step(z_turn=0.15), theta=(M,H0,Om,v), Pantheon+ N={args.n_sn} "
+                       f"full covariance (synthetic SPD stand-in), z-grid 4000, batch {args.batch} per GPU",
+           "n_sn": args.n_sn, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "n_grid": int(spec.z_grid.size),
+           "parallelism": f"theta rows sharded over {world} GPU(s), statics replicated, NCCL all-gather of logL",
+           "l2": "no explicit flush: each step writes+reads the residual matrix (B*N*8 = 0.9 GB) which exceeds the 126 MB L2; "
+                 "theta batches rotate between steps"}
+    if sample_rows is not None:
+        cfg["cpu_sample_rows_per_step"] = sample_rows
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--n-sn", type=int, default=1701, choices=[1590, 1701])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (tuning experiments)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.spec import OUT_LOGLIKE
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = build_spec(args.n_sn)
+    eng = Engine(spec, device=local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+    B, nd = args.batch, spec.ndim
+    n_rot = 4  # distinct theta batches rotated between steps
+    host_batches = [theta_batch(spec, B, seed=1000 + rank * 16 + i) for i in range(n_rot)]
+    d_theta = [torch.from_numpy(h).to(dev) for h in host_batches]
+    d_out = torch.empty(B, dtype=torch.float64, device=dev)
+    d_all = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    stream = torch.cuda.Stream(dev)  # a non-default stream: the kernels, the NCCL gather and the timing events share it
+    torch.cuda.set_stream(stream)
+
+    def step(i):
+        eng.eval_device(d_theta[i % n_rot].data_ptr(), B, nd, OUT_LOGLIKE, d_out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_out)
+
+    peak_tf = dgemm_peak_tflops(torch, dev)
+    torch.cuda.synchronize(dev)
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+
+    # ---- parity spot check of the benchmarked configuration before timing (rank 0, 64 rows vs the oracle) ----
+    parity = None
+    if rank == 0:
+        import oracle.oracle as O
+        got = d_out[:64].cpu().numpy()
+        want = O.Oracle(spec).log_likelihood(host_batches[(args.warmup - 1) % n_rot][:64])
+        parity = float(np.max(np.abs(-2 * got - -2 * want) / np.maximum(1.0, 1e-6 * np.abs(2 * want)) ))
+        if not np.all(np.abs(2 * got - 2 * want) <= np.maximum(1e-6, 1e-12 * np.abs(2 * want))):
+            raise SystemExit(f"parity check failed before timing: max |dchi2| = {np.max(np.abs(2*got-2*want))}")
+
+    # ---- timed region: device-resident ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    hist = eng.timing_history(min(args.steps, 64))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer C ABI (cl_eval): H2D of theta and D2H of logL every step ----
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        eng.log_likelihood(host_batches[i % n_rot])
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        res = eng.log_likelihood(host_batches[i % n_rot])
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, float(res[0]))
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank == 0:
+        N = args.n_sn
+        value = B * world * args.steps / (ms * 1e-3)
+        gemm_ms = float(np.mean(hist[:, 1])); s12_ms = float(np.mean(hist[:, 0]))
+        flops = B * (N * N + 2.0 * N)  # algorithmic: forward-substitution-equivalent MACs*2
+        ach = flops / (gemm_ms * 1e-3) / 1e12
+        pk = measured_peaks()
+        hbm_peak = pk.get("hbm_gbs", 6650.0)
+        s12_bytes = B * (8.0 * nd + 8.0 * N + 8.0)  # theta in, residual row out, aux
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, spec, world),
+            "roofline": {"bound": "tensor", "kernel": "k_chi2_gemm (stage 3, FP64 DMMA)", "achieved": ach, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                                        "DMMA.8x8x4 issue peak measured 37.1 TFLOP/s (profiles/r01_ubench_fp64.log)",
+                         "algorithmic_flops_per_eval": N * N + 2.0 * N, "avg_kernel_ms": gemm_ms},
+            "roofline_stage12": {"bound": "hbm", "kernel": "k_friedmann_residuals (stage 1+2)", "achieved": s12_bytes / (s12_ms * 1e-3) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s", "frac": s12_bytes / (s12_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "avg_kernel_ms": s12_ms, "note": "FP64-ALU bound, not HBM bound (SURVEY.md T5)"},
+            "stage_ms": {"stage12": s12_ms, "stage3": gemm_ms, "finalize": float(np.mean(hist[:, 2])), "total": float(np.mean(hist[:, 3]))},
+            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * nd * 8, "d2h_bytes_per_step": B * 8,
+                    "steps": e2e_steps, "api": "Engine.log_likelihood(batch) -> cl_eval (host buffers, pinned staging)"},
+            "gpu_launches": int(launches), "clocks": clocks, "parity_check": "64 rows vs oracle ok",
+            "engine": eng.describe(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(spec, host_batches[0])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

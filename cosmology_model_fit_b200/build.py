@@ -27,11 +27,17 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None):
+    global LIB
+    if out:
+        LIB_OUT = out
+    else:
+        LIB_OUT = LIB
+    if not force and not out and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC,-O2", "-shared", "-cudart", "static", "-o", LIB]
+           "-Xcompiler", "-fPIC,-O2", "-shared", "-cudart", "static", "-o", LIB_OUT]
+    cmd += os.environ.get("CL_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread", "-ldl", "-lrt"]
@@ -40,7 +46,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed")
-    return LIB
+    return LIB_OUT
 
 
 if __name__ == "__main__":

@@ -12,8 +12,11 @@
 // both operands, which leaves the product unchanged.
 //
 // Work decomposition: items (row block, column tile) ordered by decreasing k-extent of the column tile and
-// dealt round-robin to a persistent grid; the k loop of column tile j stops at the diagonal, so only
-// ~N^2/2 (1 + 128/N) MACs per row are executed instead of N^2.
+// dealt round-robin to a persistent grid.  Column tiles are aligned to the END of the matrix (tile t covers
+// columns [N - 128 (T - t), +128), the first tile may start at a negative column that TMA zero-fills), so the
+// ragged tile is the cheap one; the k loop of a tile stops at its diagonal block, and inside the diagonal block
+// every 8-column MMA tile stops at its own last column.  Each warp owns the interleaved 8-column tiles
+// {w, w+4, w+8, w+12} of the 128-column tile, so this skipping stays balanced across warps and sub-partitions.  Executed MACs per row ~ N^2/2 (1 + ~0.05) instead of N^2.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,7 +27,8 @@ namespace cosmolike {
 constexpr int kBM = 128, kBN = 128, kBK = 16;
 constexpr int kStages = 6;
 constexpr int kConsumerWarps = 8;
-constexpr int kGemmThreads = (kConsumerWarps + 1) * 32;
+constexpr int kProducerWarps = 4;  // one full warpgroup so that setmaxnreg can hand its registers to the consumers
+constexpr int kGemmThreads = (kConsumerWarps + kProducerWarps) * 32;
 constexpr int kBoxBytes = kBM * kBK * 8;       // 16 KB, A and B boxes have the same shape
 constexpr int kStageBytes = 2 * kBoxBytes;     // 32 KB
 constexpr int kGemmSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 4 * kBM * 8 /*epilogue*/ + 256 /*barriers*/;
@@ -37,7 +41,14 @@ struct GemmArgs {
   double* part;    // [T][B] partial sums of squares
   double* part_u;  // nullable [T][B]: partial sums of y_j * u_j (moments mode)
   const double* u; // [N] u = W 1 (moments mode)
+  int diag_skip;   // 1: warps stop at their own last column inside the diagonal block
 };
+
+// item visited by CTA `cta` in round `k` of the persistent loop: boustrophedon over the cost-sorted item list, so
+// that every CTA gets the same mix of expensive and cheap items (static, deterministic, no atomics)
+__device__ __forceinline__ int64_t snake_item(int64_t k, int cta, int ncta) {
+  return k * ncta + ((k & 1) ? (ncta - 1 - cta) : cta);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,6 +93,27 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
   return v;
 }
 
+// one k16 step of a warp tile: 64 rows x the 8-column tiles NT0..3 (tile nt lives at smem rows +32 nt)
+template <int NT0>
+__device__ __forceinline__ void kstep(double (&acc)[4][4][4], uint32_t aS, uint32_t bS, uint32_t ch0, uint32_t ch1) {
+  double bf[4][4];
+#pragma unroll
+  for (int nt = NT0; nt < 4; nt++) {
+    double2 lo = lds128(bS + nt * 4096 + ch0), hi = lds128(bS + nt * 4096 + ch1);
+    bf[nt][0] = lo.x; bf[nt][1] = lo.y; bf[nt][2] = hi.x; bf[nt][3] = hi.y;
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const uint32_t ar = aS + mt * 2048;
+    double2 r0lo = lds128(ar + ch0), r0hi = lds128(ar + ch1);
+    double2 r1lo = lds128(ar + 1024 + ch0), r1hi = lds128(ar + 1024 + ch1);
+    // a_i: row = g + 8*(i&1), logical k = t + 4*(i>>1) -> physical k = 4t + (i>>1)
+    double af[8] = {r0lo.x, r1lo.x, r0lo.y, r1lo.y, r0hi.x, r1hi.x, r0hi.y, r1hi.y};
+#pragma unroll
+    for (int nt = NT0; nt < 4; nt++) mma_f64_16816(acc[mt][nt], af, bf[nt]);
+  }
+}
+
 template <bool MOMENTS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
@@ -107,21 +139,24 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
   int stage = 0;
   uint32_t phase = 0;
 
-  if (warp == kConsumerWarps) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp >= kConsumerWarps) {
+    // ===================== TMA producer (one lane of the producer warpgroup) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == kConsumerWarps && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-      for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+      for (int64_t round = 0;; round++) {
+        const int64_t item = snake_item(round, blockIdx.x, gridDim.x);
+        if (item >= total) { if (round * gridDim.x >= total) break; else continue; }
         const int jt = g.T - 1 - (int)(item / g.n_rb);
         const int rb = (int)(item % g.n_rb);
-        const int kmax = min(g.N, (jt + 1) * kBN);
-        const int nk = (kmax + kBK - 1) / kBK;
+        const int c0 = g.N - kBN * (g.T - jt);          // first column of the tile (may be < 0 for jt == 0)
+        const int nk = (c0 + kBN + kBK - 1) / kBK;      // k runs to the end of the diagonal block
         for (int ks = 0; ks < nk; ks++) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           tma_load_2d(sA + stage * kBoxBytes, &tmR, ks * kBK, rb * kBM, full_bar(stage));
-          tma_load_2d(sB + stage * kBoxBytes, &tmW, ks * kBK, jt * kBN, full_bar(stage));
+          tma_load_2d(sB + stage * kBoxBytes, &tmW, ks * kBK, c0, full_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -130,19 +165,23 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
   }
 
   // ===================== consumers: DMMA + fused row-dot epilogue =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
   const int gq = lane >> 2, t = lane & 3;   // mma "groupID" and "threadID_in_group"
+  // warp -> 64 rows (warp_m) x the four interleaved 8-column tiles {warp_n + 4 nt}
   const int warp_m = warp & 1, warp_n = warp >> 1;
   // byte offsets of this lane's two 16-byte chunks inside a 128-byte row, after the 128B swizzle
   const uint32_t ch0 = (uint32_t)(((2 * t) ^ gq) << 4), ch1 = (uint32_t)(((2 * t + 1) ^ gq) << 4);
   const uint32_t a_row0 = (uint32_t)(warp_m * 64 + gq) * 128u;  // + mt*16*128 (+8 rows = +1024)
-  const uint32_t b_row0 = (uint32_t)(warp_n * 32 + gq) * 128u;  // + nt*8*128
+  const uint32_t b_row0 = (uint32_t)(warp_n * 8 + gq) * 128u;   // + nt*32*128
   int epi_buf = 0;
 
-  for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+  for (int64_t round = 0;; round++) {
+    const int64_t item = snake_item(round, blockIdx.x, gridDim.x);
+    if (item >= total) { if (round * gridDim.x >= total) break; else continue; }
     const int jt = g.T - 1 - (int)(item / g.n_rb);
     const int rb = (int)(item % g.n_rb);
-    const int kmax = min(g.N, (jt + 1) * kBN);
-    const int nk = (kmax + kBK - 1) / kBK;
+    const int c0 = g.N - kBN * (g.T - jt);
+    const int nk = (c0 + kBN + kBK - 1) / kBK;
 
     double acc[4][4][4];
 #pragma unroll
@@ -154,23 +193,23 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
 
     for (int ks = 0; ks < nk; ks++) {
       mbar_wait(full_bar(stage), phase);
-      const uint32_t aS = sA + stage * kBoxBytes + a_row0;
-      const uint32_t bS = sB + stage * kBoxBytes + b_row0;
-      double bf[4][4];
-#pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
-        double2 lo = lds128(bS + nt * 1024 + ch0), hi = lds128(bS + nt * 1024 + ch1);
-        bf[nt][0] = lo.x; bf[nt][1] = lo.y; bf[nt][2] = hi.x; bf[nt][3] = hi.y;
+      // W[j][k] = 0 for k > j: the 8-column tile nt (columns c0 + 8 (warp_n + 4 nt) .. +7) needs k16 step ks only
+      // if ks*16 <= its last column.  nt0 = first tile still active (0 outside the diagonal block).
+      int nt0 = 0;
+      if (g.diag_skip) {
+        const int d = ks * kBK - c0 - 8 * warp_n - 8;  // tile nt active  <=>  32 nt > d
+        nt0 = d < 0 ? 0 : (d >> 5) + 1;
       }
-#pragma unroll
-      for (int mt = 0; mt < 4; mt++) {
-        const uint32_t ar = aS + mt * 2048;
-        double2 r0lo = lds128(ar + ch0), r0hi = lds128(ar + ch1);
-        double2 r1lo = lds128(ar + 1024 + ch0), r1hi = lds128(ar + 1024 + ch1);
-        // a_i: row = g + 8*(i&1), logical k = t + 4*(i>>1) -> physical k = 4t + (i>>1)
-        double af[8] = {r0lo.x, r1lo.x, r0lo.y, r1lo.y, r0hi.x, r1hi.x, r0hi.y, r1hi.y};
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) mma_f64_16816(acc[mt][nt], af, bf[nt]);
+      if (nt0 < 4) {
+        const uint32_t aS = sA + stage * kBoxBytes + a_row0;
+        const uint32_t bS = sB + stage * kBoxBytes + b_row0;
+        // separate unpredicated code paths per number of live tiles (predicated mma.sync serialises on temporaries)
+        switch (nt0) {
+          case 0: kstep<0>(acc, aS, bS, ch0, ch1); break;
+          case 1: kstep<1>(acc, aS, bS, ch0, ch1); break;
+          case 2: kstep<2>(acc, aS, bS, ch0, ch1); break;
+          default: kstep<3>(acc, aS, bS, ch0, ch1); break;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar(stage));
@@ -185,9 +224,9 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
     if (MOMENTS) {
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
-        int col = jt * kBN + warp_n * 32 + nt * 8 + 2 * t;
-        uu[nt][0] = col < g.N ? g.u[col] : 0.0;
-        uu[nt][1] = col + 1 < g.N ? g.u[col + 1] : 0.0;
+        int col = c0 + (warp_n + 4 * nt) * 8 + 2 * t;
+        uu[nt][0] = (col >= 0 && col < g.N) ? g.u[col] : 0.0;
+        uu[nt][1] = (col + 1 >= 0 && col + 1 < g.N) ? g.u[col + 1] : 0.0;
       }
     }
 #pragma unroll

@@ -29,8 +29,10 @@ struct cl_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {};
-  bool timing_valid = false;
+  static constexpr int kRing = 64;      // timing history: one event set per evaluation call
+  cudaEvent_t evring[kRing][6] = {};
+  cudaEvent_t* ev = evring[0];
+  int64_t n_timed = 0;
   DevSpec ds{};
   std::vector<void*> dev_allocs;
   // stage 3 operands
@@ -49,7 +51,7 @@ struct cl_ctx {
   double *h_theta = nullptr, *h_out = nullptr;  // pinned
   int64_t h_theta_cap = 0, h_out_cap = 0;
   int64_t launches = 0;
-  int opt_gemm_ctas = 0, opt_s12_ctas = 0;
+  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1;
   std::string err, desc;
   std::mutex mu;
 };
@@ -269,7 +271,7 @@ extern "C" int cl_destroy(cl_ctx* c) {
   for (double* p : {c->d_theta, c->d_out, c->d_R, c->d_aux, c->d_part, c->d_part_u, c->d_scratch, c->d_W, c->d_u}) if (p) cudaFree(p);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
-  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& r : c->evring) for (auto& e : r) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return CL_OK;
@@ -299,7 +301,7 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
 #define CTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(c, CL_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); return bail(CL_E_CUDA); } } while (0)
   CTRY(cudaSetDevice(device));
   CTRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (auto& e : c->ev) CTRY(cudaEventCreate(&e));
+  for (auto& r : c->evring) for (auto& e : r) CTRY(cudaEventCreate(&e));
 
   DevSpec& d = c->ds;
   const cl_spec& s = *spec;
@@ -318,6 +320,17 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
     d.grid_uniform = uni ? 1 : 0;
     d.step = step; d.inv_step = 1.0 / step; d.z_last = s.z_grid[s.n_grid - 1];
   }
+  {  // fast_log10 table: c_j = 1 + (j + 1/2)/128; entry = {fl(1/c_j), -log10(fl(1/c_j))}
+    std::vector<double> tab(256);
+    for (int j = 0; j < 128; j++) {
+      double inv = (double)(1.0L / (1.0L + ((long double)j + 0.5L) / 128.0L));
+      tab[2 * j] = inv;
+      tab[2 * j + 1] = (double)(-log10l((long double)inv));
+    }
+    const double* dtab = nullptr;
+    TRY(upload(c, tab.data(), tab.size(), &dtab));
+    d.logtab = reinterpret_cast<const double2*>(dtab);
+  }
   // SN
   d.n_sn = s.n_sn;
   if (s.n_sn > 0) {
@@ -325,11 +338,18 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
     d.sn_small = n <= CL_SN_SMALL_MAX ? 1 : 0;
     d.sn_form = s.sn_cov_form; d.col_offset = s.col_offset; d.n_vel = s.n_vel; d.vel_mode = s.vel_mode; d.vel_scale = s.vel_scale;
     for (int k = 0; k < CL_MAX_VEL; k++) d.col_vel[k] = k < s.n_vel ? s.col_vel[k] : 0;
-    std::vector<double> zhelp1(n);
-    for (int i = 0; i < n; i++) zhelp1[i] = 1.0 + s.sn_zhel[i];  // (1.0 + z_hel), sn/pantheon.py:54
-    TRY(upload(c, s.sn_zcmb, (size_t)n, &d.sn_zcmb));
-    TRY(upload(c, zhelp1.data(), (size_t)n, &d.sn_zhelp1));
-    TRY(upload(c, s.sn_obs, (size_t)n, &d.sn_obs));
+    // vel_pm1: one template whose weights are all +-1 (the z_turn step) and the divide form -> two reciprocals per theta
+    bool pm1 = s.n_vel == 1 && s.vel_mode == CL_VEL_DIVIDE;
+    for (int i = 0; pm1 && i < n; i++) pm1 = (s.sn_vel_weight[i] == 1.0 || s.sn_vel_weight[i] == -1.0);
+    d.vel_pm1 = pm1 ? 1 : 0;
+    std::vector<double> pack((size_t)n * 4);
+    for (int i = 0; i < n; i++) {
+      pack[4 * i + 0] = s.sn_zcmb[i];
+      pack[4 * i + 1] = s.n_vel > 0 ? s.sn_vel_weight[i] : 0.0;
+      pack[4 * i + 2] = 1.0 + s.sn_zhel[i];  // (1.0 + z_hel), sn/pantheon.py:54
+      pack[4 * i + 3] = s.sn_obs[i];
+    }
+    TRY(upload(c, pack.data(), pack.size(), &d.sn_pack));
     if (s.n_vel > 0) TRY(upload(c, s.sn_vel_weight, (size_t)n * s.n_vel, &d.sn_vel_w));
     // factor handling
     std::vector<double> Lbuf;
@@ -429,6 +449,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "max_rows_per_pass") { if (value < 128) return fail(c, CL_E_INVALID, "max_rows_per_pass must be >= 128"); c->max_rows = value; return CL_OK; }
   if (n == "gemm_ctas") { c->opt_gemm_ctas = (int)value; return CL_OK; }
   if (n == "stage12_ctas") { c->opt_s12_ctas = (int)value; return CL_OK; }
+  if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }
   return fail(c, CL_E_INVALID, "unknown option %s", name);
 }
 
@@ -436,7 +457,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
 static int ensure_rows(cl_ctx* c, int64_t rows) {
   if (rows <= c->cap_rows) return CL_OK;
   int64_t cap = std::max<int64_t>(rows, std::min<int64_t>(c->max_rows, std::max<int64_t>(1024, c->cap_rows * 2)));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaDeviceSynchronize());  // the workspace may be in use on a caller-supplied stream
   for (double** p : {&c->d_theta, &c->d_out, &c->d_R, &c->d_aux, &c->d_part, &c->d_part_u}) { if (*p) cudaFree(*p); *p = nullptr; }
   c->cap_rows = 0;
   CUDA_TRY(c, cudaMalloc(&c->d_theta, cap * CL_MAX_DIM * sizeof(double)));
@@ -506,7 +527,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
     if (rc != CL_OK) return rc;
     GemmArgs g{};
     g.B = rows; g.N = c->ds.n_sn; g.T = c->T; g.n_rb = (int)((rows + kBM - 1) / kBM);
-    g.part = c->d_part; g.part_u = c->d_part_u; g.u = c->d_u;
+    g.part = c->d_part; g.part_u = c->d_part_u; g.u = c->d_u; g.diag_skip = c->opt_diag_skip;
     int64_t items = (int64_t)g.n_rb * g.T;
     int grid = (int)std::min<int64_t>(items, c->opt_gemm_ctas > 0 ? c->opt_gemm_ctas : c->sm_count);
     if (moments) k_chi2_gemm<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
@@ -539,6 +560,7 @@ extern "C" int cl_eval_device(cl_ctx* c, const double* d_theta, int64_t B, int64
   std::lock_guard<std::mutex> lk(c->mu);
   CUDA_TRY(c, cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  c->ev = c->evring[c->n_timed % cl_ctx::kRing];
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
   for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
     int64_t rows = std::min(c->max_rows, B - r0);
@@ -546,7 +568,7 @@ extern "C" int cl_eval_device(cl_ctx* c, const double* d_theta, int64_t B, int64
     if (rc != CL_OK) return rc;
   }
   CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
-  c->timing_valid = true;
+  c->n_timed++;
   return CL_OK;
 }
 
@@ -558,6 +580,7 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int nd = c->ds.ndim;
   cudaStream_t st = c->stream;
+  c->ev = c->evring[c->n_timed % cl_ctx::kRing];
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
   for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
     int64_t rows = std::min(c->max_rows, B - r0);
@@ -585,7 +608,7 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
     CUDA_TRY(c, cudaStreamSynchronize(st));
     memcpy(out + r0 * width, c->h_out, rows * width * sizeof(double));
   }
-  c->timing_valid = true;
+  c->n_timed++;
   return CL_OK;
 }
 
@@ -664,15 +687,32 @@ extern "C" int cl_sn_residuals(cl_ctx* c, const double* theta, int64_t B, int64_
   return helper(c, theta, B, ld, MODE_RESID, nullptr, 0, out, nullptr, c->ds.n_sn);
 }
 
+static int timing_of(cl_ctx* c, int64_t idx, double ms[4]) {
+  cudaEvent_t* ev = c->evring[idx % cl_ctx::kRing];
+  CUDA_TRY(c, cudaEventSynchronize(ev[5]));
+  float t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, ev[1], ev[2])); ms[0] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, ev[2], ev[3])); ms[1] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, ev[3], ev[4])); ms[2] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, ev[0], ev[5])); ms[3] = t;
+  return CL_OK;
+}
+
 extern "C" int cl_last_timing(cl_ctx* c, double ms[4]) {
   if (!c || !ms) return CL_E_INVALID;
-  if (!c->timing_valid) return fail(c, CL_E_INVALID, "no evaluation has been timed yet");
+  if (c->n_timed == 0) return fail(c, CL_E_INVALID, "no evaluation has been timed yet");
   std::lock_guard<std::mutex> lk(c->mu);
-  CUDA_TRY(c, cudaEventSynchronize(c->ev[5]));
-  float t;
-  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[1], c->ev[2])); ms[0] = t;
-  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[2], c->ev[3])); ms[1] = t;
-  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); ms[2] = t;
-  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev[0], c->ev[5])); ms[3] = t;
-  return CL_OK;
+  return timing_of(c, c->n_timed - 1, ms);
+}
+
+extern "C" int cl_timing_history(cl_ctx* c, int n, double* ms) {
+  if (!c || !ms || n < 0) return CL_E_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int avail = (int)std::min<int64_t>(c->n_timed, cl_ctx::kRing);
+  int k = std::min(n, avail);
+  for (int i = 0; i < k; i++) {
+    int rc = timing_of(c, c->n_timed - k + i, ms + 4 * i);
+    if (rc != CL_OK) return rc;
+  }
+  return k;
 }

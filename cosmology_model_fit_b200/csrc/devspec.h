@@ -2,6 +2,7 @@
 // Passed to the kernels by value as a __grid_constant__ parameter.
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
 #include "../../include/cosmolike.h"
 
 namespace cosmolike {
@@ -29,7 +30,9 @@ struct DevSpec {
   // SN block
   int n_sn, sn_small, sn_form, col_offset, n_vel, vel_mode, vel_pm1;
   int col_vel[CL_MAX_VEL];
-  const double *sn_zcmb, *sn_zhelp1, *sn_obs, *sn_vel_w, *sn_mat_small;
+  const double* sn_pack;   // [n_sn][4] = {z_cmb, first velocity-template weight, 1 + z_hel, obs}
+  const double *sn_vel_w, *sn_mat_small;
+  const double2* logtab;   // [128] {1/c_j, log10(c_j)} for fast_log10
   double vel_scale;
   // BAO block
   int n_bao, dh_mode, rd_mode, col_rd;

@@ -7,6 +7,14 @@
 //   mu with the z_pec step correction (sn/pantheon.py:43-60), BAO ratios (bao/desi_cmb_union3.py:76-94),
 //   (R, l_A, omega_b), the small quadratic forms, priors and guards.  The SN residual row goes to HBM for the
 //   stage-3 chi-squared GEMM; everything else is reduced to a handful of scalars per theta.
+//
+// Arithmetic notes (all FP64; the FP64 pipe is the bound of this kernel):
+//   * dh = (c/H0) * rsqrt(E^2) instead of c / (H0 * sqrt(E^2)): <= 2 ulp from the reference's three roundings.
+//   * on the np.linspace grid the Hermite abscissa is t = z/step - i (one FMA) instead of (z - x_i)/h_i; the two
+//     differ by ~1e-13 relative in t, i.e. < 1e-13 relative in D_M (the interpolant is C1 across nodes).
+//   * log10 is a 128-entry table + degree-7 polynomial (abs. error < 3e-16 on the D_L range), no special cases.
+//   * grid {D_M, dh} pairs are interleaved as double2 with one pad slot per 16 entries: conflict-free 16-byte
+//     stores from the per-thread chunks, one 16-byte load per node when interpolating.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -14,19 +22,24 @@
 
 namespace cosmolike {
 
+#ifndef CL_S12_MINBLOCKS
+#define CL_S12_MINBLOCKS 3
+#endif
 constexpr int kS12Threads = 256;
 constexpr int kPPT = 16;  // grid points per thread: 256*16 = 4096 >= n_grid
+constexpr int kMaxGrid = kS12Threads * kPPT;
 
-__host__ __device__ __forceinline__ int pad_idx(int i) { return i + ((i >> 4) << 1); }
-constexpr int kPaddedGrid = 4096 + (4096 / 16) * 2;
+__host__ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
+constexpr int kPaddedGrid = kMaxGrid + kMaxGrid / 16;
 
 struct Cosmo {
-  double H0, h, Om, Or, Obc, Onu, Ode, obh2, och2, w0, wa;
+  double H0, h, K /* c/H0 */, Om, Or, Obc, Onu, Ode, obh2, och2, w0, wa;
 };
 
 __device__ __forceinline__ void unpack(const DevSpec& s, const double* __restrict__ th, Cosmo& c) {
   c.H0 = s.col_H0 >= 0 ? s.H0_scale * th[s.col_H0] : s.H0_fixed;
   c.h = c.H0 / 100;
+  c.K = kC_KMS / c.H0;
   c.w0 = s.col_w0 >= 0 ? th[s.col_w0] : -1.0;
   c.wa = s.col_wa >= 0 ? th[s.col_wa] : 0.0;
   c.Om = c.Or = c.Obc = c.Onu = c.Ode = c.obh2 = c.och2 = 0.0;
@@ -45,12 +58,14 @@ __device__ __forceinline__ void unpack(const DevSpec& s, const double* __restric
   }
 }
 
+__device__ __forceinline__ double fast_sqrt(double x) { return x * rsqrt(x); }  // x > 0, <= 2 ulp
+
 // 5-node massive-neutrino density (cmb/data_planck_act_compression.py:53-66)
 __device__ __forceinline__ double omnu_z(const cl_cmb_consts& k, double zp1) {
   double r = k.nu_m0 / zp1;
   double mz = r * r;
-  double f0 = sqrt(k.nu_q2[0] + mz), f1 = sqrt(k.nu_q2[1] + mz), f2 = sqrt(k.nu_q2[2] + mz);
-  double f3 = sqrt(k.nu_q2[3] + mz), f4 = sqrt(k.nu_q2[4] + mz);
+  double f0 = fast_sqrt(k.nu_q2[0] + mz), f1 = fast_sqrt(k.nu_q2[1] + mz), f2 = fast_sqrt(k.nu_q2[2] + mz);
+  double f3 = fast_sqrt(k.nu_q2[3] + mz), f4 = fast_sqrt(k.nu_q2[4] + mz);
   double ws = f0 * k.nu_w[0] + f1 * k.nu_w[1] + f2 * k.nu_w[2] + f3 * k.nu_w[3] + f4 * k.nu_w[4];
   double z2 = zp1 * zp1;
   return z2 * z2 * ws / k.nu_rho0;
@@ -67,20 +82,28 @@ __device__ __forceinline__ double fde(const Cosmo& c, double z, double zp1, doub
   return 1.0;
 }
 
-// H(z) (sn/pantheon.py:28-31 late family, bao/desi_cmb_union3.py:37-57 full family)
+// E(z)^2 = (H/H0)^2 (sn/pantheon.py:28-31 late family, bao/desi_cmb_union3.py:37-57 full family)
 template <int FAM, int DE>
-__device__ __forceinline__ double H_of_z(const DevSpec& s, const Cosmo& c, double z) {
+__device__ __forceinline__ double E2_of_z(const DevSpec& s, const Cosmo& c, double z) {
   double zp1 = 1.0 + z;
   double cubed = zp1 * zp1 * zp1;
   if (FAM == CL_FAMILY_LATE) {
     double de = (DE == CL_DE_LCDM) ? (1.0 - c.Om) : (1.0 - c.Om) * fde<DE>(c, z, zp1, cubed);
-    return c.H0 * sqrt(c.Om * cubed + de);
+    return c.Om * cubed + de;
   }
   double radiation = c.Or * (cubed * zp1);
   double matter = c.Obc * cubed;
   double neutrino = c.Onu * omnu_z(s.k, zp1);
   double de = (DE == CL_DE_LCDM) ? c.Ode : c.Ode * fde<DE>(c, z, zp1, cubed);
-  return c.H0 * sqrt(radiation + matter + de + neutrino);
+  return radiation + matter + de + neutrino;
+}
+template <int FAM, int DE>
+__device__ __forceinline__ double DH_of_z(const DevSpec& s, const Cosmo& c, double z) {  // c / H(z)
+  return c.K * rsqrt(E2_of_z<FAM, DE>(s, c, z));
+}
+template <int FAM, int DE>
+__device__ __forceinline__ double H_of_z(const DevSpec& s, const Cosmo& c, double z) {
+  return c.H0 * fast_sqrt(E2_of_z<FAM, DE>(s, c, z));
 }
 
 __device__ __forceinline__ double grid_z(const DevSpec& s, int i) {
@@ -88,51 +111,75 @@ __device__ __forceinline__ double grid_z(const DevSpec& s, int i) {
   return __ldg(s.z_grid + i);
 }
 
-// index i with x[i] < xq <= x[i+1]  (np.searchsorted(x, xq) - 1, interpolator.py:94); caller excluded the ends
-__device__ __forceinline__ int find_interval(const DevSpec& s, double xq) {
+// log10(x) for normal positive x: x = 2^e m, m in [1,2); table entry j = top 7 mantissa bits holds
+// {1/c_j rounded, -log10 of that rounded value}; log10(m) = log10(m/c_j) + log10(c_j) with |m/c_j - 1| < 2^-8.
+__device__ __forceinline__ double fast_log10(double x, const double2* __restrict__ tab) {
+  if (!(x >= 2.2250738585072014e-308 && x < INFINITY)) return log10(x);  // zero, negative, subnormal, inf, nan
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 tc = tab[(hi >> 13) & 127];
+  const double r = fma(m, tc.x, -1.0);
+  // log1p(r)/ln(10) = r (c1 + c2 r + ... + c7 r^6), c_k = (-1)^(k+1) / (k ln 10)
+  double p = 0.062042069733182864;           //  1/(7 ln10)
+  p = fma(p, r, -0.072382414688713337);      // -1/(6 ln10)
+  p = fma(p, r, 0.086858896380650366);       //  1/(5 ln10)
+  p = fma(p, r, -0.10857362047581296);       // -1/(4 ln10)
+  p = fma(p, r, 0.14476482730108395);        //  1/(3 ln10)
+  p = fma(p, r, -0.21714724095162591);       // -1/(2 ln10)
+  p = fma(p, r, 0.43429448190325182);        //  1/ln10
+  const double ed = (double)e;
+  // log10(2) = hi + lo with hi exact in 32 bits so that e*hi is exact
+  double res = fma(ed, 0.30102999566406652, tc.y);
+  res = fma(ed, -8.5323443170571066e-14, res);
+  return fma(r, p, res);
+}
+
+// cubic Hermite segment in Horner form: y(t) on [node i, node i+1], t in [0,1], hd = h * slope
+__device__ __forceinline__ double hermite_seg(double y0, double hd0, double y1, double hd1, double t) {
+  const double D = y1 - y0;
+  const double c2 = fma(3.0, D, -fma(2.0, hd0, hd1));
+  const double c3 = (hd0 + hd1) - 2.0 * D;
+  return fma(t, fma(t, fma(t, c3, c2), hd0), y0);
+}
+
+// D_M(xq): cubic Hermite with analytic node derivatives y' = dh (interp_hermite, interpolator.py:71-108,117-119);
+// linear extrapolation with the end slope outside the grid
+__device__ __forceinline__ double hermite_dm(const DevSpec& s, const double2* __restrict__ gd, double xq) {
   const int G = s.G;
   if (s.grid_uniform) {
-    int i = (int)(xq * s.inv_step);
-    i = max(0, min(i, G - 2));
-    while (i > 0 && grid_z(s, i) >= xq) --i;
-    while (i < G - 2 && grid_z(s, i + 1) < xq) ++i;
-    return i;
+    if (xq > 0.0 && xq < s.z_last) {
+      const double u = xq * s.inv_step;
+      const int i = min((int)u, G - 2);
+      const double t = fma(xq, s.inv_step, -(double)i);
+      const double2 a = gd[pad_idx(i)], b = gd[pad_idx(i + 1)];
+      return hermite_seg(a.x, s.step * a.y, b.x, s.step * b.y, t);
+    }
+    if (xq <= 0.0) { const double2 a = gd[0]; return a.x + a.y * xq; }
+    const double2 b = gd[pad_idx(G - 1)];
+    return b.x + b.y * (xq - s.z_last);
   }
-  int lo = 0, hi = G;
+  const double x0 = __ldg(s.z_grid), xn = __ldg(s.z_grid + G - 1);
+  if (xq <= x0) { const double2 a = gd[0]; return a.x + a.y * (xq - x0); }
+  if (xq >= xn) { const double2 b = gd[pad_idx(G - 1)]; return b.x + b.y * (xq - xn); }
+  int lo = 0, hi = G;  // np.searchsorted(x, xq) - 1 (interpolator.py:94)
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
     if (__ldg(s.z_grid + mid) < xq) lo = mid + 1; else hi = mid;
   }
-  return lo - 1;
-}
-
-// cubic Hermite with analytic node derivatives y' = dh (interp_hermite, interpolator.py:71-108,117-119)
-__device__ __forceinline__ double hermite_dm(const DevSpec& s, const double* __restrict__ s_cum,
-                                             const double* __restrict__ s_dh, double xq) {
-  const int G = s.G;
-  double x0 = grid_z(s, 0), xn = grid_z(s, G - 1);
-  if (xq <= x0) return s_cum[0] + s_dh[0] * (xq - x0);
-  if (xq >= xn) return s_cum[pad_idx(G - 1)] + s_dh[pad_idx(G - 1)] * (xq - xn);
-  int i = find_interval(s, xq);
-  double xi = grid_z(s, i);
-  double h_i = grid_z(s, i + 1) - xi;
-  double t = (xq - xi) / h_i;
-  double t2 = t * t, t3 = t2 * t;
-  double h00 = 2 * t3 - 3 * t2 + 1;
-  double h10 = t3 - 2 * t2 + t;
-  double h01 = -2 * t3 + 3 * t2;
-  double h11 = t3 - t2;
-  int p0 = pad_idx(i), p1 = pad_idx(i + 1);
-  return h00 * s_cum[p0] + h10 * h_i * s_dh[p0] + h01 * s_cum[p1] + h11 * h_i * s_dh[p1];
+  const int i = lo - 1;
+  const double xi = __ldg(s.z_grid + i), h_i = __ldg(s.z_grid + i + 1) - xi;
+  const double2 a = gd[pad_idx(i)], b = gd[pad_idx(i + 1)];
+  return hermite_seg(a.x, h_i * a.y, b.x, h_i * b.y, (xq - xi) / h_i);
 }
 
 __device__ __forceinline__ double sgn(double v) { return (double)((v > 0) - (v < 0)); }
 
 // Fritsch-Carlson slope at node j of (z_grid, dh_grid) (_pchip_slopes, interpolator.py:5-68); local stencil
-__device__ double pchip_slope(const DevSpec& s, const double* __restrict__ y, int j) {
+__device__ double pchip_slope(const DevSpec& s, const double2* __restrict__ gd, int j) {
   const int n = s.G;
   auto H = [&](int i) { return grid_z(s, i + 1) - grid_z(s, i); };
-  auto D = [&](int i) { return (y[pad_idx(i + 1)] - y[pad_idx(i)]) / H(i); };
+  auto D = [&](int i) { return (gd[pad_idx(i + 1)].y - gd[pad_idx(i)].y) / H(i); };
   if (j == 0) {
     double h0 = H(0), h1 = H(1), d0 = D(0), d1 = D(1);
     double v = ((2 * h0 + h1) * d0 - h0 * d1) / (h0 + h1);
@@ -155,19 +202,25 @@ __device__ double pchip_slope(const DevSpec& s, const double* __restrict__ y, in
   return 0.0;
 }
 
-// interp_pchip(xq, z_grid, dh_grid) (interpolator.py:111-114): clamps outside the grid
-__device__ double pchip_dh(const DevSpec& s, const double* __restrict__ s_dh, double xq) {
+// interp_pchip(xq, z_grid, dh_grid) (interpolator.py:111-114): clamps outside the grid.  Only <= 32 BAO points
+// per theta use this, so it follows the reference formulas literally.
+__device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, double xq) {
   const int G = s.G;
-  if (xq <= grid_z(s, 0)) return s_dh[0];
-  if (xq >= grid_z(s, G - 1)) return s_dh[pad_idx(G - 1)];
-  int i = find_interval(s, xq);
+  if (xq <= grid_z(s, 0)) return gd[0].y;
+  if (xq >= grid_z(s, G - 1)) return gd[pad_idx(G - 1)].y;
+  int lo = 0, hi = G;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (grid_z(s, mid) < xq) lo = mid + 1; else hi = mid;
+  }
+  const int i = lo - 1;
   double xi = grid_z(s, i);
   double h_i = grid_z(s, i + 1) - xi;
   double t = (xq - xi) / h_i;
   double t2 = t * t, t3 = t2 * t;
   double h00 = 2 * t3 - 3 * t2 + 1, h10 = t3 - 2 * t2 + t, h01 = -2 * t3 + 3 * t2, h11 = t3 - t2;
-  double d0 = pchip_slope(s, s_dh, i), d1 = pchip_slope(s, s_dh, i + 1);
-  return h00 * s_dh[pad_idx(i)] + h10 * h_i * d0 + h01 * s_dh[pad_idx(i + 1)] + h11 * h_i * d1;
+  double d0 = pchip_slope(s, gd, i), d1 = pchip_slope(s, gd, i + 1);
+  return h00 * gd[pad_idx(i)].y + h10 * h_i * d0 + h01 * gd[pad_idx(i + 1)].y + h11 * h_i * d1;
 }
 
 // closed-form fits (cmb/data_planck_act_compression.py:86-124)
@@ -214,21 +267,23 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*
 }
 
 struct S12Smem {
-  double cum[kPaddedGrid];
-  double dh[kPaddedGrid];
+  double2 gd[kPaddedGrid];  // {cumulative D_M, dh} per grid node, padded
+  double2 logtab[128];
   double wsum[8];
   double red[5 * 8];
   double vec[CL_MAX_BAO + CL_MAX_CC + CL_SN_SMALL_MAX];
-  double scal[4];  // z*, r_drag
+  double scal[4];  // z*, r_drag, 1/(1+z_pec) for w=+1, for w=-1
 };
 
 template <int FAM, int DE>
-__global__ void __launch_bounds__(kS12Threads, 3)
+__global__ void __launch_bounds__(kS12Threads, CL_S12_MINBLOCKS)
 k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__ Stage12Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = s.G;
+  if (tid < 128) sm.logtab[tid] = s.logtab[tid];
+  // (visible after the first __syncthreads of the loop body)
 
   for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
     const double* __restrict__ th = a.theta + b * a.ld;
@@ -265,42 +320,27 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const bool need_rd = s.rd_mode == CL_RD_FIT && ((a.mode == MODE_EVAL && s.n_bao > 0) || a.mode == MODE_BAO || a.mode == MODE_CMB);
 
     // ================= stage 1: dh = c/H on the grid, cumulative trapezoid =================
-    double dh[kPPT];
+    // thread t owns nodes [16t, 16t+16) and the 16 intervals that start at them (it also evaluates node 16t+16)
+    double dh[kPPT + 1];
+    double run = 0.0;
     const int i0 = tid * kPPT;
     if (need_grid) {
+      if (s.grid_uniform) {
+        const double di0 = (double)i0, halfstep = 0.5 * s.step;
 #pragma unroll
-      for (int k = 0; k < kPPT; k++) {
-        int i = i0 + k;
-        dh[k] = (i < G) ? kC_KMS / H_of_z<FAM, DE>(s, c, grid_z(s, i)) : 0.0;
-      }
-      if (i0 < G) {
-        double2* dst = reinterpret_cast<double2*>(&sm.dh[pad_idx(i0)]);
-#pragma unroll
-        for (int k = 0; k < kPPT / 2; k++) dst[k] = make_double2(dh[2 * k], dh[2 * k + 1]);
-      }
-    }
-    // scalar fits run on the last thread while the others finish their grid points
-    if (tid == kS12Threads - 1 && (need_cmb || need_rd)) {
-      double obh2 = c.obh2;
-      double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
-      sm.scal[0] = need_cmb ? z_star_fit(s.k, obh2, wm) : 0.0;
-      sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
-    }
-    __syncthreads();
-
-    if (need_grid) {
-      double nxt = (i0 + kPPT < G) ? sm.dh[pad_idx(i0 + kPPT)] : 0.0;
-      double pre[kPPT];
-      double run = 0.0;
-#pragma unroll
-      for (int k = 0; k < kPPT; k++) {
-        int i = i0 + k;
-        pre[k] = run;
-        double d1 = (k + 1 < kPPT) ? dh[(k + 1) % kPPT] : nxt;
-        if (i + 1 < G) {
-          double dz = grid_z(s, i + 1) - grid_z(s, i);
-          run += ((dh[k] + d1) / 2) * dz;
+        for (int k = 0; k <= kPPT; k++) {
+          const double z = (di0 + (double)k) * s.step;  // == np.linspace node bits ((double)(i0+k) is exact)
+          dh[k] = DH_of_z<FAM, DE>(s, c, z);
         }
+#pragma unroll
+        for (int k = 0; k < kPPT; k++)
+          if (i0 + k + 1 < G) run = fma(dh[k] + dh[k + 1], halfstep, run);
+      } else {
+#pragma unroll
+        for (int k = 0; k <= kPPT; k++) dh[k] = (i0 + k < G) ? DH_of_z<FAM, DE>(s, c, __ldg(s.z_grid + i0 + k)) : 0.0;
+#pragma unroll
+        for (int k = 0; k < kPPT; k++)
+          if (i0 + k + 1 < G) run += ((dh[k] + dh[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
       }
       // block-exclusive scan of the per-thread totals
       double inc = run;
@@ -310,13 +350,43 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         if (lane >= o) inc += t;
       }
       if (lane == 31) sm.wsum[warp] = inc;
-      __syncthreads();
-      double off = inc - run;
+      run = inc - run;  // exclusive prefix within the warp
+    }
+    // scalar work on the last thread while the others finish their grid points
+    if (tid == kS12Threads - 1) {
+      if (need_cmb || need_rd) {
+        double obh2 = c.obh2;
+        double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
+        sm.scal[0] = need_cmb ? z_star_fit(s.k, obh2, wm) : 0.0;
+        sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
+      }
+      if (s.vel_pm1) {  // step template: only two distinct 1/(1+z_pec) per theta (sn/pantheon.py:46-48)
+        double z_pec = (s.vel_scale * th[s.col_vel[0]]) / kC_KMS;
+        sm.scal[2] = 1.0 / (1.0 + z_pec);
+        sm.scal[3] = 1.0 / (1.0 - z_pec);
+      }
+    }
+    __syncthreads();
+
+    if (need_grid) {
+      double off = run;
       for (int w = 0; w < warp; w++) off += sm.wsum[w];
       if (i0 < G) {
-        double2* dst = reinterpret_cast<double2*>(&sm.cum[pad_idx(i0)]);
+        double2* dst = &sm.gd[pad_idx(i0)];
+        if (s.grid_uniform) {
+          const double halfstep = 0.5 * s.step;
 #pragma unroll
-        for (int k = 0; k < kPPT / 2; k++) dst[k] = make_double2(off + pre[2 * k], off + pre[2 * k + 1]);
+          for (int k = 0; k < kPPT; k++) {
+            dst[k] = make_double2(off, dh[k]);
+            off = fma(dh[k] + dh[k + 1], halfstep, off);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kPPT; k++) {
+            dst[k] = make_double2(off, dh[k]);
+            if (i0 + k + 1 < G) off += ((dh[k] + dh[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
+          }
+        }
       }
       __syncthreads();
     }
@@ -325,8 +395,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (a.mode == MODE_DIST) {
       for (int q = tid; q < a.nq; q += kS12Threads) {
         double z = a.zq[q];
-        if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.cum, sm.dh, z);
-        if (a.outDH) a.outDH[b * a.nq + q] = kC_KMS / H_of_z<FAM, DE>(s, c, z);
+        if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.gd, z);
+        if (a.outDH) a.outDH[b * a.nq + q] = DH_of_z<FAM, DE>(s, c, z);
       }
       __syncthreads();
       continue;
@@ -336,26 +406,40 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const int n_sn = s.n_sn;
     if ((a.mode == MODE_EVAL || a.mode == MODE_RESID) && n_sn > 0) {
       const double offset = (s.col_offset >= 0 && !a.zero_offset) ? th[s.col_offset] : 0.0;
-      double vamp[CL_MAX_VEL];
-#pragma unroll
-      for (int k = 0; k < CL_MAX_VEL; k++) vamp[k] = k < s.n_vel ? s.vel_scale * th[s.col_vel[k]] : 0.0;
       const int64_t ld = a.mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
-      for (int i = tid; i < n_sn; i += kS12Threads) {
-        double zq = __ldg(s.sn_zcmb + i);
-        if (s.n_vel > 0) {
+      const bool to_smem = s.sn_small && a.mode == MODE_EVAL;
+      const double2* __restrict__ pack = reinterpret_cast<const double2*>(s.sn_pack);
+      if (s.n_vel == 0 || s.vel_pm1) {
+        const double rp = sm.scal[2], rm = sm.scal[3];
+        const bool shift = s.n_vel > 0;
+        for (int i = tid; i < n_sn; i += kS12Threads) {
+          const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);  // {z_cmb, w}, {1+z_hel, obs}
           // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)): D_M(z_cmb) cancels
+          double zq = p0.x;
+          if (shift) zq = fma(1.0 + p0.x, p0.y > 0.0 ? rp : rm, -1.0);  // (1+z_cmb)/(1+z_pec) - 1
+          const double DM = hermite_dm(s, sm.gd, zq);
+          const double mu = fma(5.0, fast_log10(p1.x * DM, sm.logtab), 25.0);
+          const double d = (p1.y - offset) - mu;
+          if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
+        }
+      } else {
+        double vamp[CL_MAX_VEL];
+#pragma unroll
+        for (int k = 0; k < CL_MAX_VEL; k++) vamp[k] = k < s.n_vel ? s.vel_scale * th[s.col_vel[k]] : 0.0;
+        for (int i = tid; i < n_sn; i += kS12Threads) {
+          const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);
           double v_km_s = 0.0;
           for (int k = 0; k < s.n_vel; k++) v_km_s += vamp[k] * __ldg(s.sn_vel_w + (size_t)k * n_sn + i);
-          double z_pec = v_km_s / kC_KMS;
-          if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + zq) / (1.0 + z_pec);
-          else zq = fmax((1.0 + zq) * (1.0 + z_pec) - 1.0, 1e-8);
+          const double z_pec = v_km_s / kC_KMS;
+          double zq;
+          if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + p0.x) / (1.0 + z_pec);
+          else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
+          const double DM = hermite_dm(s, sm.gd, zq);
+          const double mu = fma(5.0, fast_log10(p1.x * DM, sm.logtab), 25.0);
+          const double d = (p1.y - offset) - mu;
+          if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
         }
-        double DM = hermite_dm(s, sm.cum, sm.dh, zq);
-        double mu = 25.0 + 5 * log10(__ldg(s.sn_zhelp1 + i) * DM);
-        double d = __ldg(s.sn_obs + i) - offset - mu;
-        if (s.sn_small && a.mode == MODE_EVAL) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d;
-        else Rrow[i] = d;
       }
     }
     if (a.mode == MODE_RESID) { __syncthreads(); continue; }
@@ -365,8 +449,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (do_bao && tid < s.n_bao) {
       double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : sm.scal[1]);
       double z = __ldg(s.bao_z + tid);
-      double DM = hermite_dm(s, sm.cum, sm.dh, z);
-      double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.dh, z) : kC_KMS / H_of_z<FAM, DE>(s, c, z);
+      double DM = hermite_dm(s, sm.gd, z);
+      double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.gd, z) : DH_of_z<FAM, DE>(s, c, z);
       int q = __ldg(s.bao_qty + tid);
       double v;
       if (q == CL_BAO_DV_OVER_RS) v = pow(z * DH * (DM * DM), 1.0 / 3) / rd;
@@ -391,7 +475,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       if (tid < s.n_gl) {
         double hw = zstar / 2.0;
         double z = hw * __ldg(s.gl_x + tid) + hw;
-        v[0] = __ldg(s.gl_w + tid) * (kC_KMS / H_of_z<FAM, DE>(s, c, z));
+        v[0] = __ldg(s.gl_w + tid) * DH_of_z<FAM, DE>(s, c, z);
       } else if (tid < 2 * s.n_gl) {
         int q = tid - s.n_gl;
         double a_lim = 1.0 / (1.0 + zstar);
@@ -399,7 +483,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         double av = hw * __ldg(s.gl_x + q) + hw;
         double z = (1.0 / av) - 1.0;
         double Rb = (3.0 / 4.0) * (c.obh2 / s.k.Ogamma_h2) * av;
-        v[1] = __ldg(s.gl_w + q) * (kC_KMS / (av * av * H_of_z<FAM, DE>(s, c, z) * sqrt(3.0 * (1.0 + Rb))));
+        v[1] = __ldg(s.gl_w + q) * (DH_of_z<FAM, DE>(s, c, z) / (av * av * sqrt(3.0 * (1.0 + Rb))));
       }
     }
     __syncthreads();  // sm.vec complete
@@ -428,6 +512,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         }
       }
     }
+    const double rd_out = (need_rd && tid == 0) ? sm.scal[1] : 0.0;
     block_sum<5>(v, sm.red);
 
     if (tid == 0) {
@@ -442,7 +527,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       if (a.mode == MODE_CMB) {
         double* r = a.out + b * 8;
         r[0] = cmbv[0]; r[1] = cmbv[1]; r[2] = cmbv[2]; r[3] = zstar; r[4] = rs; r[5] = dm;
-        r[6] = need_rd ? sm.scal[1] : 0.0; r[7] = 100 * (rs / dm);
+        r[6] = rd_out; r[7] = 100 * (rs / dm);
       } else {
         double chi2_cmb = 0.0;
         if (s.cmb_mode != CL_CMB_NONE) {
@@ -472,7 +557,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         a.aux[AUX_SN_SMALL * a.B + b] = v[4];
       }
     }
-    __syncthreads();
+    // (the two barriers inside block_sum order this iteration's shared-memory reads before the next writes)
   }
 }
 

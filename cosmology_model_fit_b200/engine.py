@@ -25,7 +25,7 @@ _LIB_NAME = "libcosmolike_b200.so"
 ABI_SYMBOLS = (
     "cl_create", "cl_destroy", "cl_last_error", "cl_eval", "cl_eval_device", "cl_eval_components",
     "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
-    "cl_launch_count", "cl_set_option", "cl_describe",
+    "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe",
 )
 
 
@@ -34,7 +34,7 @@ class EngineError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, _LIB_NAME)
+    return os.environ.get("COSMOLIKE_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 _lib = None
@@ -66,6 +66,7 @@ def load_library():
     lib.cl_cmb.argtypes = [ctxp, _dp, i64, i64, _dp]
     lib.cl_sn_residuals.argtypes = [ctxp, _dp, i64, i64, _dp]
     lib.cl_last_timing.argtypes = [ctxp, C.c_double * 4]
+    lib.cl_timing_history.argtypes = [ctxp, C.c_int, _dp]
     lib.cl_launch_count.argtypes = [ctxp]
     lib.cl_launch_count.restype = i64
     lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
@@ -222,6 +223,14 @@ class Engine:
         ms = (C.c_double * 4)()
         self._check(self.lib.cl_last_timing(self._ctx, ms))
         return {"stage12_ms": ms[0], "stage3_ms": ms[1], "finalize_ms": ms[2], "total_ms": ms[3]}
+
+    def timing_history(self, n):
+        """[k, 4] array (stage12, stage3, finalize, total ms) of the last k <= n evaluations, oldest first."""
+        buf = np.zeros((max(n, 1), 4))
+        k = self.lib.cl_timing_history(self._ctx, int(n), _p(buf))
+        if k < 0:
+            self._check(k)
+        return buf[:k]
 
     def launch_count(self):
         return int(self.lib.cl_launch_count(self._ctx))

@@ -199,8 +199,9 @@ const char* cl_last_error(const cl_ctx* ctx); /* ctx may be NULL for errors of c
  * H2D and D2H copies go through the context's pinned staging buffers; returns after the result is in out. */
 int cl_eval(cl_ctx* ctx, const double* theta, int64_t B, int64_t ld, int what, double* out);
 
-/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t cast to void*, NULL = the context's
- * own stream).  The caller synchronises. */
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t cast to void*; NULL = the context's
+ * own non-blocking stream — pass cudaStreamLegacy (0x1) to target the legacy default stream).  The caller
+ * synchronises.  One stream at a time per context: the workspace is shared between calls. */
 int cl_eval_device(cl_ctx* ctx, const double* d_theta, int64_t B, int64_t ld, int what, double* d_out, void* stream);
 
 /* chi2 components, host memory: out[B][4] = (sn, bao, cmb, cc+gaussian)
@@ -232,6 +233,9 @@ int cl_sn_residuals(cl_ctx* ctx, const double* theta, int64_t B, int64_t ld, dou
  * ms[0] stage 1+2 (Friedmann distances + residuals), ms[1] stage 3 (chi-squared GEMM), ms[2] finalize,
  * ms[3] total device time incl. copies for cl_eval.  Blocks until the events have completed. */
 int cl_last_timing(cl_ctx* ctx, double ms[4]);
+/* Same for the most recent n evaluations (the library keeps the last 64), oldest first: ms[i][4].
+ * Returns the number of entries written (<= n) or a negative error. */
+int cl_timing_history(cl_ctx* ctx, int n, double* ms);
 /* Number of kernels this library launched on the context since creation. */
 int64_t cl_launch_count(const cl_ctx* ctx);
 
