@@ -325,7 +325,7 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
     for (int j = 0; j < 128; j++) {
       double inv = (double)(1.0L / (1.0L + ((long double)j + 0.5L) / 128.0L));
       tab[2 * j] = inv;
-      tab[2 * j + 1] = (double)(-log10l((long double)inv));
+      tab[2 * j + 1] = (double)(-5.0L * log10l((long double)inv));
     }
     const double* dtab = nullptr;
     TRY(upload(c, tab.data(), tab.size(), &dtab));
@@ -350,6 +350,18 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
       pack[4 * i + 3] = s.sn_obs[i];
     }
     TRY(upload(c, pack.data(), pack.size(), &d.sn_pack));
+    {
+      std::vector<double> zs((size_t)n * 2), obsp(n);
+      for (int i = 0; i < n; i++) {
+        zs[2 * i] = pm1 ? 1.0 + s.sn_zcmb[i] : s.sn_zcmb[i];
+        zs[2 * i + 1] = pm1 ? s.sn_vel_weight[i] : 0.0;
+        obsp[i] = (double)((long double)s.sn_obs[i] - 25.0L - 5.0L * log10l(1.0L + (long double)s.sn_zhel[i]));
+      }
+      const double* dz = nullptr;
+      TRY(upload(c, zs.data(), zs.size(), &dz));
+      d.sn_zs = reinterpret_cast<const double2*>(dz);
+      TRY(upload(c, obsp.data(), obsp.size(), &d.sn_obsp));
+    }
     if (s.n_vel > 0) TRY(upload(c, s.sn_vel_weight, (size_t)n * s.n_vel, &d.sn_vel_w));
     // factor handling
     std::vector<double> Lbuf;

@@ -30,9 +30,11 @@ struct DevSpec {
   // SN block
   int n_sn, sn_small, sn_form, col_offset, n_vel, vel_mode, vel_pm1;
   int col_vel[CL_MAX_VEL];
-  const double* sn_pack;   // [n_sn][4] = {z_cmb, first velocity-template weight, 1 + z_hel, obs}
+  const double* sn_pack;   // [n_sn][4] = {z_cmb, first velocity-template weight, 1 + z_hel, obs} (general path)
+  const double2* sn_zs;    // [n_sn] {1 + z_cmb, w} with a +-1 step template, {z_cmb, 0} without one (fast path)
+  const double* sn_obsp;   // [n_sn] obs - 25 - 5 log10(1 + z_hel)
   const double *sn_vel_w, *sn_mat_small;
-  const double2* logtab;   // [128] {1/c_j, log10(c_j)} for fast_log10
+  const double2* logtab;   // [128] {1/c_j, log10(c_j)} for fast_5log10 (second entry scaled by 5)
   double vel_scale;
   // BAO block
   int n_bao, dh_mode, rd_mode, col_rd;

@@ -58,7 +58,31 @@ __device__ __forceinline__ void unpack(const DevSpec& s, const double* __restric
   }
 }
 
-__device__ __forceinline__ double fast_sqrt(double x) { return x * rsqrt(x); }  // x > 0, <= 2 ulp
+// ---- shared-memory access by 32-bit shared-window offset (keeps address arithmetic out of the generic space) ----
+__device__ __forceinline__ uint32_t s12_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_d2(uint32_t addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+
+// 1/sqrt(x) for normal positive x: MUFU.RSQ64H seed + one third-order correction (the sequence CUDA's rsqrt() uses,
+// without its special-case branch); <= 1 ulp
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-x, y0 * y0, 1.0);
+  return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+__device__ __forceinline__ double fast_sqrt(double x) { return x * rsqrt_pos(x); }  // x > 0, <= 2 ulp
+
+// 5 log10(x) = 5 e log10(2) + 5 log10(c_j) + 5 log1p(r)/ln 10 coefficients, k = 1..7: (-1)^(k+1) 5 / (k ln 10)
+__constant__ double kLog5Poly[8] = {0.0, 2.171472409516259, -1.0857362047581296, 0.7238241365054197, -0.5428681023790648,
+                                    0.4342944819032518, -0.36191206825270983, 0.3102103442166084};
+__constant__ double kLog5Two[2] = {1.5051499791443348 /* 30-bit head of 5 log10(2): e*head is exact */, -8.244288170221258e-10};
 
 // 5-node massive-neutrino density (cmb/data_planck_act_compression.py:53-66)
 __device__ __forceinline__ double omnu_z(const cl_cmb_consts& k, double zp1) {
@@ -84,8 +108,7 @@ __device__ __forceinline__ double fde(const Cosmo& c, double z, double zp1, doub
 
 // E(z)^2 = (H/H0)^2 (sn/pantheon.py:28-31 late family, bao/desi_cmb_union3.py:37-57 full family)
 template <int FAM, int DE>
-__device__ __forceinline__ double E2_of_z(const DevSpec& s, const Cosmo& c, double z) {
-  double zp1 = 1.0 + z;
+__device__ __forceinline__ double E2_of_zp1(const DevSpec& s, const Cosmo& c, double z, double zp1) {
   double cubed = zp1 * zp1 * zp1;
   if (FAM == CL_FAMILY_LATE) {
     double de = (DE == CL_DE_LCDM) ? (1.0 - c.Om) : (1.0 - c.Om) * fde<DE>(c, z, zp1, cubed);
@@ -98,8 +121,12 @@ __device__ __forceinline__ double E2_of_z(const DevSpec& s, const Cosmo& c, doub
   return radiation + matter + de + neutrino;
 }
 template <int FAM, int DE>
+__device__ __forceinline__ double E2_of_z(const DevSpec& s, const Cosmo& c, double z) {
+  return E2_of_zp1<FAM, DE>(s, c, z, 1.0 + z);
+}
+template <int FAM, int DE>
 __device__ __forceinline__ double DH_of_z(const DevSpec& s, const Cosmo& c, double z) {  // c / H(z)
-  return c.K * rsqrt(E2_of_z<FAM, DE>(s, c, z));
+  return c.K * rsqrt_pos(E2_of_z<FAM, DE>(s, c, z));
 }
 template <int FAM, int DE>
 __device__ __forceinline__ double H_of_z(const DevSpec& s, const Cosmo& c, double z) {
@@ -111,27 +138,20 @@ __device__ __forceinline__ double grid_z(const DevSpec& s, int i) {
   return __ldg(s.z_grid + i);
 }
 
-// log10(x) for normal positive x: x = 2^e m, m in [1,2); table entry j = top 7 mantissa bits holds
-// {1/c_j rounded, -log10 of that rounded value}; log10(m) = log10(m/c_j) + log10(c_j) with |m/c_j - 1| < 2^-8.
-__device__ __forceinline__ double fast_log10(double x, const double2* __restrict__ tab) {
-  if (!(x >= 2.2250738585072014e-308 && x < INFINITY)) return log10(x);  // zero, negative, subnormal, inf, nan
+// 5 log10(x) for normal positive x: x = 2^e m, m in [1,2); table entry j = top 7 mantissa bits holds
+// {fl(1/c_j), -5 log10 of that rounded value}; log10(m) = log10(m/c_j) + log10(c_j) with |m/c_j - 1| < 2^-8.
+// `tab` is the 32-bit shared-memory address of the table.
+__device__ __forceinline__ double fast_5log10(double x, uint32_t tab) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int e = (hi >> 20) - 1023;
+  const double ed = (double)((hi >> 20) - 1023);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const double2 tc = tab[(hi >> 13) & 127];
+  const double2 tc = lds_d2(tab + (((uint32_t)hi >> 9) & 0x7f0u));  // 16 bytes per entry, index = (hi >> 13) & 127
   const double r = fma(m, tc.x, -1.0);
-  // log1p(r)/ln(10) = r (c1 + c2 r + ... + c7 r^6), c_k = (-1)^(k+1) / (k ln 10)
-  double p = 0.062042069733182864;           //  1/(7 ln10)
-  p = fma(p, r, -0.072382414688713337);      // -1/(6 ln10)
-  p = fma(p, r, 0.086858896380650366);       //  1/(5 ln10)
-  p = fma(p, r, -0.10857362047581296);       // -1/(4 ln10)
-  p = fma(p, r, 0.14476482730108395);        //  1/(3 ln10)
-  p = fma(p, r, -0.21714724095162591);       // -1/(2 ln10)
-  p = fma(p, r, 0.43429448190325182);        //  1/ln10
-  const double ed = (double)e;
-  // log10(2) = hi + lo with hi exact in 32 bits so that e*hi is exact
-  double res = fma(ed, 0.30102999566406652, tc.y);
-  res = fma(ed, -8.5323443170571066e-14, res);
+  double p = kLog5Poly[7];
+#pragma unroll
+  for (int k = 6; k >= 1; k--) p = fma(p, r, kLog5Poly[k]);
+  double res = fma(ed, kLog5Two[0], tc.y);
+  res = fma(ed, kLog5Two[1], res);
   return fma(r, p, res);
 }
 
@@ -144,20 +164,21 @@ __device__ __forceinline__ double hermite_seg(double y0, double hd0, double y1, 
 }
 
 // D_M(xq): cubic Hermite with analytic node derivatives y' = dh (interp_hermite, interpolator.py:71-108,117-119);
-// linear extrapolation with the end slope outside the grid
+// linear extrapolation with the end slope outside the grid.  gd[] holds {D_M, hscale * dh} per node (hscale = step
+// on the np.linspace grid, 1 otherwise).  This is the general (any redshift, any grid) form; the SN loop has its own
+// in-range fast path.
 __device__ __forceinline__ double hermite_dm(const DevSpec& s, const double2* __restrict__ gd, double xq) {
   const int G = s.G;
   if (s.grid_uniform) {
     if (xq > 0.0 && xq < s.z_last) {
-      const double u = xq * s.inv_step;
-      const int i = min((int)u, G - 2);
+      const int i = min((int)(xq * s.inv_step), G - 2);
       const double t = fma(xq, s.inv_step, -(double)i);
       const double2 a = gd[pad_idx(i)], b = gd[pad_idx(i + 1)];
-      return hermite_seg(a.x, s.step * a.y, b.x, s.step * b.y, t);
+      return hermite_seg(a.x, a.y, b.x, b.y, t);
     }
-    if (xq <= 0.0) { const double2 a = gd[0]; return a.x + a.y * xq; }
+    if (xq <= 0.0) { const double2 a = gd[0]; return a.x + (a.y * s.inv_step) * xq; }
     const double2 b = gd[pad_idx(G - 1)];
-    return b.x + b.y * (xq - s.z_last);
+    return b.x + (b.y * s.inv_step) * (xq - s.z_last);
   }
   const double x0 = __ldg(s.z_grid), xn = __ldg(s.z_grid + G - 1);
   if (xq <= x0) { const double2 a = gd[0]; return a.x + a.y * (xq - x0); }
@@ -179,7 +200,8 @@ __device__ __forceinline__ double sgn(double v) { return (double)((v > 0) - (v <
 __device__ double pchip_slope(const DevSpec& s, const double2* __restrict__ gd, int j) {
   const int n = s.G;
   auto H = [&](int i) { return grid_z(s, i + 1) - grid_z(s, i); };
-  auto D = [&](int i) { return (gd[pad_idx(i + 1)].y - gd[pad_idx(i)].y) / H(i); };
+  const double ih = s.grid_uniform ? s.inv_step : 1.0;
+  auto D = [&](int i) { return (gd[pad_idx(i + 1)].y * ih - gd[pad_idx(i)].y * ih) / H(i); };
   if (j == 0) {
     double h0 = H(0), h1 = H(1), d0 = D(0), d1 = D(1);
     double v = ((2 * h0 + h1) * d0 - h0 * d1) / (h0 + h1);
@@ -206,8 +228,9 @@ __device__ double pchip_slope(const DevSpec& s, const double2* __restrict__ gd, 
 // per theta use this, so it follows the reference formulas literally.
 __device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, double xq) {
   const int G = s.G;
-  if (xq <= grid_z(s, 0)) return gd[0].y;
-  if (xq >= grid_z(s, G - 1)) return gd[pad_idx(G - 1)].y;
+  const double ih = s.grid_uniform ? s.inv_step : 1.0;
+  if (xq <= grid_z(s, 0)) return gd[0].y * ih;
+  if (xq >= grid_z(s, G - 1)) return gd[pad_idx(G - 1)].y * ih;
   int lo = 0, hi = G;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -220,7 +243,7 @@ __device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, dou
   double t2 = t * t, t3 = t2 * t;
   double h00 = 2 * t3 - 3 * t2 + 1, h10 = t3 - 2 * t2 + t, h01 = -2 * t3 + 3 * t2, h11 = t3 - t2;
   double d0 = pchip_slope(s, gd, i), d1 = pchip_slope(s, gd, i + 1);
-  return h00 * gd[pad_idx(i)].y + h10 * h_i * d0 + h01 * gd[pad_idx(i + 1)].y + h11 * h_i * d1;
+  return h00 * (gd[pad_idx(i)].y * ih) + h10 * h_i * d0 + h01 * (gd[pad_idx(i + 1)].y * ih) + h11 * h_i * d1;
 }
 
 // closed-form fits (cmb/data_planck_act_compression.py:86-124)
@@ -272,7 +295,7 @@ struct S12Smem {
   double wsum[8];
   double red[5 * 8];
   double vec[CL_MAX_BAO + CL_MAX_CC + CL_SN_SMALL_MAX];
-  double scal[4];  // z*, r_drag, 1/(1+z_pec) for w=+1, for w=-1
+  double scal[4];  // z*, r_drag, mean and half-difference of 1/(1 +- z_pec)
 };
 
 template <int FAM, int DE>
@@ -282,8 +305,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = s.G;
-  if (tid < 128) sm.logtab[tid] = s.logtab[tid];
-  // (visible after the first __syncthreads of the loop body)
+  if (tid < 128) sm.logtab[tid] = s.logtab[tid];  // visible after the first __syncthreads of the loop body
+  const uint32_t gd_addr = s12_smem_u32(sm.gd), tab_addr = s12_smem_u32(sm.logtab);
 
   for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
     const double* __restrict__ th = a.theta + b * a.ld;
@@ -320,27 +343,34 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const bool need_rd = s.rd_mode == CL_RD_FIT && ((a.mode == MODE_EVAL && s.n_bao > 0) || a.mode == MODE_BAO || a.mode == MODE_CMB);
 
     // ================= stage 1: dh = c/H on the grid, cumulative trapezoid =================
-    // thread t owns nodes [16t, 16t+16) and the 16 intervals that start at them (it also evaluates node 16t+16)
-    double dh[kPPT + 1];
+    // thread t owns nodes [16t, 16t+16) and the 16 intervals that start at them (it also evaluates node 16t+16);
+    // hd[k] = hscale * dh(node) with hscale = step on the np.linspace grid (the Hermite segment wants h * slope)
+    double hd[kPPT + 1];
     double run = 0.0;
     const int i0 = tid * kPPT;
+    const bool full_chunk = i0 + kPPT < G;  // all 17 nodes inside the grid
     if (need_grid) {
       if (s.grid_uniform) {
-        const double di0 = (double)i0, halfstep = 0.5 * s.step;
+        const double dk0 = (double)i0, Ks = c.K * s.step;
 #pragma unroll
         for (int k = 0; k <= kPPT; k++) {
-          const double z = (di0 + (double)k) * s.step;  // == np.linspace node bits ((double)(i0+k) is exact)
-          dh[k] = DH_of_z<FAM, DE>(s, c, z);
+          const double zp1 = fma(dk0 + (double)k, s.step, 1.0);  // 1 + z_grid[i0+k] (the integer sum is exact)
+          hd[k] = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1 - 1.0, zp1));
         }
+        if (full_chunk) {
 #pragma unroll
-        for (int k = 0; k < kPPT; k++)
-          if (i0 + k + 1 < G) run = fma(dh[k] + dh[k + 1], halfstep, run);
+          for (int k = 0; k < kPPT; k++) run = fma(hd[k] + hd[k + 1], 0.5, run);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kPPT; k++)
+            if (i0 + k + 1 < G) run = fma(hd[k] + hd[k + 1], 0.5, run);
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k <= kPPT; k++) dh[k] = (i0 + k < G) ? DH_of_z<FAM, DE>(s, c, __ldg(s.z_grid + i0 + k)) : 0.0;
+        for (int k = 0; k <= kPPT; k++) hd[k] = (i0 + k < G) ? DH_of_z<FAM, DE>(s, c, __ldg(s.z_grid + i0 + k)) : 0.0;
 #pragma unroll
         for (int k = 0; k < kPPT; k++)
-          if (i0 + k + 1 < G) run += ((dh[k] + dh[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
+          if (i0 + k + 1 < G) run += ((hd[k] + hd[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
       }
       // block-exclusive scan of the per-thread totals
       double inc = run;
@@ -361,9 +391,10 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
       }
       if (s.vel_pm1) {  // step template: only two distinct 1/(1+z_pec) per theta (sn/pantheon.py:46-48)
-        double z_pec = (s.vel_scale * th[s.col_vel[0]]) / kC_KMS;
-        sm.scal[2] = 1.0 / (1.0 + z_pec);
-        sm.scal[3] = 1.0 / (1.0 - z_pec);
+        const double z_pec = (s.vel_scale * th[s.col_vel[0]]) / kC_KMS;
+        const double rp = 1.0 / (1.0 + z_pec), rm = 1.0 / (1.0 - z_pec);
+        sm.scal[2] = 0.5 * (rp + rm);  // 1/(1 + w z_pec) = scal[2] + w scal[3] for w = +-1
+        sm.scal[3] = 0.5 * (rp - rm);
       }
     }
     __syncthreads();
@@ -372,19 +403,18 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       double off = run;
       for (int w = 0; w < warp; w++) off += sm.wsum[w];
       if (i0 < G) {
-        double2* dst = &sm.gd[pad_idx(i0)];
+        const uint32_t dst = gd_addr + (uint32_t)pad_idx(i0) * 16u;
         if (s.grid_uniform) {
-          const double halfstep = 0.5 * s.step;
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
-            dst[k] = make_double2(off, dh[k]);
-            off = fma(dh[k] + dh[k + 1], halfstep, off);
+            sts_d2(dst + 16u * k, off, hd[k]);
+            off = fma(hd[k] + hd[k + 1], 0.5, off);
           }
         } else {
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
-            dst[k] = make_double2(off, dh[k]);
-            if (i0 + k + 1 < G) off += ((dh[k] + dh[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
+            sts_d2(dst + 16u * k, off, hd[k]);
+            if (i0 + k + 1 < G) off += ((hd[k] + hd[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
           }
         }
       }
@@ -409,34 +439,55 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       const int64_t ld = a.mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
       const bool to_smem = s.sn_small && a.mode == MODE_EVAL;
-      const double2* __restrict__ pack = reinterpret_cast<const double2*>(s.sn_pack);
-      if (s.n_vel == 0 || s.vel_pm1) {
-        const double rp = sm.scal[2], rm = sm.scal[3];
+      if (s.grid_uniform && (s.n_vel == 0 || s.vel_pm1)) {
+        // fast path.  Static per-SN operands: zs = {1 + z_cmb, w} (or {z_cmb, 0} without a velocity template) and
+        // obsp = obs - 25 - 5 log10(1 + z_hel), so that delta = obsp - offset - 5 log10 D_M(z_cosmo):
+        // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)), D_M(z_cmb) cancels.
         const bool shift = s.n_vel > 0;
-        for (int i = tid; i < n_sn; i += kS12Threads) {
-          const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);  // {z_cmb, w}, {1+z_hel, obs}
-          // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)): D_M(z_cmb) cancels
-          double zq = p0.x;
-          if (shift) zq = fma(1.0 + p0.x, p0.y > 0.0 ? rp : rm, -1.0);  // (1+z_cmb)/(1+z_pec) - 1
-          const double DM = hermite_dm(s, sm.gd, zq);
-          const double mu = fma(5.0, fast_log10(p1.x * DM, sm.logtab), 25.0);
-          const double d = (p1.y - offset) - mu;
+        const double ravg = sm.scal[2], rdif = sm.scal[3];
+        const double inv_step = s.inv_step, z_last = s.z_last;
+        const int imax = G - 2;
+        const double2* __restrict__ zsp = s.sn_zs;
+        const double* __restrict__ obp = s.sn_obsp;
+        int i = tid;
+        double2 zs = i < n_sn ? __ldg(zsp + i) : make_double2(1.0, 0.0);
+        double ob = i < n_sn ? __ldg(obp + i) : 0.0;
+        while (i < n_sn) {
+          const int inext = i + kS12Threads;
+          const double2 zs_n = inext < n_sn ? __ldg(zsp + inext) : make_double2(1.0, 0.0);  // prefetch: L1 is all smem
+          const double ob_n = inext < n_sn ? __ldg(obp + inext) : 0.0;
+          const double zq = shift ? fma(zs.x, fma(zs.y, rdif, ravg), -1.0) : zs.x;  // (1+z_cmb)/(1+z_pec) - 1
+          double dl5;
+          if (zq > 1e-9 && zq < z_last) {
+            const int j = min((int)(zq * inv_step), imax);
+            const double t = fma(zq, inv_step, -(double)j);
+            const double2 n0 = lds_d2(gd_addr + (uint32_t)pad_idx(j) * 16u);
+            const double2 n1 = lds_d2(gd_addr + (uint32_t)pad_idx(j + 1) * 16u);
+            dl5 = fast_5log10(hermite_seg(n0.x, n0.y, n1.x, n1.y, t), tab_addr);
+          } else {
+            dl5 = 5.0 * log10(hermite_dm(s, sm.gd, zq));
+          }
+          const double d = (ob - offset) - dl5;
           if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
+          i = inext; zs = zs_n; ob = ob_n;
         }
       } else {
+        const double2* __restrict__ pack = reinterpret_cast<const double2*>(s.sn_pack);
         double vamp[CL_MAX_VEL];
 #pragma unroll
         for (int k = 0; k < CL_MAX_VEL; k++) vamp[k] = k < s.n_vel ? s.vel_scale * th[s.col_vel[k]] : 0.0;
         for (int i = tid; i < n_sn; i += kS12Threads) {
-          const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);
-          double v_km_s = 0.0;
-          for (int k = 0; k < s.n_vel; k++) v_km_s += vamp[k] * __ldg(s.sn_vel_w + (size_t)k * n_sn + i);
-          const double z_pec = v_km_s / kC_KMS;
-          double zq;
-          if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + p0.x) / (1.0 + z_pec);
-          else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
+          const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);  // {z_cmb, w0}, {1+z_hel, obs}
+          double zq = p0.x;
+          if (s.n_vel > 0) {
+            double v_km_s = 0.0;
+            for (int k = 0; k < s.n_vel; k++) v_km_s += vamp[k] * __ldg(s.sn_vel_w + (size_t)k * n_sn + i);
+            const double z_pec = v_km_s / kC_KMS;
+            if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + p0.x) / (1.0 + z_pec);
+            else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
+          }
           const double DM = hermite_dm(s, sm.gd, zq);
-          const double mu = fma(5.0, fast_log10(p1.x * DM, sm.logtab), 25.0);
+          const double mu = 25.0 + 5 * log10(p1.x * DM);
           const double d = (p1.y - offset) - mu;
           if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
         }
@@ -513,7 +564,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       }
     }
     const double rd_out = (need_rd && tid == 0) ? sm.scal[1] : 0.0;
-    block_sum<5>(v, sm.red);
+    if (need_cmb || s.n_bao > 0 || s.n_cc > 0 || s.sn_small) block_sum<5>(v, sm.red);
+    else __syncthreads();  // orders this iteration's shared-memory reads before the next iteration's writes
 
     if (tid == 0) {
       double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
