@@ -51,7 +51,7 @@ struct cl_ctx {
   double *h_theta = nullptr, *h_out = nullptr;  // pinned
   int64_t h_theta_cap = 0, h_out_cap = 0;
   int64_t launches = 0;
-  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1;
+  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0;
   std::string err, desc;
   std::mutex mu;
 };
@@ -461,6 +461,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "max_rows_per_pass") { if (value < 128) return fail(c, CL_E_INVALID, "max_rows_per_pass must be >= 128"); c->max_rows = value; return CL_OK; }
   if (n == "gemm_ctas") { c->opt_gemm_ctas = (int)value; return CL_OK; }
   if (n == "stage12_ctas") { c->opt_s12_ctas = (int)value; return CL_OK; }
+  if (n == "dbg") { c->opt_dbg = (int)value; return CL_OK; }
   if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }
   return fail(c, CL_E_INVALID, "unknown option %s", name);
 }
@@ -528,7 +529,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   const bool large = c->d_W != nullptr;
   Stage12Args a{};
   a.theta = d_theta; a.B = rows; a.ld = ld; a.mode = MODE_EVAL; a.what = moments ? CL_OUT_CHI2 : what;
-  a.R = c->d_R; a.ldR = c->ldR; a.aux = c->d_aux; a.zero_offset = moments ? 1 : 0;
+  a.R = c->d_R; a.ldR = c->ldR; a.aux = c->d_aux; a.zero_offset = moments ? 1 : 0; a.dbg = c->opt_dbg;
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
   rc = launch_s12(c, a, st);
   if (rc != CL_OK) return rc;

@@ -62,6 +62,7 @@ struct Stage12Args {
   const double* theta;  // [B][ld]
   int64_t B, ld;
   int mode, what;
+  int dbg;              // profiling experiments: bit0 skip the grid pass, bit1 skip the SN loop (results invalid)
   int zero_offset;      // moments mode: residuals with the magnitude offset set to 0
   double* R;            // MODE_EVAL: residual rows [B][ldR]; MODE_RESID: [B][n_sn]
   int64_t ldR;

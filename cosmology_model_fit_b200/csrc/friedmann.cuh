@@ -36,28 +36,6 @@ struct Cosmo {
   double H0, h, K /* c/H0 */, Om, Or, Obc, Onu, Ode, obh2, och2, w0, wa;
 };
 
-__device__ __forceinline__ void unpack(const DevSpec& s, const double* __restrict__ th, Cosmo& c) {
-  c.H0 = s.col_H0 >= 0 ? s.H0_scale * th[s.col_H0] : s.H0_fixed;
-  c.h = c.H0 / 100;
-  c.K = kC_KMS / c.H0;
-  c.w0 = s.col_w0 >= 0 ? th[s.col_w0] : -1.0;
-  c.wa = s.col_wa >= 0 ? th[s.col_wa] : 0.0;
-  c.Om = c.Or = c.Obc = c.Onu = c.Ode = c.obh2 = c.och2 = 0.0;
-  if (s.family == CL_FAMILY_LATE) {
-    c.Om = th[s.col_Om];
-    if (s.Om_is_physical) c.Om = c.Om / (c.h * c.h);
-    if (s.col_obh2 >= 0) c.obh2 = th[s.col_obh2];
-  } else {
-    double h2 = c.h * c.h;
-    c.obh2 = th[s.col_obh2];
-    c.och2 = th[s.col_och2];
-    c.Onu = s.k.Omnu_h2 / h2;
-    c.Or = s.k.Or_h2 / h2;
-    c.Obc = (c.obh2 + c.och2) / h2;
-    c.Ode = 1.0 - c.Obc - c.Or - c.Onu;
-  }
-}
-
 // ---- shared-memory access by 32-bit shared-window offset (keeps address arithmetic out of the generic space) ----
 __device__ __forceinline__ uint32_t s12_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double2 lds_d2(uint32_t addr) {
@@ -78,6 +56,35 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
   return fma(fma(e, 0.375, 0.5), y0 * e, y0);
 }
 __device__ __forceinline__ double fast_sqrt(double x) { return x * rsqrt_pos(x); }  // x > 0, <= 2 ulp
+// 1/x for normal positive x: MUFU.RCP64H seed, then y0 (1 + e + e^2) with e = 1 - x y0; <= 1 ulp
+__device__ __forceinline__ double rcp_pos(double x) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-x, y0, 1.0);
+  return fma(y0, fma(e, e, e), y0);
+}
+
+__device__ __forceinline__ void unpack(const DevSpec& s, const double* __restrict__ th, Cosmo& c) {
+  c.H0 = s.col_H0 >= 0 ? s.H0_scale * th[s.col_H0] : s.H0_fixed;
+  c.h = c.H0 / 100;
+  c.K = kC_KMS * rcp_pos(c.H0);  // c/H0 to 1 ulp
+  c.w0 = s.col_w0 >= 0 ? th[s.col_w0] : -1.0;
+  c.wa = s.col_wa >= 0 ? th[s.col_wa] : 0.0;
+  c.Om = c.Or = c.Obc = c.Onu = c.Ode = c.obh2 = c.och2 = 0.0;
+  if (s.family == CL_FAMILY_LATE) {
+    c.Om = th[s.col_Om];
+    if (s.Om_is_physical) c.Om = c.Om / (c.h * c.h);
+    if (s.col_obh2 >= 0) c.obh2 = th[s.col_obh2];
+  } else {
+    double h2 = c.h * c.h;
+    c.obh2 = th[s.col_obh2];
+    c.och2 = th[s.col_och2];
+    c.Onu = s.k.Omnu_h2 / h2;
+    c.Or = s.k.Or_h2 / h2;
+    c.Obc = (c.obh2 + c.och2) / h2;
+    c.Ode = 1.0 - c.Obc - c.Or - c.Onu;
+  }
+}
 
 // 5 log10(x) = 5 e log10(2) + 5 log10(c_j) + 5 log1p(r)/ln 10 coefficients, k = 1..7: (-1)^(k+1) 5 / (k ln 10)
 __constant__ double kLog5Poly[8] = {0.0, 2.171472409516259, -1.0857362047581296, 0.7238241365054197, -0.5428681023790648,
@@ -167,22 +174,24 @@ __device__ __forceinline__ double hermite_seg(double y0, double hd0, double y1, 
 // linear extrapolation with the end slope outside the grid.  gd[] holds {D_M, hscale * dh} per node (hscale = step
 // on the np.linspace grid, 1 otherwise).  This is the general (any redshift, any grid) form; the SN loop has its own
 // in-range fast path.
-__device__ __forceinline__ double hermite_dm(const DevSpec& s, const double2* __restrict__ gd, double xq) {
+__device__ __forceinline__ double hermite_dm(const DevSpec& s, const double2* __restrict__ gdraw,
+                                             const double* __restrict__ off, double xq) {
   const int G = s.G;
+  auto node = [&](int i) { double2 v = gdraw[pad_idx(i)]; v.x += off[i >> 4]; return v; };
   if (s.grid_uniform) {
     if (xq > 0.0 && xq < s.z_last) {
       const int i = min((int)(xq * s.inv_step), G - 2);
       const double t = fma(xq, s.inv_step, -(double)i);
-      const double2 a = gd[pad_idx(i)], b = gd[pad_idx(i + 1)];
+      const double2 a = node(i), b = node(i + 1);
       return hermite_seg(a.x, a.y, b.x, b.y, t);
     }
-    if (xq <= 0.0) { const double2 a = gd[0]; return a.x + (a.y * s.inv_step) * xq; }
-    const double2 b = gd[pad_idx(G - 1)];
+    if (xq <= 0.0) { const double2 a = node(0); return a.x + (a.y * s.inv_step) * xq; }
+    const double2 b = node(G - 1);
     return b.x + (b.y * s.inv_step) * (xq - s.z_last);
   }
   const double x0 = __ldg(s.z_grid), xn = __ldg(s.z_grid + G - 1);
-  if (xq <= x0) { const double2 a = gd[0]; return a.x + a.y * (xq - x0); }
-  if (xq >= xn) { const double2 b = gd[pad_idx(G - 1)]; return b.x + b.y * (xq - xn); }
+  if (xq <= x0) { const double2 a = node(0); return a.x + a.y * (xq - x0); }
+  if (xq >= xn) { const double2 b = node(G - 1); return b.x + b.y * (xq - xn); }
   int lo = 0, hi = G;  // np.searchsorted(x, xq) - 1 (interpolator.py:94)
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -190,7 +199,7 @@ __device__ __forceinline__ double hermite_dm(const DevSpec& s, const double2* __
   }
   const int i = lo - 1;
   const double xi = __ldg(s.z_grid + i), h_i = __ldg(s.z_grid + i + 1) - xi;
-  const double2 a = gd[pad_idx(i)], b = gd[pad_idx(i + 1)];
+  const double2 a = node(i), b = node(i + 1);
   return hermite_seg(a.x, h_i * a.y, b.x, h_i * b.y, (xq - xi) / h_i);
 }
 
@@ -290,12 +299,14 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*
 }
 
 struct S12Smem {
-  double2 gd[kPaddedGrid];  // {cumulative D_M, dh} per grid node, padded
+  double2 gd[kPaddedGrid];  // {D_M relative to the first node of the 16-node chunk, hscale * dh} per grid node, padded
+  double off[kS12Threads];  // D_M at the first node of each chunk
   double2 logtab[128];
   double wsum[8];
   double red[5 * 8];
   double vec[CL_MAX_BAO + CL_MAX_CC + CL_SN_SMALL_MAX];
-  double scal[4];  // z*, r_drag, mean and half-difference of 1/(1 +- z_pec)
+  double scal[4];  // z*, r_drag
+  double theta[2][CL_MAX_DIM];  // this row's and the next row's parameter vector
 };
 
 template <int FAM, int DE>
@@ -308,8 +319,15 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   if (tid < 128) sm.logtab[tid] = s.logtab[tid];  // visible after the first __syncthreads of the loop body
   const uint32_t gd_addr = s12_smem_u32(sm.gd), tab_addr = s12_smem_u32(sm.logtab);
 
-  for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
-    const double* __restrict__ th = a.theta + b * a.ld;
+  if (tid < s.ndim && (int64_t)blockIdx.x < a.B) sm.theta[0][tid] = a.theta[(int64_t)blockIdx.x * a.ld + tid];
+  __syncthreads();
+  int tb = 0;
+  for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, tb ^= 1) {
+    const double* __restrict__ th = sm.theta[tb];
+    // theta of the next row is staged into the other buffer while this row computes (its L2 latency would otherwise
+    // stall every warp); the write happens after the first barrier of the iteration, when no thread can still be
+    // reading that buffer for the previous row
+    const bool stage_next = tid < s.ndim && b + gridDim.x < a.B;
     Cosmo c;
     unpack(s, th, c);
 
@@ -333,6 +351,9 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           a.aux[AUX_FLAGS * a.B + b] = (double)flags;
           a.aux[AUX_LOGPRIOR * a.B + b] = lp;
         }
+        __syncthreads();
+        if (stage_next) sm.theta[tb ^ 1][tid] = a.theta[(b + gridDim.x) * a.ld + tid];
+        __syncthreads();
         continue;
       }
     }
@@ -343,34 +364,49 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const bool need_rd = s.rd_mode == CL_RD_FIT && ((a.mode == MODE_EVAL && s.n_bao > 0) || a.mode == MODE_BAO || a.mode == MODE_CMB);
 
     // ================= stage 1: dh = c/H on the grid, cumulative trapezoid =================
-    // thread t owns nodes [16t, 16t+16) and the 16 intervals that start at them (it also evaluates node 16t+16);
-    // hd[k] = hscale * dh(node) with hscale = step on the np.linspace grid (the Hermite segment wants h * slope)
-    double hd[kPPT + 1];
+    // thread t owns nodes [16t, 16t+16) and the 16 intervals that start at them.  It stores {D_M relative to its first
+    // node, hscale * dh} per node as it goes (hscale = step on the np.linspace grid: the interpolant wants h * slope);
+    // the block-wide exclusive scan of the chunk totals goes to sm.off[] and is added when a node is read.
     double run = 0.0;
     const int i0 = tid * kPPT;
-    const bool full_chunk = i0 + kPPT < G;  // all 17 nodes inside the grid
     if (need_grid) {
-      if (s.grid_uniform) {
-        const double dk0 = (double)i0, Ks = c.K * s.step;
+      const uint32_t dst = gd_addr + (uint32_t)pad_idx(i0) * 16u;
+      if (a.dbg & 1) {
+        run = 1.0;
+      } else if (s.grid_uniform) {
+        const double Ks = c.K * s.step, zp1_0 = fma((double)i0, s.step, 1.0);
+        double prev = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1_0 - 1.0, zp1_0));
+        if (i0 + kPPT < G) {  // all 17 nodes inside the grid
 #pragma unroll
-        for (int k = 0; k <= kPPT; k++) {
-          const double zp1 = fma(dk0 + (double)k, s.step, 1.0);  // 1 + z_grid[i0+k] (the integer sum is exact)
-          hd[k] = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1 - 1.0, zp1));
+          for (int k = 0; k < kPPT; k++) {
+            const double zp1 = fma((double)(k + 1), s.step, zp1_0);  // 1 + z_grid[i0+k+1] to 1 ulp
+            const double nxt = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1 - 1.0, zp1));
+            sts_d2(dst + 16u * k, run, prev);
+            run = fma(prev + nxt, 0.5, run);
+            prev = nxt;
+          }
+        } else if (i0 < G) {
+#pragma unroll
+          for (int k = 0; k < kPPT; k++) {
+            const double zp1 = fma((double)(k + 1), s.step, zp1_0);
+            const double nxt = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1 - 1.0, zp1));
+            if (i0 + k < G) sts_d2(dst + 16u * k, run, prev);
+            if (i0 + k + 1 < G) run = fma(prev + nxt, 0.5, run);
+            prev = nxt;
+          }
         }
-        if (full_chunk) {
+      } else if (i0 < G) {
+        double prev = DH_of_z<FAM, DE>(s, c, __ldg(s.z_grid + i0));
 #pragma unroll
-          for (int k = 0; k < kPPT; k++) run = fma(hd[k] + hd[k + 1], 0.5, run);
-        } else {
-#pragma unroll
-          for (int k = 0; k < kPPT; k++)
-            if (i0 + k + 1 < G) run = fma(hd[k] + hd[k + 1], 0.5, run);
+        for (int k = 0; k < kPPT; k++) {
+          if (i0 + k < G) sts_d2(dst + 16u * k, run, prev);
+          if (i0 + k + 1 < G) {
+            const double z0 = __ldg(s.z_grid + i0 + k), z1 = __ldg(s.z_grid + i0 + k + 1);
+            const double nxt = DH_of_z<FAM, DE>(s, c, z1);
+            run += ((prev + nxt) / 2) * (z1 - z0);
+            prev = nxt;
+          }
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k <= kPPT; k++) hd[k] = (i0 + k < G) ? DH_of_z<FAM, DE>(s, c, __ldg(s.z_grid + i0 + k)) : 0.0;
-#pragma unroll
-        for (int k = 0; k < kPPT; k++)
-          if (i0 + k + 1 < G) run += ((hd[k] + hd[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
       }
       // block-exclusive scan of the per-thread totals
       double inc = run;
@@ -383,41 +419,19 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       run = inc - run;  // exclusive prefix within the warp
     }
     // scalar work on the last thread while the others finish their grid points
-    if (tid == kS12Threads - 1) {
-      if (need_cmb || need_rd) {
-        double obh2 = c.obh2;
-        double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
-        sm.scal[0] = need_cmb ? z_star_fit(s.k, obh2, wm) : 0.0;
-        sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
-      }
-      if (s.vel_pm1) {  // step template: only two distinct 1/(1+z_pec) per theta (sn/pantheon.py:46-48)
-        const double z_pec = (s.vel_scale * th[s.col_vel[0]]) / kC_KMS;
-        const double rp = 1.0 / (1.0 + z_pec), rm = 1.0 / (1.0 - z_pec);
-        sm.scal[2] = 0.5 * (rp + rm);  // 1/(1 + w z_pec) = scal[2] + w scal[3] for w = +-1
-        sm.scal[3] = 0.5 * (rp - rm);
-      }
+    if (tid == kS12Threads - 1 && (need_cmb || need_rd)) {
+      double obh2 = c.obh2;
+      double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
+      sm.scal[0] = need_cmb ? z_star_fit(s.k, obh2, wm) : 0.0;
+      sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
     }
     __syncthreads();
+    if (stage_next) sm.theta[tb ^ 1][tid] = a.theta[(b + gridDim.x) * a.ld + tid];
 
     if (need_grid) {
       double off = run;
       for (int w = 0; w < warp; w++) off += sm.wsum[w];
-      if (i0 < G) {
-        const uint32_t dst = gd_addr + (uint32_t)pad_idx(i0) * 16u;
-        if (s.grid_uniform) {
-#pragma unroll
-          for (int k = 0; k < kPPT; k++) {
-            sts_d2(dst + 16u * k, off, hd[k]);
-            off = fma(hd[k] + hd[k + 1], 0.5, off);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < kPPT; k++) {
-            sts_d2(dst + 16u * k, off, hd[k]);
-            if (i0 + k + 1 < G) off += ((hd[k] + hd[k + 1]) / 2) * (__ldg(s.z_grid + i0 + k + 1) - __ldg(s.z_grid + i0 + k));
-          }
-        }
-      }
+      sm.off[tid] = off;
       __syncthreads();
     }
 
@@ -425,7 +439,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (a.mode == MODE_DIST) {
       for (int q = tid; q < a.nq; q += kS12Threads) {
         double z = a.zq[q];
-        if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.gd, z);
+        if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.gd, sm.off, z);
         if (a.outDH) a.outDH[b * a.nq + q] = DH_of_z<FAM, DE>(s, c, z);
       }
       __syncthreads();
@@ -434,7 +448,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 
     // ================= stage 2: residuals =================
     const int n_sn = s.n_sn;
-    if ((a.mode == MODE_EVAL || a.mode == MODE_RESID) && n_sn > 0) {
+    if ((a.mode == MODE_EVAL || a.mode == MODE_RESID) && n_sn > 0 && !(a.dbg & 2)) {
       const double offset = (s.col_offset >= 0 && !a.zero_offset) ? th[s.col_offset] : 0.0;
       const int64_t ld = a.mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
@@ -443,33 +457,54 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         // fast path.  Static per-SN operands: zs = {1 + z_cmb, w} (or {z_cmb, 0} without a velocity template) and
         // obsp = obs - 25 - 5 log10(1 + z_hel), so that delta = obsp - offset - 5 log10 D_M(z_cosmo):
         // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)), D_M(z_cmb) cancels.
+        // step template (w = +-1): 1/(1 + w z_pec) = ravg + w rdif with ravg = 1/(1 - z_pec^2), rdif = -z_pec ravg
         const bool shift = s.n_vel > 0;
-        const double ravg = sm.scal[2], rdif = sm.scal[3];
-        const double inv_step = s.inv_step, z_last = s.z_last;
+        double ravg = 1.0, rdif = 0.0;
+        if (shift) {
+          const double z_pec = (s.vel_scale * th[s.col_vel[0]]) * (1.0 / kC_KMS);
+          ravg = rcp_pos(fma(-z_pec, z_pec, 1.0));
+          rdif = -z_pec * ravg;
+        }
+        const double inv_step = s.inv_step, z_last = s.z_last, obs_off = -offset;
         const int imax = G - 2;
-        const double2* __restrict__ zsp = s.sn_zs;
-        const double* __restrict__ obp = s.sn_obsp;
-        int i = tid;
-        double2 zs = i < n_sn ? __ldg(zsp + i) : make_double2(1.0, 0.0);
-        double ob = i < n_sn ? __ldg(obp + i) : 0.0;
-        while (i < n_sn) {
-          const int inext = i + kS12Threads;
-          const double2 zs_n = inext < n_sn ? __ldg(zsp + inext) : make_double2(1.0, 0.0);  // prefetch: L1 is all smem
-          const double ob_n = inext < n_sn ? __ldg(obp + inext) : 0.0;
+        auto resid = [&](double2 zs, double ob) -> double {
           const double zq = shift ? fma(zs.x, fma(zs.y, rdif, ravg), -1.0) : zs.x;  // (1+z_cmb)/(1+z_pec) - 1
-          double dl5;
           if (zq > 1e-9 && zq < z_last) {
             const int j = min((int)(zq * inv_step), imax);
             const double t = fma(zq, inv_step, -(double)j);
             const double2 n0 = lds_d2(gd_addr + (uint32_t)pad_idx(j) * 16u);
             const double2 n1 = lds_d2(gd_addr + (uint32_t)pad_idx(j + 1) * 16u);
-            dl5 = fast_5log10(hermite_seg(n0.x, n0.y, n1.x, n1.y, t), tab_addr);
-          } else {
-            dl5 = 5.0 * log10(hermite_dm(s, sm.gd, zq));
+            // On the trapezoid-built grid D_M(i+1) - D_M(i) = (hd_i + hd_{i+1})/2, so the cubic Hermite segment
+            // (interpolator.py:96-108) collapses to the quadratic y_i + t hd_i + t^2 (hd_{i+1} - hd_i)/2; the dropped
+            // cubic coefficient is pure rounding of the cumulative sum (~1e-16 D_M).
+            const double dm = fma(t, fma(0.5 * t, n1.y - n0.y, n0.y), n0.x + sm.off[j >> 4]);
+            return (ob + obs_off) - fast_5log10(dm, tab_addr);
           }
-          const double d = (ob - offset) - dl5;
-          if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
-          i = inext; zs = zs_n; ob = ob_n;
+          return (ob + obs_off) - 5.0 * log10(hermite_dm(s, sm.gd, sm.off, zq));  // outside the grid / non-positive distance
+        };
+        // two SNe per thread per trip (independent dependency chains); operands are prefetched one trip ahead
+        // because all of L1 is carved out as shared memory and the static arrays live in L2
+        const double2* __restrict__ zsp = s.sn_zs + tid;
+        const double* __restrict__ obp = s.sn_obsp + tid;
+        double* __restrict__ outp = to_smem ? (sm.vec + CL_MAX_BAO + CL_MAX_CC + tid) : (Rrow + tid);
+        const int n_pair = (n_sn - tid + 2 * kS12Threads - 1) / (2 * kS12Threads);  // trips for this thread
+        int i = tid;
+        double2 zs0 = make_double2(1.0, 0.0), zs1 = zs0;
+        double ob0 = 0.0, ob1 = 0.0;
+        if (i < n_sn) { zs0 = __ldg(zsp); ob0 = __ldg(obp); }
+        if (i + kS12Threads < n_sn) { zs1 = __ldg(zsp + kS12Threads); ob1 = __ldg(obp + kS12Threads); }
+        for (int trip = 0; trip < n_pair; trip++) {
+          const double2 c0 = zs0, c1 = zs1;
+          const double o0 = ob0, o1 = ob1;
+          const bool v1 = i + kS12Threads < n_sn;
+          zsp += 2 * kS12Threads; obp += 2 * kS12Threads;
+          if (i + 2 * kS12Threads < n_sn) { zs0 = __ldg(zsp); ob0 = __ldg(obp); }
+          if (i + 3 * kS12Threads < n_sn) { zs1 = __ldg(zsp + kS12Threads); ob1 = __ldg(obp + kS12Threads); }
+          const double d0 = resid(c0, o0);
+          const double d1 = resid(c1, o1);
+          outp[0] = d0;
+          if (v1) outp[kS12Threads] = d1;
+          outp += 2 * kS12Threads; i += 2 * kS12Threads;
         }
       } else {
         const double2* __restrict__ pack = reinterpret_cast<const double2*>(s.sn_pack);
@@ -486,7 +521,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
             if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + p0.x) / (1.0 + z_pec);
             else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
           }
-          const double DM = hermite_dm(s, sm.gd, zq);
+          const double DM = hermite_dm(s, sm.gd, sm.off, zq);
           const double mu = 25.0 + 5 * log10(p1.x * DM);
           const double d = (p1.y - offset) - mu;
           if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
@@ -500,7 +535,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (do_bao && tid < s.n_bao) {
       double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : sm.scal[1]);
       double z = __ldg(s.bao_z + tid);
-      double DM = hermite_dm(s, sm.gd, z);
+      double DM = hermite_dm(s, sm.gd, sm.off, z);
       double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.gd, z) : DH_of_z<FAM, DE>(s, c, z);
       int q = __ldg(s.bao_qty + tid);
       double v;
@@ -537,7 +572,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         v[1] = __ldg(s.gl_w + q) * (DH_of_z<FAM, DE>(s, c, z) / (av * av * sqrt(3.0 * (1.0 + Rb))));
       }
     }
-    __syncthreads();  // sm.vec complete
+    const bool need_red = need_cmb || s.n_bao > 0 || s.n_cc > 0 || s.sn_small;  // uniform
+    if (need_red) __syncthreads();  // sm.vec complete
 
     if (a.mode == MODE_EVAL) {
       if (tid < s.n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
@@ -564,8 +600,9 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       }
     }
     const double rd_out = (need_rd && tid == 0) ? sm.scal[1] : 0.0;
-    if (need_cmb || s.n_bao > 0 || s.n_cc > 0 || s.sn_small) block_sum<5>(v, sm.red);
-    else __syncthreads();  // orders this iteration's shared-memory reads before the next iteration's writes
+    // The next iteration stores its grid nodes before its first barrier, so every thread must be done reading gd.
+    if (need_red) block_sum<5>(v, sm.red);
+    else __syncthreads();
 
     if (tid == 0) {
       double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;

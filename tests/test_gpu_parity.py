@@ -158,6 +158,21 @@ def test_ragged_batches_and_row_order(engines, oracles):
     chi2_close(full[:64], oracles("sn_pantheon").chi_squared(theta[:64]))
 
 
+def test_many_rows_per_cta(engines, oracles):
+    """Few stage-1/2 CTAs -> each CTA loops over many theta rows (shared-memory reuse across rows must be race
+    free); all model families."""
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    for name in ("sn_pantheon", "bao_desi_cmb_union3", "bao_desi_des5y_bbn_theta_star", "bao_desi_fs_lya_cmb"):
+        g = golden(name)
+        theta = uniform_theta(g["bounds"], 400, seed=11)
+        ref = engines(name).chi_squared(theta)
+        with Engine(spec(name)) as e2:
+            e2.set_option("stage12_ctas", 7)
+            got = e2.chi_squared(theta)
+        assert np.array_equal(got, ref), name
+
+
 def test_multi_pass_matches_single_pass(engines):
     from cosmology_model_fit_b200 import Engine
     from cosmology_model_fit_b200.synthetic import uniform_theta
