@@ -268,18 +268,31 @@ def main():
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the host-buffer C ABI (cl_eval): H2D of theta and D2H of logL every step ----
+    # ---- end to end from HOST buffers: H2D of theta and D2H of logL inside the timed region, every step ----
+    # 1 GPU: Engine.log_likelihood(batch) -> cl_eval (pinned staging inside the library).
+    # N GPUs: ShardedEngine.log_likelihood(global batch): each rank uploads its row shard, evaluates, NCCL all-gather,
+    #         and every rank downloads the full result vector (what a sampler driving N GPUs needs).
     e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        from cosmology_model_fit_b200.parallel import ShardedEngine
+        sh = ShardedEngine(spec, device=local_rank, engine=eng)
+        global_batches = [np.concatenate([theta_batch(spec, B, seed=1000 + r * 16 + i) for r in range(world)]) for i in range(2)]
+        e2e_call = lambda i: sh.log_likelihood(global_batches[i % 2])
+        e2e_api = "ShardedEngine.log_likelihood(global batch): pinned H2D of the row shard, cl_eval_device, NCCL all-gather, D2H"
+        h2d, d2h = B * nd * 8, B * world * 8
+    else:
+        e2e_call = lambda i: eng.log_likelihood(host_batches[i % n_rot])
+        e2e_api = "Engine.log_likelihood(batch) -> cl_eval (host buffers, pinned staging)"
+        h2d, d2h = B * nd * 8, B * 8
     for i in range(2):
-        eng.log_likelihood(host_batches[i % n_rot])
+        e2e_call(i)
     if world > 1:
         dist.barrier()
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        res = eng.log_likelihood(host_batches[i % n_rot])
-        if world > 1:
-            gathered = [None] * world
-            dist.all_gather_object(gathered, float(res[0]))
+        e2e_call(i)
+    torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -308,8 +321,8 @@ def main():
                                  "peak": hbm_peak, "unit": "GB/s", "frac": s12_bytes / (s12_ms * 1e-3) / 1e9 / hbm_peak,
                                  "avg_kernel_ms": s12_ms, "note": "FP64-ALU bound, not HBM bound (SURVEY.md T5)"},
             "stage_ms": {"stage12": s12_ms, "stage3": gemm_ms, "finalize": float(np.mean(hist[:, 2])), "total": float(np.mean(hist[:, 3]))},
-            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * nd * 8, "d2h_bytes_per_step": B * 8,
-                    "steps": e2e_steps, "api": "Engine.log_likelihood(batch) -> cl_eval (host buffers, pinned staging)"},
+            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": int(launches), "clocks": clocks, "parity_check": "64 rows vs oracle ok",
             "engine": eng.describe(),
         }
