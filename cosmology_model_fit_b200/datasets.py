@@ -53,3 +53,16 @@ def desi_fs_lya(root=None):
     """(z, value, quantity, cov) DESI DR2 + full-shape Lya, 14 points (y2025BAO/data_fs_lya.py)."""
     d = _load("data_desi_bao.npz", root)
     return d["fs_lya_z"], d["fs_lya_value"], d["fs_lya_quantity"], d["fs_lya_cov"]
+
+
+def pantheon_plus_positions(cut=True, root=None):
+    """(RA, DEC, IDSURVEY) of the Pantheon+ rows (y2022pantheonSHOES/data.py:38-48)."""
+    d = _load("data_pantheon_plus.npz", root)
+    keep = np.where(d["zHD"] > 0.01)[0] if cut else np.arange(d["zHD"].size)
+    return d["RA"][keep], d["DEC"][keep], d["IDSURVEY"][keep]
+
+
+def cosmic_chronometers(root=None):
+    """(z, H, cov) (y2005cc/data.py:5-40)."""
+    d = _load("data_cc.npz", root)
+    return d["z"], d["H"], d["cov"]

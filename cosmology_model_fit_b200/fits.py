@@ -174,6 +174,35 @@ def bao_desi_bbn(desi, consts=None):
     return _bao_block(sp, desi, S.DH_PCHIP, S.RD_FIT)
 
 
+def bao_desi_pantheon_cc(sn, desi, cc):
+    """bao/desi_pantheon_cc.py: theta = (H0, M, r_d, Om, v, f_cc); late LCDM; uniform flow with the multiplicative shift
+    z_cosmo = max((1+z)(1+v/c) - 1, 1e-8) (:83-90); r_d sampled; CC term with its normalisation (:134-137)."""
+    bounds = np.array([(40.0, 90.0), (-20.0, -19.0), (115.0, 170.0), (0.0, 1.0), (-1.3, 3.5), (0.4, 2.5)])  # :94-103
+    zc, Hc, covc = cc
+    sp = LikelihoodSpec(ndim=6, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=0, col_Om=3, z_grid=_grid(sn[0], desi[0]),
+                        bounds=bounds, cc_z=zc, cc_H=Hc, cc_inv_cov=np.linalg.inv(covc), col_fcc=5,
+                        cc_logdet=float(np.linalg.slogdet(covc)[1]), cc_norm_sign=1.0)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 1, 4)
+    sp.sn_vel_weight = np.ones_like(np.asarray(sn[0], dtype=np.float64))
+    sp.vel_mode = S.VEL_MULTIPLY
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=2)
+
+
+def sn_pantheon_dipole_xyz(sn, ra, dec, survey_id, z_c=0.10, dz=0.02, target_ids=(1, 5, 15, 50, 51, 56, 63, 150)):
+    """sn/pantheon_dipole_xyz.py: theta = (M, H0, Om, vx, vy, vz); velocity templates n_k * attenuation * survey mask
+    (:14-21, 47-55)."""
+    z_cmb = np.asarray(sn[0], dtype=np.float64)
+    ra_rad, dec_rad = np.deg2rad(ra), np.deg2rad(dec)
+    n = np.vstack([np.cos(dec_rad) * np.cos(ra_rad), np.cos(dec_rad) * np.sin(ra_rad), np.sin(dec_rad)])
+    att = 0.5 * (1.0 - np.tanh((z_cmb - z_c) / dz))
+    mask = np.isin(survey_id, target_ids).astype(int)
+    sp = LikelihoodSpec(ndim=6, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=1, col_Om=2, z_grid=_grid(sn[0]))
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    sp.col_vel = (3, 4, 5)
+    sp.sn_vel_weight = n * att * mask
+    return sp
+
+
 # --------------------------------------------------------------------------------------------- ohd/*
 def ohd_cc(cc):
     """ohd/cc.py: theta = (H0, Om, f); chi2 = f^2 d^T C^-1 d; log L adds N ln 2pi + logdet - 2N ln f."""

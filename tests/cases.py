@@ -32,6 +32,8 @@ des = _memo(datasets.des_dovekie)
 union3 = _memo(datasets.union3_1)
 desi = _memo(datasets.desi_dr2)
 desi_fs = _memo(datasets.desi_fs_lya)
+cc = _memo(datasets.cosmic_chronometers)
+pantheon_pos = _memo(datasets.pantheon_plus_positions)
 
 SPECS = {
     "sn_pantheon": lambda: fits.sn_pantheon(pantheon()),
@@ -44,11 +46,16 @@ SPECS = {
     "bao_desi_des5y_bbn_theta_star": lambda: fits.bao_desi_des5y_bbn_theta_star(des(), desi()),
     "bao_desi_cmb_pantheon": lambda: fits.bao_desi_cmb_pantheon(pantheon(), desi()),
     "bao_desi_cmb_des5y": lambda: fits.bao_desi_cmb_des5y(des(), desi_fs()),
+    "ohd_cc": lambda: fits.ohd_cc(cc()),
+    "bao_desi_bbn": lambda: fits.bao_desi_bbn(desi()),
+    "bao_desi_pantheon_cc": lambda: fits.bao_desi_pantheon_cc(pantheon(), desi(), cc()),
+    "sn_pantheon_dipole_xyz": lambda: fits.sn_pantheon_dipole_xyz(pantheon(), *pantheon_pos()),
 }
 
 #: cases whose golden file has a plain chi2[n] for theta[n]
 CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cmb_union3",
-              "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y"]
+              "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y",
+              "ohd_cc", "bao_desi_bbn", "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz"]
 
 
 def spec(name):

@@ -46,6 +46,9 @@ def dump_data_columns():
         zHEL=df["zHEL"].to_numpy(np.float64),
         m_b_corr=df["m_b_corr"].to_numpy(np.float64),
         m_b_corr_err_DIAG=df["m_b_corr_err_DIAG"].to_numpy(np.float64),
+        RA=df["RA"].to_numpy(np.float64),
+        DEC=df["DEC"].to_numpy(np.float64),
+        IDSURVEY=df["IDSURVEY"].to_numpy(np.int32),
     )
     df = pd.read_csv(f"{REF}/y2025DESdovekie/raw-data/distances.csv", sep=r"\s+")
     np.savez_compressed(
@@ -78,6 +81,17 @@ def dump_data_columns():
         out[f"{tag}_quantity"] = d["quantity"]
         out[f"{tag}_cov"] = np.loadtxt(f"{REF}/y2025BAO/raw-data/{cfile}", delimiter=" ", dtype=np.float64)
     np.savez_compressed(f"{HERE}/data_desi_bao.npz", **out)
+    # cosmic chronometers: the loader builds the covariance with the reference's own pchip (y2005cc/data.py:5-40)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    try:
+        from y2005cc.data import get_data as cc_get
+        _, zc, Hc, covc = cc_get()
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    np.savez_compressed(f"{HERE}/data_cc.npz", z=np.asarray(zc, dtype=np.float64), H=np.asarray(Hc, dtype=np.float64), cov=np.asarray(covc, dtype=np.float64))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -91,8 +105,13 @@ def _stub_pantheon():
     def get_data():
         return ("Pantheon+ (2022)", d["zHD"][keep], d["zHEL"][keep], d["m_b_corr"][keep], cov_full[np.ix_(keep, keep)])
 
+    def get_data_with_position():
+        return ("Pantheon+ (2022)", d["zHD"][keep], d["zHEL"][keep], d["m_b_corr"][keep], d["RA"][keep], d["DEC"][keep],
+                d["IDSURVEY"][keep], cov_full[np.ix_(keep, keep)])
+
     m = types.ModuleType("y2022pantheonSHOES.data")
     m.get_data = get_data
+    m.get_data_with_position = get_data_with_position
     pkg = types.ModuleType("y2022pantheonSHOES")
     pkg.__path__ = []
     pkg.data = m
@@ -307,6 +326,58 @@ def case_sn_des5y():
     theta = uniform_theta(bounds, 32)
     chi2 = np.array([ref.chi_squared(t) for t in theta])
     return dict(theta=theta, chi2=chi2, bounds=bounds, z_grid=ref.z_grid)
+
+
+def case_ohd_cc():
+    """ohd/cc.py: theta = (H0, Om, f); chi2 = f^2 |L^-1 d|^2; log L with the N ln 2pi + logdet - 2N ln f term."""
+    _enter_reference()
+    import ohd.cc as ref
+
+    bounds = np.array([(30.0, 100.0), (0.0, 1.0), (0.4, 2.5)])
+    theta = uniform_theta(bounds, 40)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    ll = np.array([ref.log_likelihood(t) for t in theta])
+    return dict(theta=theta, chi2=chi2, loglike=ll, bounds=bounds)
+
+
+def case_bao_desi_bbn():
+    """bao/desi_bbn.py: late thawing, r_d = r_drag(obh2, Om h^2) with the Planck-module fit, pchip D_H."""
+    _enter_reference()
+    import bao.desi_bbn as ref
+
+    theta = uniform_theta(ref.bounds, 40)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    theory = np.array([ref.bao_theory(ref.bao["z"], ref.bao_qty, t) for t in theta[:8]])
+    return dict(theta=theta, chi2=chi2, theory=theory, bounds=ref.bounds, z_grid=ref.z_grid)
+
+
+def case_bao_desi_pantheon_cc():
+    """bao/desi_pantheon_cc.py: theta = (H0, M, r_d, Om, v, f_cc); multiplicative z shift with the 1e-8 floor,
+    sampled r_d, CC term with normalisation, box prior."""
+    _stub_pantheon()
+    _enter_reference()
+    import bao.desi_pantheon_cc as ref
+
+    theta = uniform_theta(ref.bounds, 24)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    ll = np.array([ref.log_likelihood(t) for t in theta])
+    tp = np.vstack([theta[:4], [[95.0, -19.3, 147.0, 0.3, 0.0, 1.0]]])
+    logp = np.array([ref.log_probability(t) for t in tp])
+    return dict(theta=theta, chi2=chi2, loglike=ll, theta_logp=tp, logp=logp, bounds=ref.bounds, z_grid=ref.z_grid)
+
+
+def case_sn_pantheon_dipole_xyz():
+    """sn/pantheon_dipole_xyz.py: theta = (M, H0, Om, vx, vy, vz); three velocity templates n_k * attenuation * mask."""
+    _stub_pantheon()
+    _enter_reference()
+    import sn.pantheon_dipole_xyz as ref
+
+    bounds = np.array([(-20.0, -19.0), (60.0, 80.0), (0.1, 0.6), (-8.0, 8.0), (-8.0, 8.0), (-8.0, 8.0)])
+    theta = uniform_theta(bounds, 24)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    att = 0.5 * (1.0 - np.tanh((ref.z_cmb - 0.10) / 0.02))
+    w = np.vstack([ref.nx, ref.ny, ref.nz]) * att * ref.survey_mask
+    return dict(theta=theta, chi2=chi2, bounds=bounds, z_grid=ref.z_grid, weights=w)
 
 
 def case_interpolator():

@@ -143,6 +143,93 @@ def test_config1_log_probability(engines):
     assert rel_err(e.bao_theory(g["theta"][:8]), g["bao_theory"]) < DIST_RTOL
 
 
+def test_cc_normalisation_and_multiplicative_shift(engines):
+    """ohd/cc.py:29-34 log-likelihood normalisation; bao/desi_pantheon_cc.py multiplicative z shift + sampled r_d."""
+    for name in ("ohd_cc", "bao_desi_pantheon_cc"):
+        g = golden(name)
+        chi2_close(-2 * engines(name).log_likelihood(g["theta"]), -2 * g["loglike"])
+    g = golden("bao_desi_pantheon_cc")
+    lp = engines("bao_desi_pantheon_cc").log_probability(g["theta_logp"])
+    fin = np.isfinite(g["logp"])
+    assert np.array_equal(np.isneginf(lp), ~fin)
+    chi2_close(-2 * lp[fin], -2 * g["logp"][fin])
+
+
+def test_bao_desi_bbn_theory(engines):
+    g = golden("bao_desi_bbn")
+    assert rel_err(engines("bao_desi_bbn").bao_theory(g["theta"][:8]), g["theory"]) < DIST_RTOL
+
+
+def test_nonuniform_grid_and_wcdm_vs_oracle(oracles):
+    """Paths no reference script exercises as checked in (oracle-only parity): a non-np.linspace grid (bisection +
+    full cubic Hermite), wCDM and CPL late-time families, omega_m parameterisation."""
+    import oracle.oracle as O
+    from cosmology_model_fit_b200 import Engine, fits
+    from cosmology_model_fit_b200 import spec as S
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    from cases import desi, union3
+    rng = np.random.default_rng(5)
+    sp = fits.sn_union3_1(union3())
+    z = np.sort(np.concatenate([[0.0], rng.uniform(0, 2.4, 2998), [2.45]]))
+    sp.z_grid = z
+    theta = uniform_theta(np.array([(-1.0, 1.0), (0.1, 0.7), (-9.0, 9.0)]), 64, seed=1)
+    with Engine(sp) as e:
+        assert "uniform" not in e.describe()
+        chi2_close(e.chi_squared(theta), O.Oracle(sp).chi_squared(theta))
+        zq = rng.uniform(-0.01, 2.5, 40)
+        assert rel_err(e.distances(theta[:4], zq)[0][:, 1:], O.Oracle(sp).distances(theta[:4], zq)[0][:, 1:]) < DIST_RTOL
+    for de, cols in ((S.DE_WCDM, dict(col_w0=2)), (S.DE_CPL, dict(col_w0=2, col_wa=3))):
+        sp = fits.bao_desi(desi())
+        sp.de_model = de
+        sp.ndim = 3 + (de == S.DE_CPL)
+        sp.bounds = None
+        for k, v in cols.items():
+            setattr(sp, k, v)
+        b = np.array([(0.5, 0.8), (0.1, 0.5), (-1.5, -0.5), (-1.0, 0.4)])[: sp.ndim]
+        theta = uniform_theta(b, 64, seed=2)
+        with Engine(sp) as e:
+            chi2_close(e.chi_squared(theta), O.Oracle(sp).chi_squared(theta))
+    sp = fits.bao_desi(desi())
+    sp.Om_is_physical = True
+    theta = uniform_theta(np.array([(0.5, 0.8), (0.08, 0.2), (-1.0, 0.0)]), 64, seed=3)
+    with Engine(sp) as e:
+        chi2_close(e.chi_squared(theta), O.Oracle(sp).chi_squared(theta))
+
+
+def test_config1_with_vstep_vs_oracle():
+    """BASELINE.json config 1 as worded (thawing w0 + BBN + theta* + the z_turn = 0.10563 step of the sibling DES
+    scripts): the checked-in reference file has no v column, so this union is pinned by the oracle only."""
+    import oracle.oracle as O
+    from cosmology_model_fit_b200 import Engine, fits
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    from cases import des, desi
+    sp = fits.bao_desi_des5y_bbn_theta_star(des(), desi(), with_v=True)
+    theta = uniform_theta(sp.bounds, 200, seed=21)
+    with Engine(sp) as e:
+        chi2_close(e.chi_squared(theta), O.Oracle(sp).chi_squared(theta, nthreads=0))
+        lp = e.log_probability(theta)
+        chi2_close(-2 * lp, -2 * O.Oracle(sp).log_probability(theta, nthreads=0))
+        # v = 0 reduces to the checked-in script
+        g = golden("bao_desi_des5y_bbn_theta_star")
+        t0 = np.c_[g["theta"], np.zeros(len(g["theta"]))]
+        chi2_close(e.chi_squared(t0), g["chi2"])
+
+
+def test_strided_theta_rows(engines):
+    """ld > ndim: theta rows embedded in a wider host array (cl_eval's ld argument)."""
+    import ctypes as C
+    g = golden("sn_pantheon")
+    e = engines("sn_pantheon")
+    wide = np.zeros((len(g["theta"]), 7))
+    wide[:, :4] = g["theta"]
+    out = np.empty(len(wide))
+    dp = C.POINTER(C.c_double)
+    rc = e.lib.cl_eval(e._ctx, wide.ctypes.data_as(dp), len(wide), 7, 0, out.ctypes.data_as(dp))
+    assert rc == 0
+    chi2_close(out, g["chi2"])
+    assert e.lib.cl_eval(e._ctx, wide.ctypes.data_as(dp), len(wide), 3, 0, out.ctypes.data_as(dp)) == -1  # ld < ndim
+
+
 def test_ragged_batches_and_row_order(engines, oracles):
     """B = 1, 127, 128, 129, 1000 (row-block edges of the 128-row GEMM tile) give the same per-row values."""
     from cosmology_model_fit_b200.synthetic import uniform_theta
