@@ -328,6 +328,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     // stall every warp); the write happens after the first barrier of the iteration, when no thread can still be
     // reading that buffer for the previous row
     const bool stage_next = tid < s.ndim && b + gridDim.x < a.B;
+    double th_next = 0.0;
+    if (stage_next) th_next = a.theta[(b + gridDim.x) * a.ld + tid];  // consumed only at the end of the iteration
     Cosmo c;
     unpack(s, th, c);
 
@@ -352,7 +354,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           a.aux[AUX_LOGPRIOR * a.B + b] = lp;
         }
         __syncthreads();
-        if (stage_next) sm.theta[tb ^ 1][tid] = a.theta[(b + gridDim.x) * a.ld + tid];
+        if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
         __syncthreads();
         continue;
       }
@@ -426,7 +428,6 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
     }
     __syncthreads();
-    if (stage_next) sm.theta[tb ^ 1][tid] = a.theta[(b + gridDim.x) * a.ld + tid];
 
     if (need_grid) {
       double off = run;
@@ -442,6 +443,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.gd, sm.off, z);
         if (a.outDH) a.outDH[b * a.nq + q] = DH_of_z<FAM, DE>(s, c, z);
       }
+      if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
       __syncthreads();
       continue;
     }
@@ -467,17 +469,23 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         }
         const double inv_step = s.inv_step, z_last = s.z_last, obs_off = -offset;
         const int imax = G - 2;
+        const uint32_t off_addr = s12_smem_u32(sm.off);
+        // floor(z/step) without conversion instructions: adding 1.5 * 2^52 leaves round(x) in the low word
+        const double kMagic = 6755399441055744.0;
         auto resid = [&](double2 zs, double ob) -> double {
           const double zq = shift ? fma(zs.x, fma(zs.y, rdif, ravg), -1.0) : zs.x;  // (1+z_cmb)/(1+z_pec) - 1
           if (zq > 1e-9 && zq < z_last) {
-            const int j = min((int)(zq * inv_step), imax);
-            const double t = fma(zq, inv_step, -(double)j);
-            const double2 n0 = lds_d2(gd_addr + (uint32_t)pad_idx(j) * 16u);
-            const double2 n1 = lds_d2(gd_addr + (uint32_t)pad_idx(j + 1) * 16u);
+            const double w = fma(zq, inv_step, -0.5) + kMagic;  // round(z/step - 1/2): the interval index (ties: either side)
+            const int j = min(__double2loint(w), imax);
+            const double t = fma(zq, inv_step, -(w - kMagic));  // in [0, 1] up to rounding
+            const double2 n0 = lds_d2(gd_addr + ((uint32_t)(j + (j >> 4)) << 4));
+            const double2 n1 = lds_d2(gd_addr + ((uint32_t)(j + 1 + ((j + 1) >> 4)) << 4));
+            double base;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(base) : "r"(off_addr + ((uint32_t)(j >> 4) << 3)));
             // On the trapezoid-built grid D_M(i+1) - D_M(i) = (hd_i + hd_{i+1})/2, so the cubic Hermite segment
             // (interpolator.py:96-108) collapses to the quadratic y_i + t hd_i + t^2 (hd_{i+1} - hd_i)/2; the dropped
             // cubic coefficient is pure rounding of the cumulative sum (~1e-16 D_M).
-            const double dm = fma(t, fma(0.5 * t, n1.y - n0.y, n0.y), n0.x + sm.off[j >> 4]);
+            const double dm = fma(t, fma(0.5 * t, n1.y - n0.y, n0.y), n0.x + base);
             return (ob + obs_off) - fast_5log10(dm, tab_addr);
           }
           return (ob + obs_off) - 5.0 * log10(hermite_dm(s, sm.gd, sm.off, zq));  // outside the grid / non-positive distance
@@ -528,7 +536,11 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         }
       }
     }
-    if (a.mode == MODE_RESID) { __syncthreads(); continue; }
+    if (a.mode == MODE_RESID) {
+      if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
+      __syncthreads();
+      continue;
+    }
 
     // BAO theory (bao_theory, bao/desi_cmb_union3.py:76-94 / bao/desi_cmb_pantheon.py:85-99)
     const bool do_bao = (a.mode == MODE_EVAL || a.mode == MODE_BAO) && s.n_bao > 0;
@@ -546,7 +558,11 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       if (a.mode == MODE_BAO) a.out[b * s.n_bao + tid] = v;
       else sm.vec[tid] = __ldg(s.bao_val + tid) - v;
     }
-    if (a.mode == MODE_BAO) { __syncthreads(); continue; }
+    if (a.mode == MODE_BAO) {
+      if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
+      __syncthreads();
+      continue;
+    }
 
     // cosmic chronometers (ohd/cc.py:22-26)
     if (a.mode == MODE_EVAL && tid < s.n_cc)
@@ -600,6 +616,9 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       }
     }
     const double rd_out = (need_rd && tid == 0) ? sm.scal[1] : 0.0;
+    // The theta row of the next iteration (loaded into a register at the top) is parked in the other buffer; no thread
+    // reads that buffer in this iteration (the previous row's readers all passed this iteration's first barrier).
+    if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
     // The next iteration stores its grid nodes before its first barrier, so every thread must be done reading gd.
     if (need_red) block_sum<5>(v, sm.red);
     else __syncthreads();
