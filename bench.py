@@ -313,7 +313,10 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, spec, world),
             "roofline": {"bound": "tensor", "kernel": "k_chi2_gemm (stage 3, FP64 DMMA)", "achieved": ach, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / peak_tf,
+                         "traffic": 1.20e9 if (N == 1701 and B == 65536) else None,
+                         "traffic_note": "DRAM bytes per launch (dram__bytes_read+write, ncu, profiles/r01f_gemm_dram.csv); "
+                                         "algorithmic 0.92e9 (R read once + W + partial sums)",
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
                                         "DMMA.8x8x4 issue peak measured 37.1 TFLOP/s (profiles/r01_ubench_fp64.log)",
                          "algorithmic_flops_per_eval": N * N + 2.0 * N, "avg_kernel_ms": gemm_ms},

@@ -31,7 +31,7 @@ constexpr int kProducerWarps = 4;  // one full warpgroup so that setmaxnreg can 
 constexpr int kGemmThreads = (kConsumerWarps + kProducerWarps) * 32;
 constexpr int kBoxBytes = kBM * kBK * 8;       // 16 KB, A and B boxes have the same shape
 constexpr int kStageBytes = 2 * kBoxBytes;     // 32 KB
-constexpr int kGemmSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 4 * kBM * 8 /*epilogue*/ + 256 /*barriers*/;
+constexpr int kGemmSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 4 * kBM * 8 /*epilogue*/ + 256 /*barriers + item queue*/;
 
 struct GemmArgs {
   int64_t B;       // rows of R in this pass
@@ -42,7 +42,32 @@ struct GemmArgs {
   double* part_u;  // nullable [T][B]: partial sums of y_j * u_j (moments mode)
   const double* u; // [N] u = W 1 (moments mode)
   int diag_skip;   // 1: warps stop at their own last column inside the diagonal block
+  int* counter;    // dynamic scheduling: global item counter (zeroed before the launch); nullptr = static snake order
+  int group_rb;    // dynamic scheduling: row blocks per L2 group
 };
+
+constexpr int kQueueDepth = 4;  // items the producer may run ahead of the consumers
+
+// Item order.  Static: tiles by decreasing k extent, row blocks inside (dealt boustrophedon to the CTAs).
+// Dynamic: row blocks are taken in groups whose residual rows (group_rb x 128 x N x 8 B) fit in L2 together with W;
+// inside a group the tiles go by decreasing k extent, so the R rows of a group are read from HBM once and re-read
+// from L2 for the other T-1 column tiles.  CTAs pull items from an atomic counter (the order of execution does
+// not affect the result: every item writes its own partial sums).
+__device__ __forceinline__ void decode_item(const GemmArgs& g, int64_t item, int& jt, int& rb) {
+  if (g.counter == nullptr) {
+    jt = g.T - 1 - (int)(item / g.n_rb);
+    rb = (int)(item % g.n_rb);
+    return;
+  }
+  const int per_group = g.group_rb * g.T;
+  const int n_full = g.n_rb / g.group_rb;
+  int grp = (int)(item / per_group);
+  int r, width;
+  if (grp < n_full) { r = (int)(item % per_group); width = g.group_rb; }
+  else { grp = n_full; r = (int)(item - (int64_t)n_full * per_group); width = g.n_rb - n_full * g.group_rb; }
+  jt = g.T - 1 - r / width;
+  rb = grp * g.group_rb + r % width;
+}
 
 // item visited by CTA `cta` in round `k` of the persistent loop: boustrophedon over the cost-sorted item list, so
 // that every CTA gets the same mix of expensive and cheap items (static, deterministic, no atomics)
@@ -126,18 +151,22 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
   const uint32_t bars = base + kStages * kStageBytes + 2 * 4 * kBM * 8;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto qfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto qempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kQueueDepth + s); };
+  const uint32_t q_items = bars + 8u * (2 * kStages + 2 * kQueueDepth);  // int[kQueueDepth]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kConsumerWarps); }
+    for (int s = 0; s < kQueueDepth; s++) { mbar_init(qfull_bar(s), 1); mbar_init(qempty_bar(s), kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
   const int64_t total = (int64_t)g.n_rb * g.T;
-  int stage = 0;
-  uint32_t phase = 0;
+  int stage = 0, qslot = 0;
+  uint32_t phase = 0, qphase = 0;
 
   if (warp >= kConsumerWarps) {
     // ===================== TMA producer (one lane of the producer warpgroup) =====================
@@ -146,10 +175,18 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
       for (int64_t round = 0;; round++) {
-        const int64_t item = snake_item(round, blockIdx.x, gridDim.x);
-        if (item >= total) { if (round * gridDim.x >= total) break; else continue; }
-        const int jt = g.T - 1 - (int)(item / g.n_rb);
-        const int rb = (int)(item % g.n_rb);
+        // next item: atomic counter (dynamic) or boustrophedon over the static order; published through the item queue
+        int64_t item;
+        if (g.counter) item = atomicAdd(g.counter, 1);
+        else { item = snake_item(round, blockIdx.x, gridDim.x); if (item >= total && round * gridDim.x < total) continue; }
+        const bool done = item >= total;
+        mbar_wait(qempty_bar(qslot), qphase ^ 1u);
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(q_items + 4u * qslot), "r"(done ? -1 : (int)item) : "memory");
+        mbar_arrive(qfull_bar(qslot));
+        if (++qslot == kQueueDepth) { qslot = 0; qphase ^= 1u; }
+        if (done) break;
+        int jt, rb;
+        decode_item(g, item, jt, rb);
         const int c0 = g.N - kBN * (g.T - jt);          // first column of the tile (may be < 0 for jt == 0)
         const int nk = (c0 + kBN + kBK - 1) / kBK;      // k runs to the end of the diagonal block
         for (int ks = 0; ks < nk; ks++) {
@@ -175,11 +212,16 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
   const uint32_t b_row0 = (uint32_t)(warp_n * 8 + gq) * 128u;   // + nt*32*128
   int epi_buf = 0;
 
-  for (int64_t round = 0;; round++) {
-    const int64_t item = snake_item(round, blockIdx.x, gridDim.x);
-    if (item >= total) { if (round * gridDim.x >= total) break; else continue; }
-    const int jt = g.T - 1 - (int)(item / g.n_rb);
-    const int rb = (int)(item % g.n_rb);
+  for (;;) {
+    mbar_wait(qfull_bar(qslot), qphase);
+    int item;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(q_items + 4u * qslot) : "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(qempty_bar(qslot));
+    if (++qslot == kQueueDepth) { qslot = 0; qphase ^= 1u; }
+    if (item < 0) break;
+    int jt, rb;
+    decode_item(g, item, jt, rb);
     const int c0 = g.N - kBN * (g.T - jt);
     const int nk = (c0 + kBN + kBK - 1) / kBK;
 
