@@ -284,6 +284,25 @@ def test_sn_moments_reproduce_chi2(engines):
     assert np.max(np.abs(chi2 - direct) / np.abs(direct)) < 1e-9  # cancellation: M ~ -19.5 enters squared
 
 
+def test_profile_grid_closed_forms(engines):
+    """Config-4 machinery (not in the reference): offset profiled analytically == brute-force minimum over M of the engine's
+    own chi2, and the analytic H0 axis == explicit evaluation at that H0."""
+    from cosmology_model_fit_b200.profile import sn_profile_grid
+    e = engines("sn_pantheon")  # theta = (M, H0, Om, v)
+    om, v, h0 = np.linspace(0.2, 0.45, 6), np.linspace(-2.0, 2.0, 5), np.array([62.0, 70.0, 74.5])
+    chi2, mstar = sn_profile_grid(e, {2: om, 3: v}, h0_axis=h0, h0_ref=70.0)
+    assert chi2.shape == (6, 5, 3)
+    for i, j, k in ((0, 0, 0), (3, 2, 1), (5, 4, 2)):
+        base = np.array([0.0, h0[k], om[i], v[j]])
+        M = mstar[i, j, k]
+        rows = np.array([base + [M + d, 0, 0, 0] for d in (-0.01, 0.0, 0.01)])
+        c = e.chi_squared(rows)
+        assert abs(c[1] - chi2[i, j, k]) < 1e-6 * max(1.0, abs(c[1]))   # value at the analytic minimum
+        assert c[0] > c[1] and c[2] > c[1]                                # and it is a minimum
+    full, _ = sn_profile_grid(e, {1: h0, 2: om, 3: v})                     # H0 as an explicit (GEMM) axis
+    assert np.max(np.abs(np.moveaxis(full, 0, -1) - chi2)) < 1e-6 * np.max(np.abs(chi2))
+
+
 def test_full_size_linearity_property(engines):
     """Size-independent check at the benchmark batch size: chi2 is quadratic in the magnitude offset, so the
     second difference in M is the constant 2 u.u for every row."""
