@@ -44,7 +44,7 @@ WORKER = textwrap.dedent("""
         assert np.max(np.abs(got - g["chi2"][:B])) < 1e-7, (dist.get_rank(), B)
     dist.barrier()
     dist.destroy_process_group()
-    print("rank", os.environ["RANK"], "ok")
+    sys.stdout.write("rank%sok\n" % os.environ["RANK"]); sys.stdout.flush()
 """)
 
 
@@ -57,4 +57,4 @@ def test_sharded_engine_gloo(tmp_path, world):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count(" ok") == world
+    assert res.stdout.count("ok") == world
