@@ -44,7 +44,7 @@ WORKER = textwrap.dedent("""
         assert np.max(np.abs(got - g["chi2"][:B])) < 1e-7, (dist.get_rank(), B)
     dist.barrier()
     dist.destroy_process_group()
-    sys.stdout.write("rank%sok\n" % os.environ["RANK"]); sys.stdout.flush()
+    print("rank" + os.environ["RANK"] + "ok", flush=True)
 """)
 
 
