@@ -230,6 +230,8 @@ static int validate(const cl_spec* s) {
     if (!col_ok(s->col_offset, false)) return fail(nullptr, CL_E_INVALID, "col_offset out of range");
     if (s->n_vel < 0 || s->n_vel > CL_MAX_VEL || (s->n_vel > 0 && !s->sn_vel_weight)) return fail(nullptr, CL_E_INVALID, "bad velocity templates");
     for (int k = 0; k < s->n_vel; k++) if (!col_ok(s->col_vel[k], true)) return fail(nullptr, CL_E_INVALID, "col_vel out of range");
+    if (s->n_lin < 0 || s->n_lin > CL_MAX_VEL || (s->n_lin > 0 && !s->sn_lin_template)) return fail(nullptr, CL_E_INVALID, "bad linear templates");
+    for (int k = 0; k < s->n_lin; k++) if (!col_ok(s->col_lin[k], true)) return fail(nullptr, CL_E_INVALID, "col_lin out of range");
   }
   if (s->n_bao > 0) {
     if (!s->bao_z || !s->bao_value || !s->bao_qty || !s->bao_inv_cov) return fail(nullptr, CL_E_INVALID, "BAO block has NULL arrays");
@@ -365,6 +367,10 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
       TRY(upload(c, obsp.data(), obsp.size(), &d.sn_obsp));
     }
     if (s.n_vel > 0) TRY(upload(c, s.sn_vel_weight, (size_t)n * s.n_vel, &d.sn_vel_w));
+    if (s.sn_mu_fixed) TRY(upload(c, s.sn_mu_fixed, (size_t)n, &d.sn_mu_fixed));
+    d.n_lin = s.n_lin;
+    for (int k = 0; k < CL_MAX_VEL; k++) d.col_lin[k] = k < s.n_lin ? s.col_lin[k] : 0;
+    if (s.n_lin > 0) TRY(upload(c, s.sn_lin_template, (size_t)n * s.n_lin, &d.sn_lin_t));
     // factor handling
     std::vector<double> Lbuf;
     const double* L = s.sn_mat;

@@ -34,6 +34,9 @@ struct DevSpec {
   const double2* sn_zs;    // [n_sn] {1 + z_cmb, w} with a +-1 step template, {z_cmb, 0} without one (fast path)
   const double* sn_obsp;   // [n_sn] obs - 25 - 5 log10(1 + z_hel)
   const double *sn_vel_w, *sn_mat_small;
+  const double* sn_mu_fixed;  // nullable [n_sn], NaN = model
+  const double* sn_lin_t;     // [n_lin][n_sn]
+  int n_lin, col_lin[CL_MAX_VEL];
   const double2* logtab;   // [128] {1/c_j, log10(c_j)} for fast_5log10 (second entry scaled by 5)
   double vel_scale;
   // BAO block

@@ -455,7 +455,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       const int64_t ld = a.mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
       const bool to_smem = s.sn_small && a.mode == MODE_EVAL;
-      if (s.grid_uniform && (s.n_vel == 0 || s.vel_pm1)) {
+      if (s.grid_uniform && (s.n_vel == 0 || s.vel_pm1) && s.sn_mu_fixed == nullptr && s.n_lin == 0) {
         // fast path.  Static per-SN operands: zs = {1 + z_cmb, w} (or {z_cmb, 0} without a velocity template) and
         // obsp = obs - 25 - 5 log10(1 + z_hel), so that delta = obsp - offset - 5 log10 D_M(z_cosmo):
         // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)), D_M(z_cmb) cancels.
@@ -530,8 +530,17 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
             else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
           }
           const double DM = hermite_dm(s, sm.gd, sm.off, zq);
-          const double mu = 25.0 + 5 * log10(p1.x * DM);
-          const double d = (p1.y - offset) - mu;
+          double mu;
+          if (s.sn_mu_fixed != nullptr && isfinite(__ldg(s.sn_mu_fixed + i))) {
+            // SH0ES calibrator: fixed distance modulus, mu_corr = 5 log10(D_M(z_cosmo)/D_M(z_cmb)) still applies
+            mu = __ldg(s.sn_mu_fixed + i);
+            if (s.n_vel > 0) mu += 5.0 * log10(DM / hermite_dm(s, sm.gd, sm.off, p0.x));
+          } else {
+            mu = 25.0 + 5 * log10(p1.x * DM);
+          }
+          double lin = 0.0;
+          for (int k = 0; k < s.n_lin; k++) lin += th[s.col_lin[k]] * __ldg(s.sn_lin_t + (size_t)k * n_sn + i);
+          const double d = (p1.y - (offset + lin)) - mu;
           if (to_smem) sm.vec[CL_MAX_BAO + CL_MAX_CC + i] = d; else Rrow[i] = d;
         }
       }

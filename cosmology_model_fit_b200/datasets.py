@@ -66,3 +66,11 @@ def cosmic_chronometers(root=None):
     """(z, H, cov) (y2005cc/data.py:5-40)."""
     d = _load("data_cc.npz", root)
     return d["z"], d["H"], d["cov"]
+
+
+def pantheon_plus_shoes(root=None):
+    """(z_cmb, z_hel, m_b, ceph_dist, cov): calibrators kept at any redshift, N=1657 (y2022pantheonSHOES/data_shoes.py:24-39)."""
+    d = _load("data_pantheon_plus.npz", root)
+    cov = synthetic_sn_covariance(d["m_b_corr_err_DIAG"])
+    sel = np.where((d["IS_CALIBRATOR"] == 1) | (d["zHD"] > 0.01))[0]
+    return d["zHD"][sel], d["zHEL"][sel], d["m_b_corr"][sel], d["CEPH_DIST"][sel], cov[np.ix_(sel, sel)]

@@ -76,6 +76,19 @@ def sn_pantheon(sn, z_turn=0.15):
     return _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 3)
 
 
+def sn_pantheon_and_sh0es(sn_shoes, z_turn=0.15):
+    """sn/pantheon_and_sh0es.py: theta = (M, H0, Om, v); mu of the Cepheid calibrators is their Cepheid distance (:63-69);
+    the z_turn step applies to non-calibrators only (:47)."""
+    z_cmb, z_hel, mb, ceph, cov = sn_shoes
+    ceph_mask = np.asarray(ceph) != -9
+    bounds = np.array([(-20.0, -18.5), (60.0, 85.0), (0.1, 0.6), (-3.5, 3.5)])  # :77-84
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=1, col_Om=2, z_grid=_grid(z_cmb), bounds=bounds)
+    _sn_block(sp, (z_cmb, z_hel, mb, cov), S.SN_CHOLESKY, z_turn, 0, 3)
+    sp.sn_vel_weight = np.where((np.asarray(z_cmb) <= z_turn) & ~ceph_mask, 1.0, -1.0)
+    sp.sn_mu_fixed = np.where(ceph_mask, np.asarray(ceph, dtype=np.float64), np.nan)
+    return sp
+
+
 def sn_des5y(sn, z_turn=0.11):
     """sn/des5y.py: theta = (dM, H0, Om, v); late LCDM; step at z_cmb <= 0.11 (sn/des5y.py:44-45)."""
     sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=1, col_Om=2, z_grid=_grid(sn[0]))
@@ -153,6 +166,18 @@ def bao_desi_cmb_pantheon(sn, desi, consts=None, z_turn=0.15):
     sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
                         cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0], desi[0]))
     _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 4)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_cmb_pantheon_H0trgb(sn, desi, consts=None):
+    """bao/desi_cmb_pantheon_H0trgb.py: theta = (M, H0, obh2, och2, v_flow); the flow enters as a linear magnitude
+    template 100 v (5/ln 10)/(c z) (:103-106); TRGB H0 term inside chi2 (:124)."""
+    consts = consts or S.cmb_planck_act()
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0], desi[0]), gauss_chi2=((1, *H0_TRGB),))
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    sp.col_lin = (4,)
+    sp.sn_lin_template = 100 * (5 / np.log(10)) / (S.C_KMS * np.asarray(sn[0], dtype=np.float64))
     return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
 
 

@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-CL_ABI_VERSION = 3
+CL_ABI_VERSION = 4
 CL_MAX_DIM, CL_MAX_VEL, CL_MAX_GAUSS, CL_MAX_BAO, CL_MAX_GL, CL_MAX_CC, CL_SN_SMALL_MAX = 12, 3, 4, 32, 128, 64, 64
 
 FAMILY_LATE, FAMILY_FULL = 0, 1
@@ -57,6 +57,7 @@ class ClSpec(C.Structure):
         ("n_sn", C.c_int32), ("sn_zcmb", _dp), ("sn_zhel", _dp), ("sn_obs", _dp),
         ("sn_cov_form", C.c_int32), ("sn_mat", _dp), ("col_offset", C.c_int32), ("n_vel", C.c_int32),
         ("col_vel", C.c_int32 * CL_MAX_VEL), ("sn_vel_weight", _dp), ("vel_scale", C.c_double), ("vel_mode", C.c_int32),
+        ("sn_mu_fixed", _dp), ("n_lin", C.c_int32), ("col_lin", C.c_int32 * CL_MAX_VEL), ("sn_lin_template", _dp),
         ("n_bao", C.c_int32), ("bao_z", _dp), ("bao_value", _dp), ("bao_qty", _ip), ("bao_inv_cov", _dp),
         ("bao_dh_mode", C.c_int32), ("rd_mode", C.c_int32), ("rd_fixed", C.c_double), ("col_rd", C.c_int32),
         ("cmb_mode", C.c_int32), ("cmb_prior", C.c_double * 3), ("cmb_weight", C.c_double * 9),
@@ -244,6 +245,9 @@ class LikelihoodSpec:
     sn_vel_weight: np.ndarray | None = None
     vel_scale: float = 100.0
     vel_mode: int = VEL_DIVIDE
+    sn_mu_fixed: np.ndarray | None = None      # [n_sn], NaN where the model applies (SH0ES calibrators)
+    col_lin: tuple = ()
+    sn_lin_template: np.ndarray | None = None  # [n_lin, n_sn]
     # BAO
     bao_z: np.ndarray | None = None
     bao_value: np.ndarray | None = None
@@ -323,6 +327,19 @@ class LikelihoodSpec:
                 for i, col in enumerate(self.col_vel):
                     s.col_vel[i] = int(col)
             s.vel_scale, s.vel_mode = float(self.vel_scale), int(self.vel_mode)
+            if self.sn_mu_fixed is not None:
+                mf = arr(self.sn_mu_fixed)
+                if mf.size != n:
+                    raise ValueError("sn_mu_fixed must have n_sn entries")
+                s.sn_mu_fixed = _ptr(mf)
+            s.n_lin = len(self.col_lin)
+            if s.n_lin > CL_MAX_VEL:
+                raise ValueError("too many linear templates")
+            if s.n_lin:
+                lt = arr(np.asarray(self.sn_lin_template, dtype=np.float64).reshape(s.n_lin, n))
+                s.sn_lin_template = _ptr(lt)
+                for i, col in enumerate(self.col_lin):
+                    s.col_lin[i] = int(col)
         # BAO
         if self.bao_z is not None and len(self.bao_z) > 0:
             bz, bv, bw = arr(self.bao_z), arr(self.bao_value), arr(self.bao_inv_cov)

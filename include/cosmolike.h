@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CL_ABI_VERSION 3u
+#define CL_ABI_VERSION 4u
 #define CL_MAX_DIM 12      /* max length of one parameter vector theta */
 #define CL_MAX_VEL 3       /* max peculiar-velocity template amplitudes (step: 1, dipole xyz: 3) */
 #define CL_MAX_GAUSS 4     /* max extra Gaussian terms of each kind */
@@ -129,6 +129,13 @@ typedef struct cl_spec {
   const double* sn_vel_weight; /* [n_vel*n_sn] e.g. +1 where z_cmb<=z_turn else -1 (sn/pantheon.py:46) */
   double vel_scale;        /* 100 when v is sampled in units of 100 km/s */
   int32_t vel_mode;        /* CL_VEL_* */
+  const double* sn_mu_fixed; /* nullable [n_sn]: where finite, the model distance modulus 25 + 5 log10(d_L) is replaced by this
+                                value (SH0ES Cepheid calibrators, sn/pantheon_and_sh0es.py:47,63-69; mu_corr still applies);
+                                NaN = use the model */
+  int32_t n_lin;           /* linear-in-magnitude templates: delta -= sum_k theta[col_lin[k]] * sn_lin_template[k][i]
+                              (bao/desi_cmb_pantheon_H0trgb.py:103-106: 100 (5/ln10) / (c z_i)) */
+  int32_t col_lin[CL_MAX_VEL];
+  const double* sn_lin_template; /* [n_lin*n_sn] */
 
   /* ---- BAO block ---- */
   int32_t n_bao;              /* 0 = none */

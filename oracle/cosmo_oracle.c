@@ -341,8 +341,12 @@ static void sn_residuals(const cl_spec* s, const double* th, work_t* w, double* 
       double DMc = pchip_eval(z_cosmo, s->z_grid, w->cum_dm, w->dh_grid, G, 1);
       mu_corr = 5.0 * log10(DMc / DM);
     }
-    double mu = 25.0 + 5 * log10((1.0 + s->sn_zhel[i]) * DM);
-    delta[i] = s->sn_obs[i] - offset - mu_corr - mu;
+    /* sn/pantheon_and_sh0es.py:63-69: mu_pred = where(ceph_mask, ceph_dists, mu_theory(DM_cmb)) */
+    double mu = (s->sn_mu_fixed && isfinite(s->sn_mu_fixed[i])) ? s->sn_mu_fixed[i]
+                                                                : 25.0 + 5 * log10((1.0 + s->sn_zhel[i]) * DM);
+    double lin = 0.0; /* bao/desi_cmb_pantheon_H0trgb.py:103-106 */
+    for (int k = 0; k < s->n_lin; k++) lin += th[s->col_lin[k]] * s->sn_lin_template[(size_t)k * n + i];
+    delta[i] = s->sn_obs[i] - (offset + lin) - mu_corr - mu;
   }
 }
 

@@ -34,6 +34,7 @@ desi = _memo(datasets.desi_dr2)
 desi_fs = _memo(datasets.desi_fs_lya)
 cc = _memo(datasets.cosmic_chronometers)
 pantheon_pos = _memo(datasets.pantheon_plus_positions)
+pantheon_shoes = _memo(datasets.pantheon_plus_shoes)
 
 SPECS = {
     "sn_pantheon": lambda: fits.sn_pantheon(pantheon()),
@@ -50,12 +51,15 @@ SPECS = {
     "bao_desi_bbn": lambda: fits.bao_desi_bbn(desi()),
     "bao_desi_pantheon_cc": lambda: fits.bao_desi_pantheon_cc(pantheon(), desi(), cc()),
     "sn_pantheon_dipole_xyz": lambda: fits.sn_pantheon_dipole_xyz(pantheon(), *pantheon_pos()),
+    "sn_pantheon_and_sh0es": lambda: fits.sn_pantheon_and_sh0es(pantheon_shoes()),
+    "bao_desi_cmb_pantheon_H0trgb": lambda: fits.bao_desi_cmb_pantheon_H0trgb(pantheon(), desi()),
 }
 
 #: cases whose golden file has a plain chi2[n] for theta[n]
 CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cmb_union3",
               "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y",
-              "ohd_cc", "bao_desi_bbn", "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz"]
+              "ohd_cc", "bao_desi_bbn", "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz",
+              "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb"]
 
 
 def spec(name):

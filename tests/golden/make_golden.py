@@ -49,6 +49,8 @@ def dump_data_columns():
         RA=df["RA"].to_numpy(np.float64),
         DEC=df["DEC"].to_numpy(np.float64),
         IDSURVEY=df["IDSURVEY"].to_numpy(np.int32),
+        CEPH_DIST=df["CEPH_DIST"].to_numpy(np.float64),
+        IS_CALIBRATOR=df["IS_CALIBRATOR"].to_numpy(np.int32),
     )
     df = pd.read_csv(f"{REF}/y2025DESdovekie/raw-data/distances.csv", sep=r"\s+")
     np.savez_compressed(
@@ -112,11 +114,22 @@ def _stub_pantheon():
     m = types.ModuleType("y2022pantheonSHOES.data")
     m.get_data = get_data
     m.get_data_with_position = get_data_with_position
+    # y2022pantheonSHOES/data_shoes.py:24-39 (calibrators kept regardless of redshift)
+    sel = np.where((d["IS_CALIBRATOR"] == 1) | (d["zHD"] > 0.01))[0]
+
+    def get_data_shoes(z_cut_ceph=0.0):
+        return ("Pantheon+ and SH0ES", d["zHD"][sel], d["zHEL"][sel], d["m_b_corr"][sel], d["CEPH_DIST"][sel],
+                cov_full[np.ix_(sel, sel)])
+
+    ms = types.ModuleType("y2022pantheonSHOES.data_shoes")
+    ms.get_data = get_data_shoes
     pkg = types.ModuleType("y2022pantheonSHOES")
     pkg.__path__ = []
     pkg.data = m
+    pkg.data_shoes = ms
     sys.modules["y2022pantheonSHOES"] = pkg
     sys.modules["y2022pantheonSHOES.data"] = m
+    sys.modules["y2022pantheonSHOES.data_shoes"] = ms
 
 
 def _stub_des():
@@ -378,6 +391,30 @@ def case_sn_pantheon_dipole_xyz():
     att = 0.5 * (1.0 - np.tanh((ref.z_cmb - 0.10) / 0.02))
     w = np.vstack([ref.nx, ref.ny, ref.nz]) * att * ref.survey_mask
     return dict(theta=theta, chi2=chi2, bounds=bounds, z_grid=ref.z_grid, weights=w)
+
+
+def case_sn_pantheon_and_sh0es():
+    """sn/pantheon_and_sh0es.py: Cepheid distances replace mu for the calibrators; step mask excludes them."""
+    _stub_pantheon()
+    _enter_reference()
+    import sn.pantheon_and_sh0es as ref
+
+    theta = uniform_theta(ref.bounds, 24)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    return dict(theta=theta, chi2=chi2, bounds=ref.bounds, z_grid=ref.z_grid, n_sn=np.int64(ref.z_cmb.size),
+                n_ceph=np.int64(ref.ceph_mask.sum()))
+
+
+def case_bao_desi_cmb_pantheon_H0trgb():
+    """bao/desi_cmb_pantheon_H0trgb.py: linear-in-magnitude flow template + TRGB H0 chi2 term."""
+    _stub_pantheon()
+    _enter_reference()
+    import bao.desi_cmb_pantheon_H0trgb as ref
+
+    bounds = np.array([(-20.0, -19.0), (60.0, 75.0), (0.019, 0.025), (0.01, 0.25), (-1.2, 3.2)])
+    theta = uniform_theta(bounds, 24)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    return dict(theta=theta, chi2=chi2, bounds=bounds, z_grid=ref.z_grid)
 
 
 def case_interpolator():
