@@ -122,6 +122,28 @@ def bao_desi(desi, des_y6=DES_Y6_BAO):
     return _bao_block(sp, bao, S.DH_PCHIP, S.RD_FIXED, 147.09)
 
 
+def bao_desi_cmb(desi, consts=None):
+    """bao/desi_cmb.py: theta = (H0, obh2, och2, w0); thawing; early-LCDM compressed CMB (theta*, omega_b, omega_m);
+    exact D_H; emcee vectorize=True."""
+    consts = consts or S.cmb_early_lcdm()
+    bounds = np.array([(50.0, 80.0), (0.020, 0.024), (0.05, 0.30), (-1.0, 0.0)])  # bao/desi_cmb.py:105-112
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_FULL, de_model=S.DE_THAWING, col_H0=0, col_obh2=1, col_och2=2, col_w0=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(desi[0]), bounds=bounds)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_union3_obh2_theta_star(sn, desi, consts=None):
+    """bao/desi_union3_obh2_theta_star.py: theta = (dM, H0, obh2, och2, v); LCDM; CMB rows [1:] (l_A, omega_b) weighted by
+    the inverse of the 2x2 sub-covariance (:17,124-128)."""
+    consts = consts or S.cmb_planck_act()
+    w = np.zeros((3, 3))
+    w[1:, 1:] = np.linalg.inv(consts.covariance[1:, 1:])
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=w, z_grid=_grid(sn[0], desi[0]))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 0, 4)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
 def bao_desi_cmb_union3(sn, desi_fs_lya, consts=None, des_y6=DES_Y6_BAO, sixdf=SIXDF_BAO, de_model=S.DE_LCDM):
     """bao/desi_cmb_union3.py (config 2): theta = (dM, H0, obh2, och2, v [, w0, wa])."""
     consts = consts or S.cmb_planck_act()

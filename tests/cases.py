@@ -53,13 +53,15 @@ SPECS = {
     "sn_pantheon_dipole_xyz": lambda: fits.sn_pantheon_dipole_xyz(pantheon(), *pantheon_pos()),
     "sn_pantheon_and_sh0es": lambda: fits.sn_pantheon_and_sh0es(pantheon_shoes()),
     "bao_desi_cmb_pantheon_H0trgb": lambda: fits.bao_desi_cmb_pantheon_H0trgb(pantheon(), desi()),
+    "bao_desi_cmb": lambda: fits.bao_desi_cmb(desi()),
+    "bao_desi_union3_obh2_theta_star": lambda: fits.bao_desi_union3_obh2_theta_star(union3(), desi()),
 }
 
 #: cases whose golden file has a plain chi2[n] for theta[n]
 CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cmb_union3",
               "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y",
               "ohd_cc", "bao_desi_bbn", "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz",
-              "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb"]
+              "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb", "bao_desi_cmb", "bao_desi_union3_obh2_theta_star"]
 
 
 def spec(name):

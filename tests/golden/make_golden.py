@@ -417,6 +417,31 @@ def case_bao_desi_cmb_pantheon_H0trgb():
     return dict(theta=theta, chi2=chi2, bounds=bounds, z_grid=ref.z_grid)
 
 
+def case_bao_desi_cmb():
+    """bao/desi_cmb.py: early-LCDM compression (theta*, omega_b, omega_m), thawing w0, emcee vectorize=True (float32)."""
+    _enter_reference()
+    import bao.desi_cmb as ref
+
+    theta = uniform_theta(ref.bounds, 32)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    cmbd = np.array([ref.cmb.cmb_distances(t[1], t[2], t) for t in theta])
+    batch = np.vstack([theta, [[85.0, 0.022, 0.12, -0.5]]])
+    logp32 = ref.log_probability_vect(np.ascontiguousarray(batch))
+    return dict(theta=theta, chi2=chi2, cmb_distances=cmbd, batch=batch, logp32=logp32, bounds=ref.bounds, z_grid=ref.z_grid)
+
+
+def case_bao_desi_union3_obh2_theta_star():
+    """bao/desi_union3_obh2_theta_star.py: CMB rows [1:] with the inverse of the sub-covariance (no shift parameter R)."""
+    _enter_reference()
+    import bao.desi_union3_obh2_theta_star as ref
+
+    bounds = np.array([(-1.0, 1.0), (50.0, 90.0), (0.01, 0.03), (0.05, 0.3), (-12.0, 5.0)])
+    theta = uniform_theta(bounds, 32)
+    chi2 = np.array([ref.chi_squared(t) for t in theta])
+    c_cmb = np.array([ref.chi2_cmb(t) for t in theta])
+    return dict(theta=theta, chi2=chi2, chi2_cmb=c_cmb, bounds=bounds, z_grid=ref.z_grid)
+
+
 def case_interpolator():
     """interpolator.py known answers on non-uniform and monotone/non-monotone data (pchip + hermite)."""
     _enter_reference()

@@ -155,6 +155,22 @@ def test_cc_normalisation_and_multiplicative_shift(engines):
     chi2_close(-2 * lp[fin], -2 * g["logp"][fin])
 
 
+def test_early_lcdm_cmb_mode_and_float32_batch(engines):
+    """bao/desi_cmb.py: (theta*, omega_b, omega_m) compression and the float32 emcee batch wrapper (:137-143)."""
+    g = golden("bao_desi_cmb")
+    e = engines("bao_desi_cmb")
+    assert rel_err(e.cmb(g["theta"])[:, :3], g["cmb_distances"]) < DIST_RTOL
+    lp32 = e.log_probs_vectorized(g["batch"])
+    assert np.array_equal(np.isneginf(lp32), np.isneginf(g["logp32"]))
+    fin = np.isfinite(g["logp32"])
+    assert np.max(np.abs(lp32[fin] - g["logp32"][fin]) / np.abs(g["logp32"][fin])) < 1e-6
+
+
+def test_cmb_subselection_weight(engines):
+    g = golden("bao_desi_union3_obh2_theta_star")
+    chi2_close(engines("bao_desi_union3_obh2_theta_star").components(g["theta"])[:, 2], g["chi2_cmb"])
+
+
 def test_bao_desi_bbn_theory(engines):
     g = golden("bao_desi_bbn")
     assert rel_err(engines("bao_desi_bbn").bao_theory(g["theta"][:8]), g["theory"]) < DIST_RTOL
