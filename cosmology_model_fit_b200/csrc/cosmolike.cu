@@ -313,6 +313,7 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
   d.col_H0 = s.col_H0; d.col_Om = s.col_Om; d.Om_is_physical = s.Om_is_physical; d.col_obh2 = s.col_obh2; d.col_och2 = s.col_och2;
   d.col_w0 = s.de_model == CL_DE_LCDM ? -1 : s.col_w0; d.col_wa = s.de_model == CL_DE_CPL ? s.col_wa : -1;
   d.H0_fixed = s.H0_fixed; d.H0_scale = s.H0_scale; d.k = s.cmbc;
+  d.nu_inv_rho0 = s.cmbc.nu_rho0 != 0.0 ? 1.0 / s.cmbc.nu_rho0 : 0.0;
   // grid
   d.G = s.z_grid ? s.n_grid : 0;
   if (s.z_grid) {
@@ -323,6 +324,22 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
     for (int i = 0; uni && i < s.n_grid - 1; i++) uni = (s.z_grid[i] == (double)i * step);
     d.grid_uniform = uni ? 1 : 0;
     d.step = step; d.inv_step = 1.0 / step; d.z_last = s.z_grid[s.n_grid - 1];
+    if (uni) {
+      std::vector<double> ln1pz(s.n_grid + 17);
+      for (int i = 0; i < s.n_grid + 17; i++) ln1pz[i] = (double)log1pl((long double)i * (long double)step);
+      TRY(upload(c, ln1pz.data(), ln1pz.size(), &d.grid_ln1pz));
+      if (s.family == CL_FAMILY_FULL) {
+        // Omnu_z(z_i) with the reference's formula (cmb/data_planck_act_compression.py:53-66); independent of theta
+        std::vector<double> om(s.n_grid + 17);
+        const cl_cmb_consts& k = s.cmbc;
+        for (int i = 0; i < s.n_grid + 17; i++) {
+          double zp1 = 1.0 + (double)i * step, r = k.nu_m0 / zp1, mz = r * r, ws = 0.0;
+          for (int q = 0; q < 5; q++) ws += sqrt(k.nu_q2[q] + mz) * k.nu_w[q];
+          om[i] = zp1 * zp1 * zp1 * zp1 * ws / k.nu_rho0;
+        }
+        TRY(upload(c, om.data(), om.size(), &d.grid_omnu));
+      }
+    }
   }
   {  // fast_log10 table: c_j = 1 + (j + 1/2)/128; entry = {fl(1/c_j), -log10(fl(1/c_j))}
     std::vector<double> tab(256);

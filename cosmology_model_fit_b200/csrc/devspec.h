@@ -21,8 +21,11 @@ struct DevSpec {
   int col_H0, col_Om, Om_is_physical, col_obh2, col_och2, col_w0, col_wa;
   double H0_fixed, H0_scale;
   cl_cmb_consts k;
+  double nu_inv_rho0;  // 1 / k.nu_rho0
   // z grid
   const double* z_grid;
+  const double* grid_omnu;   // [G + 17] Omnu_z(z) at the same nodes (theta-independent): FULL family grid pass
+  const double* grid_ln1pz;  // [G + 17] ln(1 + z) at the np.linspace nodes (and 17 nodes beyond): wCDM / CPL grid pass
   int G, grid_uniform;
   double step;      // z_grid[i] == i*step bit-for-bit when grid_uniform (np.linspace from 0), except the last node
   double z_last;    // z_grid[G-1] (np.linspace stores `stop` there exactly)

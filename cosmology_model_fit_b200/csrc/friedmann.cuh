@@ -91,15 +91,17 @@ __constant__ double kLog5Poly[8] = {0.0, 2.171472409516259, -1.0857362047581296,
                                     0.4342944819032518, -0.36191206825270983, 0.3102103442166084};
 __constant__ double kLog5Two[2] = {1.5051499791443348 /* 30-bit head of 5 log10(2): e*head is exact */, -8.244288170221258e-10};
 
-// 5-node massive-neutrino density (cmb/data_planck_act_compression.py:53-66)
-__device__ __forceinline__ double omnu_z(const cl_cmb_consts& k, double zp1) {
-  double r = k.nu_m0 / zp1;
-  double mz = r * r;
-  double f0 = fast_sqrt(k.nu_q2[0] + mz), f1 = fast_sqrt(k.nu_q2[1] + mz), f2 = fast_sqrt(k.nu_q2[2] + mz);
-  double f3 = fast_sqrt(k.nu_q2[3] + mz), f4 = fast_sqrt(k.nu_q2[4] + mz);
-  double ws = f0 * k.nu_w[0] + f1 * k.nu_w[1] + f2 * k.nu_w[2] + f3 * k.nu_w[3] + f4 * k.nu_w[4];
-  double z2 = zp1 * zp1;
-  return z2 * z2 * ws / k.nu_rho0;
+// 5-node massive-neutrino density (cmb/data_planck_act_compression.py:53-66):
+//   Omnu_z = zp1^4 sum_k w_k sqrt(q_k^2 + (m0/zp1)^2) / rho0 = zp1^3 sum_k w_k sqrt(q_k^2 zp1^2 + m0^2) / rho0
+// (the second form needs no division; it differs from the first by rounding only)
+__device__ __forceinline__ double omnu_z(const DevSpec& s, double zp1) {
+  const cl_cmb_consts& k = s.k;
+  const double z2 = zp1 * zp1, m2 = k.nu_m0 * k.nu_m0;
+  const double f0 = fast_sqrt(fma(k.nu_q2[0], z2, m2)), f1 = fast_sqrt(fma(k.nu_q2[1], z2, m2));
+  const double f2 = fast_sqrt(fma(k.nu_q2[2], z2, m2)), f3 = fast_sqrt(fma(k.nu_q2[3], z2, m2));
+  const double f4 = fast_sqrt(fma(k.nu_q2[4], z2, m2));
+  const double ws = f0 * k.nu_w[0] + f1 * k.nu_w[1] + f2 * k.nu_w[2] + f3 * k.nu_w[3] + f4 * k.nu_w[4];
+  return (z2 * zp1) * ws * s.nu_inv_rho0;
 }
 
 template <int DE>
@@ -123,9 +125,25 @@ __device__ __forceinline__ double E2_of_zp1(const DevSpec& s, const Cosmo& c, do
   }
   double radiation = c.Or * (cubed * zp1);
   double matter = c.Obc * cubed;
-  double neutrino = c.Onu * omnu_z(s.k, zp1);
+  double neutrino = c.Onu * omnu_z(s, zp1);
   double de = (DE == CL_DE_LCDM) ? c.Ode : c.Ode * fde<DE>(c, z, zp1, cubed);
   return radiation + matter + de + neutrino;
+}
+// E^2 at grid node i of the np.linspace grid.  Two theta-independent node tables (built once by cl_create) take the
+// expensive pieces out of the 4000-node loop: ln(1+z_i) turns the wCDM / CPL power into one exp (instead of pow + exp +
+// a division), and Omnu_z(z_i) replaces five square roots per node in the FULL family.
+template <int FAM, int DE>
+__device__ __forceinline__ double E2_at_node(const DevSpec& s, const Cosmo& c, int i, double zp1) {
+  const double cubed = zp1 * zp1 * zp1;
+  double f = 1.0;  // dark-energy density factor
+  if (DE == CL_DE_WCDM) f = exp(3 * (1.0 + c.w0) * __ldg(s.grid_ln1pz + i));
+  if (DE == CL_DE_CPL)  // z/(1+z) = 1 - 1/(1+z)
+    f = exp(fma(3 * (1 + c.w0 + c.wa), __ldg(s.grid_ln1pz + i), -3 * c.wa * (1.0 - rcp_pos(zp1))));
+  if (DE == CL_DE_THAWING) f = fde<DE>(c, zp1 - 1.0, zp1, cubed);
+  if (FAM == CL_FAMILY_LATE) return c.Om * cubed + ((DE == CL_DE_LCDM) ? (1.0 - c.Om) : (1.0 - c.Om) * f);
+  // massive neutrinos: the theta-independent Omnu_z(z_i) comes from the static node table
+  const double de = (DE == CL_DE_LCDM) ? c.Ode : c.Ode * f;
+  return c.Or * (cubed * zp1) + c.Obc * cubed + de + c.Onu * __ldg(s.grid_omnu + i);
 }
 template <int FAM, int DE>
 __device__ __forceinline__ double E2_of_z(const DevSpec& s, const Cosmo& c, double z) {
@@ -255,21 +273,25 @@ __device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, dou
   return h00 * (gd[pad_idx(i)].y * ih) + h10 * h_i * d0 + h01 * (gd[pad_idx(i + 1)].y * ih) + h11 * h_i * d1;
 }
 
-// closed-form fits (cmb/data_planck_act_compression.py:86-124)
-__device__ double z_star_fit(const cl_cmb_consts& k, double wb, double wm) {
-  wb = pow(wb, k.zstar_b);
-  wm = pow(wm, k.zstar_m);
-  return pow(wm, -0.7316314841257655) +
-         k.zstar_s1 * 391.6723594873167 * pow(wb, 0.9368102670600895) * pow(wm, -0.35300106475765136) +
-         k.zstar_s2 * 937.4224935298015 * pow(wm, 0.0192950634264157) * pow(wb, -0.04285000485853785);
-}
-__device__ double r_drag_fit(const cl_cmb_consts& k, double wb, double wm) {
-  wb = pow(wb, k.rdrag_b);
-  wm = pow(wm, k.rdrag_m);
-  const double a1 = 0.00257366, a2 = 0.05032, a3 = 0.013, a4 = 0.7720642, a5 = 0.24346362, a6 = 0.00641072,
-               a7 = 0.5350899, a8 = 32.7525, a9 = 0.315473;
-  double den = (a1 * pow(wb, a2)) + (a3 * pow(wb, a4) * pow(wm, a5)) + (a6 * pow(wm, a7));
-  return 1.0 / den - a8 / pow(wm, a9);
+// closed-form fits (cmb/data_planck_act_compression.py:86-124).  Every term of the reference is a product of powers of
+// wb and wm, e.g. (wb^b)^p (wm^m)^q = exp(p b ln wb + q m ln wm): two logs and one exp per term instead of the 14 pow()
+// calls of the literal form (agreement ~4e-16 relative, the fits are needed to 1e-9).
+__device__ __noinline__ void cmb_fits(const cl_cmb_consts& k, double wb, double wm, bool want_zstar, bool want_rdrag,
+                                      double* zstar, double* rdrag) {
+  const double lb = log(wb), lm = log(wm);
+  if (want_zstar) {
+    const double Lb = k.zstar_b * lb, Lm = k.zstar_m * lm;
+    *zstar = exp(-0.7316314841257655 * Lm) +
+             k.zstar_s1 * 391.6723594873167 * exp(0.9368102670600895 * Lb - 0.35300106475765136 * Lm) +
+             k.zstar_s2 * 937.4224935298015 * exp(0.0192950634264157 * Lm - 0.04285000485853785 * Lb);
+  }
+  if (want_rdrag) {
+    const double Lb = k.rdrag_b * lb, Lm = k.rdrag_m * lm;
+    const double a1 = 0.00257366, a2 = 0.05032, a3 = 0.013, a4 = 0.7720642, a5 = 0.24346362, a6 = 0.00641072,
+                 a7 = 0.5350899, a8 = 32.7525, a9 = 0.315473;
+    const double den = a1 * exp(a2 * Lb) + a3 * exp(a4 * Lb + a5 * Lm) + a6 * exp(a7 * Lm);
+    *rdrag = 1.0 / den - a8 * exp(-a9 * Lm);
+  }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -377,12 +399,12 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         run = 1.0;
       } else if (s.grid_uniform) {
         const double Ks = c.K * s.step, zp1_0 = fma((double)i0, s.step, 1.0);
-        double prev = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1_0 - 1.0, zp1_0));
+        double prev = Ks * rsqrt_pos(E2_at_node<FAM, DE>(s, c, i0, zp1_0));
         if (i0 + kPPT < G) {  // all 17 nodes inside the grid
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
             const double zp1 = fma((double)(k + 1), s.step, zp1_0);  // 1 + z_grid[i0+k+1] to 1 ulp
-            const double nxt = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1 - 1.0, zp1));
+            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(s, c, i0 + k + 1, zp1));
             sts_d2(dst + 16u * k, run, prev);
             run = fma(prev + nxt, 0.5, run);
             prev = nxt;
@@ -391,7 +413,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
             const double zp1 = fma((double)(k + 1), s.step, zp1_0);
-            const double nxt = Ks * rsqrt_pos(E2_of_zp1<FAM, DE>(s, c, zp1 - 1.0, zp1));
+            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(s, c, i0 + k + 1, zp1));
             if (i0 + k < G) sts_d2(dst + 16u * k, run, prev);
             if (i0 + k + 1 < G) run = fma(prev + nxt, 0.5, run);
             prev = nxt;
@@ -424,8 +446,10 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (tid == kS12Threads - 1 && (need_cmb || need_rd)) {
       double obh2 = c.obh2;
       double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
-      sm.scal[0] = need_cmb ? z_star_fit(s.k, obh2, wm) : 0.0;
-      sm.scal[1] = need_rd ? r_drag_fit(s.k, obh2, wm) : 0.0;
+      double zs = 0.0, rd = 0.0;
+      cmb_fits(s.k, obh2, wm, need_cmb, need_rd, &zs, &rd);
+      sm.scal[0] = zs;
+      sm.scal[1] = rd;
     }
     __syncthreads();
 
@@ -560,7 +584,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.gd, z) : DH_of_z<FAM, DE>(s, c, z);
       int q = __ldg(s.bao_qty + tid);
       double v;
-      if (q == CL_BAO_DV_OVER_RS) v = pow(z * DH * (DM * DM), 1.0 / 3) / rd;
+      if (q == CL_BAO_DV_OVER_RS) v = cbrt(z * DH * (DM * DM)) / rd;  // reference: x ** (1/3), equal to ~1e-16
       else if (q == CL_BAO_DM_OVER_RS) v = DM / rd;
       else if (q == CL_BAO_DH_OVER_RS) v = DH / rd;
       else v = DM / DH;
