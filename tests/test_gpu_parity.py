@@ -231,6 +231,29 @@ def test_config1_with_vstep_vs_oracle():
         chi2_close(e.chi_squared(t0), g["chi2"])
 
 
+def test_uniform_grids_of_odd_sizes_vs_oracle():
+    """np.linspace grids whose size is not a multiple of the 16-node thread chunk (partial last chunk), the minimum and the
+    maximum grid size."""
+    import oracle.oracle as O
+    from cosmology_model_fit_b200 import Engine, fits
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    from cases import union3, pantheon
+    theta3 = uniform_theta(np.array([(-1.0, 1.0), (0.1, 0.7), (-9.0, 9.0)]), 40, seed=4)
+    for G in (16, 17, 1003, 2049, 4095, 4096):
+        sp = fits.sn_union3_1(union3())
+        sp.z_grid = np.linspace(0, float(np.max(sp.sn_zcmb)) + 0.1, num=G)
+        with Engine(sp) as e:
+            assert "uniform" in e.describe()
+            got, want = e.chi_squared(theta3), O.Oracle(sp).chi_squared(theta3)
+            # a coarse grid changes the physics identically on both sides; parity must still hold
+            chi2_close(got, want)
+    sp = fits.sn_pantheon(pantheon())
+    sp.z_grid = np.linspace(0, float(np.max(sp.sn_zcmb)) + 0.1, num=3001)
+    theta4 = uniform_theta(sp.bounds, 200, seed=6)
+    with Engine(sp) as e:
+        chi2_close(e.chi_squared(theta4), O.Oracle(sp).chi_squared(theta4, nthreads=0))
+
+
 def test_strided_theta_rows(engines):
     """ld > ndim: theta rows embedded in a wider host array (cl_eval's ld argument)."""
     import ctypes as C
