@@ -250,7 +250,56 @@ def sn_pantheon_dipole_xyz(sn, ra, dec, survey_id, z_c=0.10, dz=0.02, target_ids
     return sp
 
 
+def sn_pantheon_dipole(sn, ra, dec, survey_id, ra_fixed_deg=217, dec_fixed_deg=-29, z_c=0.10, dz=0.02,
+                       target_ids=(1, 5, 15, 50, 51, 56, 63, 150)):
+    """sn/pantheon_dipole.py: theta = (M, H0, Om, v); dipole of fixed direction: weight = cos(angle) * attenuation * mask
+    (:14-32, 60-68)."""
+    z_cmb = np.asarray(sn[0], dtype=np.float64)
+    ra_rad, dec_rad = np.deg2rad(ra), np.deg2rad(dec)
+    nx, ny, nz = np.cos(dec_rad) * np.cos(ra_rad), np.cos(dec_rad) * np.sin(ra_rad), np.sin(dec_rad)
+    raf, decf = np.deg2rad(ra_fixed_deg), np.deg2rad(dec_fixed_deg)
+    cos_angle = nx * (np.cos(decf) * np.cos(raf)) + ny * (np.cos(decf) * np.sin(raf)) + nz * np.sin(decf)
+    att = 0.5 * (1.0 - np.tanh((z_cmb - z_c) / dz))
+    mask = np.isin(survey_id, target_ids).astype(int)
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=1, col_Om=2, z_grid=_grid(sn[0]))
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    sp.col_vel = (3,)
+    sp.sn_vel_weight = cos_angle * att * mask
+    return sp
+
+
+def bao_desi_omh2(desi):
+    """bao/desi_omh2.py: theta = (r_d, H0, omega_m, w0); late thawing with Om = omega_m / h^2; r_d sampled; exact D_H."""
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=2, Om_is_physical=True, col_w0=3,
+                        z_grid=_grid(desi[0]), gauss_prior=((2, 0.1430, 0.0011),))
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=0)
+
+
 # --------------------------------------------------------------------------------------------- ohd/*
+def _cc_block(sp, cc, col_fcc, norm_sign=1.0):
+    z, H, cov = cc
+    sp.cc_z, sp.cc_H, sp.cc_inv_cov, sp.col_fcc = z, H, np.linalg.inv(cov), col_fcc
+    sp.cc_logdet, sp.cc_norm_sign = float(np.linalg.slogdet(cov)[1]), norm_sign
+    return sp
+
+
+def ohd_cc_des5y(sn, cc):
+    """ohd/cc_des5y.py: theta = (f_cc, dM, H0, Om, w0); late wCDM; DES-Dovekie SN (Cholesky) + CC."""
+    bounds = np.array([(0.2, 3), (-0.5, 0.5), (50, 85), (0.05, 0.6), (-1, -1 / 3)], dtype=np.float64)  # :53-62
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_WCDM, col_H0=2, col_Om=3, col_w0=4, z_grid=_grid(sn[0]),
+                        bounds=bounds)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 1, None)
+    return _cc_block(sp, cc, 0)
+
+
+def ohd_cc_union3(sn, cc, z_turn=0.2):
+    """ohd/cc_union3.py: theta = (f_cc, dM, H0, Om, v); v in km/s (no factor 100, :46); the grid ends at max(z_cmb) (:19)."""
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=2, col_Om=3,
+                        z_grid=np.linspace(0, np.max(sn[0]), num=4000), vel_scale=1.0)
+    _sn_block(sp, sn, S.SN_INVCOV, z_turn, 1, 4)
+    return _cc_block(sp, cc, 0)
+
+
 def ohd_cc(cc):
     """ohd/cc.py: theta = (H0, Om, f); chi2 = f^2 d^T C^-1 d; log L adds N ln 2pi + logdet - 2N ln f."""
     z, H, cov = cc

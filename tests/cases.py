@@ -54,6 +54,10 @@ SPECS = {
     "sn_pantheon_and_sh0es": lambda: fits.sn_pantheon_and_sh0es(pantheon_shoes()),
     "bao_desi_cmb_pantheon_H0trgb": lambda: fits.bao_desi_cmb_pantheon_H0trgb(pantheon(), desi()),
     "bao_desi_cmb": lambda: fits.bao_desi_cmb(desi()),
+    "sn_pantheon_dipole": lambda: fits.sn_pantheon_dipole(pantheon(), *pantheon_pos()),
+    "ohd_cc_des5y": lambda: fits.ohd_cc_des5y(des(), cc()),
+    "ohd_cc_union3": lambda: fits.ohd_cc_union3(union3(), cc()),
+    "bao_desi_omh2": lambda: fits.bao_desi_omh2(desi()),
     "bao_desi_union3_obh2_theta_star": lambda: fits.bao_desi_union3_obh2_theta_star(union3(), desi()),
 }
 
@@ -61,7 +65,8 @@ SPECS = {
 CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cmb_union3",
               "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y",
               "ohd_cc", "bao_desi_bbn", "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz",
-              "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb", "bao_desi_cmb", "bao_desi_union3_obh2_theta_star"]
+              "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb", "bao_desi_cmb", "bao_desi_union3_obh2_theta_star",
+              "sn_pantheon_dipole", "ohd_cc_des5y", "ohd_cc_union3", "bao_desi_omh2"]
 
 
 def spec(name):

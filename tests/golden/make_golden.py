@@ -442,6 +442,48 @@ def case_bao_desi_union3_obh2_theta_star():
     return dict(theta=theta, chi2=chi2, chi2_cmb=c_cmb, bounds=bounds, z_grid=ref.z_grid)
 
 
+def _generic(module, bounds, extra=lambda ref, theta: {}, n=24, loglike=False):
+    import importlib
+    ref = importlib.import_module(module)
+    bounds = np.asarray(bounds, dtype=np.float64)
+    theta = uniform_theta(bounds, n)
+    out = dict(theta=theta, chi2=np.array([ref.chi_squared(t) for t in theta]), bounds=bounds)
+    if loglike:
+        out["loglike"] = np.array([ref.log_likelihood(t) for t in theta])
+    for name in ("z_grid", "grid"):
+        if hasattr(ref, name):
+            out["z_grid"] = getattr(ref, name)
+    out.update(extra(ref, theta))
+    return out
+
+
+def case_sn_pantheon_dipole():
+    """sn/pantheon_dipole.py: one velocity template cos(angle) * tanh attenuation * survey mask (not +-1)."""
+    _stub_pantheon()
+    _enter_reference()
+    att = lambda ref, th: dict(weights=ref.cos_angle * 0.5 * (1.0 - np.tanh((ref.z_cmb - 0.10) / 0.02)) * ref.survey_mask)
+    return _generic("sn.pantheon_dipole", [(-20, -19), (62, 78), (0.1, 0.7), (-0.5, 4.5)], att)
+
+
+def case_ohd_cc_des5y():
+    """ohd/cc_des5y.py: theta = (f_cc, dM, H0, Om, w0); late wCDM; DES SN + CC."""
+    _stub_des()
+    _enter_reference()
+    return _generic("ohd.cc_des5y", [(0.2, 3), (-0.5, 0.5), (50, 85), (0.05, 0.6), (-1, -1 / 3)], loglike=True)
+
+
+def case_ohd_cc_union3():
+    """ohd/cc_union3.py: theta = (f_cc, dM, H0, Om, v[km/s]); grid ends at max(z_cmb) (no +0.1)."""
+    _enter_reference()
+    return _generic("ohd.cc_union3", [(0.05, 3.35), (-1.0, 1.0), (40.0, 95.0), (0.1, 0.7), (-900, 900)], loglike=True)
+
+
+def case_bao_desi_omh2():
+    """bao/desi_omh2.py: theta = (r_d, H0, omega_m, w0); Om = omega_m / h^2; thawing."""
+    _enter_reference()
+    return _generic("bao.desi_omh2", [(120, 160), (50.0, 85.0), (0.138, 0.148), (-1.0, -1 / 3)])
+
+
 def case_interpolator():
     """interpolator.py known answers on non-uniform and monotone/non-monotone data (pchip + hermite)."""
     _enter_reference()
