@@ -18,6 +18,7 @@
 
 #include "../../include/cosmolike.h"
 #include "chi2_gemm.cuh"
+#include "chi2_ozaki.cuh"
 #include "devspec.h"
 #include "friedmann.cuh"
 
@@ -53,6 +54,16 @@ struct cl_ctx {
   int64_t launches = 0;
   int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0;
   int* d_counter = nullptr;
+  // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
+  int opt_engine = CL_CHI2_ENGINE_DMMA, opt_slices = 6, opt_diag_trim = 1;
+  int oz_slices_built = 0;           // S the W planes were built for (0 = none)
+  int oz_T = 0;                      // column tiles of the sliced kernel
+  int64_t oz_ld = 0;                 // bytes per row of a digit plane
+  int8_t *d_Ws = nullptr, *d_Rs = nullptr;
+  double *d_wscale = nullptr, *d_rscale = nullptr;
+  int64_t oz_cap_rows = 0;
+  CUtensorMap tmWs{};
+  cudaEvent_t ev_slice = nullptr;
   std::string err, desc;
   std::mutex mu;
 };
@@ -99,6 +110,20 @@ static int make_tmap(cl_ctx* c, CUtensorMap* tm, const double* ptr, int64_t rows
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(c, CL_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return CL_OK;
+}
+
+// 3-D int8 tensor [slices][rows][ld bytes] with k extent `cols`, box = {64 B of k, box_rows, slices}, 64-byte swizzle
+static int make_tmap_planes(cl_ctx* c, CUtensorMap* tm, const int8_t* ptr, int64_t cols, int64_t rows, int slices, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(c, CL_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slices};
+  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)kOzKB, (cuuint32_t)box_rows, (cuuint32_t)slices};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CL_E_CUDA, "cuTensorMapEncodeTiled (digit planes) failed with CUresult %d", (int)r);
   return CL_OK;
 }
 
@@ -273,6 +298,8 @@ extern "C" int cl_destroy(cl_ctx* c) {
   for (void* p : c->dev_allocs) cudaFree(p);
   for (double* p : {c->d_theta, c->d_out, c->d_R, c->d_aux, c->d_part, c->d_part_u, c->d_scratch, c->d_W, c->d_u}) if (p) cudaFree(p);
   if (c->d_counter) cudaFree(c->d_counter);
+  for (void* p : {(void*)c->d_Ws, (void*)c->d_Rs, (void*)c->d_wscale, (void*)c->d_rscale}) if (p) cudaFree(p);
+  if (c->ev_slice) cudaEventDestroy(c->ev_slice);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   for (auto& r : c->evring) for (auto& e : r) if (e) cudaEventDestroy(e);
@@ -306,6 +333,7 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
   CTRY(cudaSetDevice(device));
   CTRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& r : c->evring) for (auto& e : r) CTRY(cudaEventCreate(&e));
+  CTRY(cudaEventCreate(&c->ev_slice));
 
   DevSpec& d = c->ds;
   const cl_spec& s = *spec;
@@ -470,6 +498,9 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
   CTRY(cudaFuncSetAttribute(k12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
   CTRY(cudaFuncSetAttribute(k_chi2_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CTRY(cudaFuncSetAttribute(k_chi2_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  CTRY(cudaFuncSetAttribute(k_chi2_ozaki<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<5>::SMEM));
+  CTRY(cudaFuncSetAttribute(k_chi2_ozaki<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<6>::SMEM));
+  CTRY(cudaFuncSetAttribute(k_chi2_ozaki<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<7>::SMEM));
 
   char buf[256];
   snprintf(buf, sizeof buf, "cosmolike_b200 abi %u, sm_100a, %s (%d SMs), n_sn=%d n_bao=%d cmb=%d n_cc=%d grid=%d%s", CL_ABI_VERSION, prop.name,
@@ -490,7 +521,15 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "dbg") { c->opt_dbg = (int)value; return CL_OK; }
   if (n == "gemm_dynamic") { c->opt_gemm_dynamic = value ? 1 : 0; return CL_OK; }
   if (n == "gemm_group_rb") { c->opt_group_rb = (int)value; return CL_OK; }
-  if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }
+  if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; c->opt_diag_trim = value ? 1 : 0; return CL_OK; }
+  if (n == "chi2_engine") {
+    if (value != CL_CHI2_ENGINE_DMMA && value != CL_CHI2_ENGINE_TCGEN05) return fail(c, CL_E_INVALID, "chi2_engine must be 0 (FP64 DMMA) or 1 (tcgen05 int8 digit planes)");
+    c->opt_engine = (int)value; return CL_OK;
+  }
+  if (n == "chi2_slices") {
+    if (value < 5 || value > 7) return fail(c, CL_E_INVALID, "chi2_slices must be 5, 6 or 7");
+    c->opt_slices = (int)value; return CL_OK;
+  }
   return fail(c, CL_E_INVALID, "unknown option %s", name);
 }
 
@@ -506,7 +545,8 @@ static int ensure_rows(cl_ctx* c, int64_t rows) {
   CUDA_TRY(c, cudaMalloc(&c->d_aux, cap * AUX_COUNT * sizeof(double)));
   if (c->d_W) {
     CUDA_TRY(c, cudaMalloc(&c->d_R, cap * c->ldR * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc(&c->d_part, cap * c->T * sizeof(double)));
+    const int64_t t_max = std::max<int64_t>(c->T, (c->ds.n_sn + OzCfg<7>::NT - 1) / OzCfg<7>::NT);  // either engine
+    CUDA_TRY(c, cudaMalloc(&c->d_part, cap * t_max * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_part_u, cap * c->T * sizeof(double)));
   }
   c->cap_rows = cap;
@@ -551,6 +591,82 @@ static int launch_s12(cl_ctx* c, const Stage12Args& a, cudaStream_t st) {
   return CL_OK;
 }
 
+// digit planes for the tcgen05 engine: W planes once per slice count, residual planes sized like the workspace
+template <int S>
+static int oz_slice_launch(cl_ctx* c, const double* src, int64_t ld_src, int64_t rows, int n, int8_t* dst, double* scale, cudaStream_t st) {
+  k_oz_slice_rows<S><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  return CL_OK;
+}
+static int oz_slice(cl_ctx* c, int S, const double* src, int64_t ld_src, int64_t rows, int n, int8_t* dst, double* scale, cudaStream_t st) {
+  return S == 5 ? oz_slice_launch<5>(c, src, ld_src, rows, n, dst, scale, st)
+       : S == 6 ? oz_slice_launch<6>(c, src, ld_src, rows, n, dst, scale, st)
+                : oz_slice_launch<7>(c, src, ld_src, rows, n, dst, scale, st);
+}
+static int oz_tile_cols(int S) { return S == 5 ? OzCfg<5>::NT : S == 6 ? OzCfg<6>::NT : OzCfg<7>::NT; }
+
+static int ensure_planes(cl_ctx* c, int64_t rows, cudaStream_t st) {
+  const int S = c->opt_slices, n = c->ds.n_sn;
+  if (c->oz_slices_built != S) {
+    CUDA_TRY(c, cudaDeviceSynchronize());
+    for (void** p : {(void**)&c->d_Ws, (void**)&c->d_Rs, (void**)&c->d_wscale, (void**)&c->d_rscale}) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->oz_cap_rows = 0;
+    c->oz_ld = ((int64_t)n + 127) & ~127LL;
+    c->oz_T = (n + oz_tile_cols(S) - 1) / oz_tile_cols(S);
+    CUDA_TRY(c, cudaMalloc(&c->d_Ws, (size_t)S * n * c->oz_ld));
+    CUDA_TRY(c, cudaMalloc(&c->d_wscale, n * sizeof(double)));
+    int rc = oz_slice(c, S, c->d_W, c->ldW, n, n, c->d_Ws, c->d_wscale, st);
+    if (rc != CL_OK) return rc;
+    rc = make_tmap_planes(c, &c->tmWs, c->d_Ws, n, n, S, c->oz_ld, oz_tile_cols(S));
+    if (rc != CL_OK) return rc;
+    c->oz_slices_built = S;
+  }
+  if (rows > c->oz_cap_rows) {
+    CUDA_TRY(c, cudaDeviceSynchronize());
+    for (void** p : {(void**)&c->d_Rs, (void**)&c->d_rscale}) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->oz_cap_rows = 0;
+    const int64_t cap = std::max(rows, c->cap_rows);
+    CUDA_TRY(c, cudaMalloc(&c->d_Rs, (size_t)S * cap * c->oz_ld));
+    CUDA_TRY(c, cudaMalloc(&c->d_rscale, cap * sizeof(double)));
+    c->oz_cap_rows = cap;
+  }
+  return CL_OK;
+}
+
+template <int S>
+static void oz_launch(int grid, cudaStream_t st, const CUtensorMap& tmR, const CUtensorMap& tmW, const OzArgs& g) {
+  k_chi2_ozaki<S><<<grid, kOzThreads, OzCfg<S>::SMEM, st>>>(tmR, tmW, g);
+}
+
+// stage 3 with the tcgen05 engine: slice the residual rows, then the int8 contraction
+static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool record) {
+  int rc = ensure_planes(c, rows, st);
+  if (rc != CL_OK) return rc;
+  const int S = c->opt_slices, n = c->ds.n_sn;
+  rc = oz_slice(c, S, c->d_R, c->ldR, rows, n, c->d_Rs, c->d_rscale, st);
+  if (rc != CL_OK) return rc;
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev_slice, st));
+  CUtensorMap tmRs;
+  rc = make_tmap_planes(c, &tmRs, c->d_Rs, n, rows, S, c->oz_ld, kOzM);
+  if (rc != CL_OK) return rc;
+  OzArgs g{};
+  g.B = rows; g.N = n; g.T = c->oz_T; g.n_rb = (int)((rows + kOzM - 1) / kOzM);
+  g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter; g.diag_trim = c->opt_diag_trim;
+  // row blocks per L2 group: the S digit planes of a group's rows (+ the W planes) stay L2-resident across its column tiles
+  int grp = c->opt_group_rb > 0 ? c->opt_group_rb : (int)std::max<int64_t>(8, ((64LL << 20) / ((int64_t)kOzM * c->oz_ld * S)) & ~7LL);
+  g.group_rb = std::min(grp, g.n_rb);
+  CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+  const int64_t items = (int64_t)g.n_rb * g.T;
+  const int grid = (int)std::min<int64_t>(items, c->opt_gemm_ctas > 0 ? c->opt_gemm_ctas : c->sm_count);
+  if (S == 5) oz_launch<5>(grid, st, tmRs, c->tmWs, g);
+  else if (S == 6) oz_launch<6>(grid, st, tmRs, c->tmWs, g);
+  else oz_launch<7>(grid, st, tmRs, c->tmWs, g);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  return CL_OK;
+}
+
 // one pass over `rows` device-resident parameter vectors: stage 1+2 -> stage 3 -> finalize
 static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, int what, double* d_out, double* d_comps,
                     bool moments, cudaStream_t st, bool record) {
@@ -564,7 +680,12 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   rc = launch_s12(c, a, st);
   if (rc != CL_OK) return rc;
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
-  if (large) {
+  const bool planes = large && !moments && c->opt_engine == CL_CHI2_ENGINE_TCGEN05;
+  if (planes) {
+    rc = run_stage3_planes(c, rows, st, record);
+    if (rc != CL_OK) return rc;
+  } else if (large) {
+    if (record) CUDA_TRY(c, cudaEventRecord(c->ev_slice, st));
     CUtensorMap tmR;
     rc = make_tmap(c, &tmR, c->d_R, rows, c->ds.n_sn, c->ldR);
     if (rc != CL_OK) return rc;
@@ -591,7 +712,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   }
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
   FinalizeArgs f{};
-  f.B = rows; f.what = what; f.n_part = c->T; f.sn_large = large ? 1 : 0;
+  f.B = rows; f.what = what; f.n_part = planes ? c->oz_T : c->T; f.sn_large = large ? 1 : 0;
   f.part = c->d_part; f.aux = c->d_aux; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value;
   k_finalize<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(f);
   c->launches++;
@@ -757,6 +878,18 @@ extern "C" int cl_last_timing(cl_ctx* c, double ms[4]) {
   if (c->n_timed == 0) return fail(c, CL_E_INVALID, "no evaluation has been timed yet");
   std::lock_guard<std::mutex> lk(c->mu);
   return timing_of(c, c->n_timed - 1, ms);
+}
+
+extern "C" int cl_stage3_split(cl_ctx* c, double ms[2]) {
+  if (!c || !ms) return CL_E_INVALID;
+  if (c->n_timed == 0 || !c->d_W) return fail(c, CL_E_INVALID, "no large-SN evaluation has been timed yet");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaEvent_t* ev = c->evring[(c->n_timed - 1) % cl_ctx::kRing];
+  CUDA_TRY(c, cudaEventSynchronize(ev[5]));
+  float t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, ev[2], c->ev_slice)); ms[0] = t;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev_slice, ev[3])); ms[1] = t;
+  return CL_OK;
 }
 
 extern "C" int cl_timing_history(cl_ctx* c, int n, double* ms) {

@@ -25,8 +25,11 @@ _LIB_NAME = "libcosmolike_b200.so"
 ABI_SYMBOLS = (
     "cl_create", "cl_destroy", "cl_last_error", "cl_eval", "cl_eval_device", "cl_eval_components",
     "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
-    "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe",
+    "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split",
 )
+
+#: chi-squared engines for large SN blocks (include/cosmolike.h CL_CHI2_ENGINE_*)
+CHI2_ENGINE_DMMA, CHI2_ENGINE_TCGEN05 = 0, 1
 
 
 class EngineError(RuntimeError):
@@ -67,6 +70,7 @@ def load_library():
     lib.cl_sn_residuals.argtypes = [ctxp, _dp, i64, i64, _dp]
     lib.cl_last_timing.argtypes = [ctxp, C.c_double * 4]
     lib.cl_timing_history.argtypes = [ctxp, C.c_int, _dp]
+    lib.cl_stage3_split.argtypes = [ctxp, C.c_double * 2]
     lib.cl_launch_count.argtypes = [ctxp]
     lib.cl_launch_count.restype = i64
     lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
@@ -223,6 +227,12 @@ class Engine:
         ms = (C.c_double * 4)()
         self._check(self.lib.cl_last_timing(self._ctx, ms))
         return {"stage12_ms": ms[0], "stage3_ms": ms[1], "finalize_ms": ms[2], "total_ms": ms[3]}
+
+    def stage3_split(self):
+        """(ms forming the int8 digit planes of the residual rows, ms in the contraction kernel) of the last evaluation."""
+        ms = (C.c_double * 2)()
+        self._check(self.lib.cl_stage3_split(self._ctx, ms))
+        return ms[0], ms[1]
 
     def timing_history(self, n):
         """[k, 4] array (stage12, stage3, finalize, total ms) of the last k <= n evaluations, oldest first."""

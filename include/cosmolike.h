@@ -28,6 +28,13 @@ extern "C" {
 #define CL_MAX_CC 64       /* max cosmic-chronometer points */
 #define CL_SN_SMALL_MAX 64 /* SN blocks up to this size use the in-kernel quadratic form (no GEMM) */
 
+/* chi-squared engines for large SN blocks (option "chi2_engine"):
+ *   DMMA    — FP64 tensor pipe (mma.sync f64), bit-stable FP64 contraction;
+ *   TCGEN05 — 5th-generation tensor cores: the residual rows and W = L^-1 are split into "chi2_slices" (5..7, default 6)
+ *             int8 digit planes, multiplied exactly with tcgen05.mma kind::i8 (int32 accumulators in TMEM) and recombined in
+ *             FP64; 6 planes carry 46 bits per row: |d chi2| / chi2 ~ 3e-13. */
+enum { CL_CHI2_ENGINE_DMMA = 0, CL_CHI2_ENGINE_TCGEN05 = 1 };
+
 /* error codes */
 enum {
   CL_OK = 0,
@@ -240,13 +247,17 @@ int cl_sn_residuals(cl_ctx* ctx, const double* theta, int64_t B, int64_t ld, dou
  * ms[0] stage 1+2 (Friedmann distances + residuals), ms[1] stage 3 (chi-squared GEMM), ms[2] finalize,
  * ms[3] total device time incl. copies for cl_eval.  Blocks until the events have completed. */
 int cl_last_timing(cl_ctx* ctx, double ms[4]);
+/* Split of ms[1] for the most recent evaluation: ms[0] = forming the int8 digit planes of the residual rows (0 with the
+ * DMMA engine), ms[1] = the contraction kernel itself. */
+int cl_stage3_split(cl_ctx* ctx, double ms[2]);
 /* Same for the most recent n evaluations (the library keeps the last 64), oldest first: ms[i][4].
  * Returns the number of entries written (<= n) or a negative error. */
 int cl_timing_history(cl_ctx* ctx, int n, double* ms);
 /* Number of kernels this library launched on the context since creation. */
 int64_t cl_launch_count(const cl_ctx* ctx);
 
-/* Tuning knobs (integers): "gemm_variant", "rows_per_block", ...; returns CL_E_INVALID for unknown names. */
+/* Options (integers): "chi2_engine" (CL_CHI2_ENGINE_*), "chi2_slices" (5..7), "max_rows_per_pass", "gemm_ctas",
+ * "stage12_ctas", "gemm_dynamic", "gemm_group_rb", "gemm_diag_skip"; returns CL_E_INVALID for unknown names. */
 int cl_set_option(cl_ctx* ctx, const char* name, int64_t value);
 
 /* Library / device description string, e.g. "cosmolike_b200 abi 3, sm_100a, NVIDIA B200 (148 SMs)". */

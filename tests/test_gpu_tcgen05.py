@@ -1,0 +1,134 @@
+"""GPU parity tests of the tcgen05 chi-squared engine (csrc/chi2_ozaki.cuh): the SN contraction |L^-1 delta|^2 of
+solve_triangular.py:5-14 evaluated with int8 digit planes on the 5th-generation tensor cores, against the golden
+vectors of the unmodified reference, the CPU oracle and the FP64 DMMA engine.
+
+Tolerances: 7 digit planes carry every bit of an FP64 row, so they must meet the same bar as the FP64 engine
+(|d chi2| < 1e-6 absolute, relaxed to 1e-12 relative where chi2 itself exceeds 1e6).  6 planes carry 46 bits per
+row: the bar is 1e-6 absolute below chi2 = 1e5 and 1e-11 relative above."""
+import numpy as np
+import pytest
+
+from cases import golden, spec
+
+pytestmark = pytest.mark.gpu
+
+#: golden cases with a large SN block (stage 3 runs); the others never reach the contraction
+LARGE_SN_CASES = ["sn_pantheon", "sn_des5y", "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y",
+                  "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz", "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb",
+                  "sn_pantheon_dipole", "ohd_cc_des5y"]
+
+
+def close(got, want, slices):
+    got, want = np.asarray(got), np.asarray(want)
+    tol = np.maximum(1e-6, (1e-12 if slices >= 7 else 1e-11) * np.abs(want))
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), (got[bad][:5], want[bad][:5], np.abs(got - want)[bad][:5])
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.engine import CHI2_ENGINE_TCGEN05
+    cache = {}
+
+    def get(name, slices):
+        key = (name, slices)
+        if key not in cache:
+            e = Engine(spec(name))
+            if slices:
+                e.set_option("chi2_engine", CHI2_ENGINE_TCGEN05)
+                e.set_option("chi2_slices", slices)
+            else:
+                e.set_option("chi2_engine", 0)
+            cache[key] = e
+        return cache[key]
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+@pytest.mark.parametrize("slices", [6, 7])
+@pytest.mark.parametrize("name", LARGE_SN_CASES)
+def test_chi2_vs_reference_golden(engines, name, slices):
+    g = golden(name)
+    close(engines(name, slices).chi_squared(g["theta"]), g["chi2"], slices)
+
+
+@pytest.mark.parametrize("slices", [6, 7])
+@pytest.mark.parametrize("name", ["sn_pantheon", "sn_des5y", "bao_desi_cmb_pantheon"])
+def test_chi2_vs_oracle_random_batch(engines, name, slices):
+    import oracle.oracle as O
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    theta = uniform_theta(golden(name)["bounds"], 300, seed=7)
+    close(engines(name, slices).chi_squared(theta), O.Oracle(spec(name)).chi_squared(theta, nthreads=0), slices)
+
+
+def test_five_planes_documented_accuracy(engines):
+    """38 bits per row: 1e-9 relative (not a parity mode; kept for coarse grid scans)."""
+    g = golden("sn_pantheon")
+    got = engines("sn_pantheon", 5).chi_squared(g["theta"])
+    assert np.max(np.abs(got - g["chi2"]) / np.abs(g["chi2"])) < 5e-9
+
+
+@pytest.mark.parametrize("slices", [6, 7])
+def test_rows_are_independent_of_the_batch(engines, slices):
+    """One exponent per residual row and exact integer accumulation: a row's value does not depend on the batch
+    size, the row-block edges of the 128-row tile, the order of the rows or the number of passes."""
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    e = engines("sn_pantheon", slices)
+    theta = uniform_theta(golden("sn_pantheon")["bounds"], 1000, seed=3)
+    full = e.chi_squared(theta)
+    for b in (1, 127, 128, 129):
+        assert np.array_equal(e.chi_squared(theta[:b]), full[:b])
+    perm = np.random.default_rng(0).permutation(1000)
+    assert np.array_equal(e.chi_squared(theta[perm]), full[perm])
+    with Engine(spec("sn_pantheon")) as e2:
+        e2.set_option("chi2_engine", 1)
+        e2.set_option("chi2_slices", slices)
+        e2.set_option("max_rows_per_pass", 256)
+        assert np.array_equal(e2.chi_squared(theta), full)
+        e2.set_option("gemm_diag_skip", 0)      # full-width MMAs inside the diagonal block: same integers
+        assert np.array_equal(e2.chi_squared(theta), full)
+        e2.set_option("gemm_ctas", 3)           # three persistent CTAs walk all items
+        assert np.array_equal(e2.chi_squared(theta), full)
+
+
+def test_prior_and_guard_rows(engines):
+    """-inf rows (outside the prior box) are never evaluated: their stale residual rows still go through the slicing
+    kernel and must not disturb anything (sn/pantheon.py:80-97)."""
+    g = golden("sn_pantheon")
+    lp = engines("sn_pantheon", 6).log_probability(g["theta_logp"])
+    want = g["logp"]
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(lp), np.isneginf(want)) and not np.isnan(lp).any()
+    close(-2 * lp[fin], -2 * want[fin], 6)
+
+
+@pytest.mark.parametrize("slices", [6, 7])
+def test_full_size_batch_against_fp64_engine(engines, slices):
+    """BASELINE.json's batch (65536 rows, Pantheon+ N = 1590 as fitted): every row against the FP64 DMMA engine,
+    plus the size-independent property that chi2 is exactly quadratic in the magnitude offset."""
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    B = 65536
+    theta = uniform_theta(golden("sn_pantheon")["bounds"], B, seed=42)
+    ref = engines("sn_pantheon", 0).chi_squared(theta)
+    e = engines("sn_pantheon", slices)
+    c0 = e.chi_squared(theta)
+    close(c0, ref, slices)
+    d = 0.01
+    tp, tm = theta.copy(), theta.copy()
+    tp[:, 0] += d; tm[:, 0] -= d
+    second = (e.chi_squared(tp) - 2 * c0 + e.chi_squared(tm)) / d**2
+    uu = e.sn_moments(theta[:1])[0, 2]
+    assert np.max(np.abs(second - 2 * uu) / (2 * uu)) < 1e-6
+
+
+def test_components_and_moments_with_the_tcgen05_engine(engines):
+    """components() goes through the sliced contraction, sn_moments() (y.y, y.u, u.u) stays on the FP64 engine."""
+    g = golden("bao_desi_cmb_pantheon")
+    e, ref = engines("bao_desi_cmb_pantheon", 7), engines("bao_desi_cmb_pantheon", 0)
+    a, b = e.components(g["theta"]), ref.components(g["theta"])
+    assert np.max(np.abs(a - b)) < 1e-6
+    m = engines("sn_pantheon", 7).sn_moments(golden("sn_pantheon")["theta"])
+    assert np.array_equal(m, engines("sn_pantheon", 0).sn_moments(golden("sn_pantheon")["theta"]))
