@@ -25,17 +25,24 @@ namespace cosmolike {
 
 constexpr int kOzM = 128;      // theta rows per tile (TMEM lanes)
 constexpr int kOzKB = 64;      // bytes of k per pipeline block (= TMA inner box = swizzle span), two K=32 MMAs
-constexpr int kOzThreads = 192;
+constexpr int kOzThreads = 320;   // producer warp, MMA warp, 8 epilogue warps
 constexpr int kOzQueue = 4;
-constexpr int kOzAStages = 3, kOzBStages = 2;
+constexpr int kOzBStages = 2;
 
 template <int S> struct OzCfg {
   static constexpr int NT = S <= 5 ? 96 : S == 6 ? 80 : 64;  // S levels x NT columns <= 512 TMEM columns
-  static constexpr int A_BYTES = S * kOzM * kOzKB;
+  // R planes per TMA box / ring unit.  SLO = S: one box per k block.  (SLO = (S + 1) / 2 lets the first half of the planes
+  // go back to the producer half way through the block, but two 24 KB boxes move measurably slower than one 48 KB box:
+  // 2.84 M cycles per CTA instead of 2.61 M at N = 1701, so the split is off.)
+  static constexpr int SLO = S;
+  static constexpr int PLANE_BYTES = kOzM * kOzKB;
+  static constexpr int A_UNIT_BYTES = SLO * PLANE_BYTES;
   static constexpr int B_BYTES = S * NT * kOzKB;
-  static constexpr int A_STAGES = (kOzAStages * A_BYTES + kOzBStages * B_BYTES <= 216 * 1024) ? kOzAStages : 2;
-  static constexpr int SMEM = 1024 + A_STAGES * A_BYTES + kOzBStages * B_BYTES + NT * 8 + 256;
+  static constexpr int A_UNITS = (3 * A_UNIT_BYTES + kOzBStages * B_BYTES <= 222 * 1024) ? 3 : 2;
+  static constexpr int A_RING = A_UNITS * A_UNIT_BYTES, B_RING = kOzBStages * B_BYTES;
+  static constexpr int SMEM = 1024 + A_RING + B_RING + NT * 8 + 384;
   static constexpr int FRAC_BITS = 6 + 8 * (S - 1);
+  static constexpr int MAX_STACK = 256 / NT;   // digit planes of W one MMA may cover (N <= 256)
 };
 
 struct OzArgs {
@@ -43,12 +50,13 @@ struct OzArgs {
   int N;                   // SN count
   int T;                   // column tiles = ceil(N / NT)
   int n_rb;                // row blocks = ceil(B / 128)
-  double* part;            // [T][B] partial sums of squares
+  double* part;            // [2 T][B] partial sums of squares (one plane per half column tile)
   const double* rowscale;  // [B] 2^eR_b
   const double* colscale;  // [N] 2^eW_n
   int* counter;            // dynamic scheduling counter (zeroed before the launch)
   int group_rb;            // row blocks per L2 group
   int diag_trim;           // 1: shrink the MMA N extent inside the diagonal block
+  long long* prof;         // nullable [grid][8]: cycle counters of the MMA issuer and of one epilogue warp
 };
 
 __device__ __forceinline__ void oz_decode_item(const OzArgs& g, int64_t item, int& jt, int& rb) {
@@ -81,13 +89,25 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// load + wait in ONE asm statement: the registers are not valid before tcgen05.wait::ld and nothing else orders
-// plain arithmetic on them after a separate wait statement
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-               "tcgen05.wait::ld.sync.aligned;"
+// asynchronous TMEM load: the registers are valid only after tmem_ld_wait() AND tmem_ld_fence() on them
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_fence8(int32_t* v) {
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// empty volatile asm that "modifies" 16 loaded registers: pins every use of them after the wait above (volatile asm
+// statements keep their order; plain arithmetic on the registers would otherwise be free to move above the wait)
+__device__ __forceinline__ void tmem_ld_fence(int32_t* v) {
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                    "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
 }
 // bounded spin: a wrong descriptor or a lost arrival traps (the context dies with an error) instead of hanging the GPU
 __device__ __forceinline__ void oz_wait(uint32_t bar, uint32_t parity) {
@@ -143,6 +163,65 @@ __global__ void __launch_bounds__(256) k_oz_slice_rows(const double* __restrict_
   }
 }
 
+// Same, one pass: the whole row lives in registers (TRIPS x 4 doubles per lane, row length <= 128 TRIPS), so the fp64
+// residuals are read from HBM once (streaming loads: they are not needed again).
+template <int S, int TRIPS>
+__global__ void __launch_bounds__(256) k_oz_slice_rows_reg(const double* __restrict__ src, int64_t ld_src, int64_t rows, int n, int8_t* __restrict__ dst,
+                                                           int64_t ld_dst, double* __restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const double* x = src + row * ld_src;
+  double2 xa[TRIPS], xb[TRIPS];
+  double mx = 0.0;
+#pragma unroll
+  for (int t = 0; t < TRIPS; t++) {
+    const int k0 = 4 * lane + 128 * t;
+    xa[t] = make_double2(0.0, 0.0); xb[t] = make_double2(0.0, 0.0);
+    if (k0 + 3 < n) {   // ld_src >= n rounded up to 2 and 32-byte aligned groups: both halves are in bounds
+      xa[t] = __ldcs(reinterpret_cast<const double2*>(x + k0));
+      xb[t] = __ldcs(reinterpret_cast<const double2*>(x + k0 + 2));
+    } else {
+      if (k0 < n) xa[t].x = x[k0];
+      if (k0 + 1 < n) xa[t].y = x[k0 + 1];
+      if (k0 + 2 < n) xb[t].x = x[k0 + 2];
+    }
+    mx = fmax(fmax(mx, fmax(fabs(xa[t].x), fabs(xa[t].y))), fmax(fabs(xb[t].x), fabs(xb[t].y)));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int e = 0;
+  if (mx > 0.0 && mx < 1.7e308) e = ilogb(mx) + 1;
+  e = max(e, -900);
+  const double up = __longlong_as_double((long long)(1023 + OzCfg<S>::FRAC_BITS - e) << 52);
+  if (lane == 0) scale[row] = __longlong_as_double((long long)(1023 + e) << 52);
+  constexpr double kLim = 1.01 * (double)(1ULL << OzCfg<S>::FRAC_BITS);
+  const int64_t plane = rows * ld_dst;
+  int8_t* d0 = dst + row * ld_dst;
+#pragma unroll
+  for (int t = 0; t < TRIPS; t++) {
+    const int k0 = 4 * lane + 128 * t;
+    if (k0 >= ld_dst) break;
+    const double xs[4] = {xa[t].x, xa[t].y, xb[t].x, xb[t].y};
+    uint32_t w[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) w[s] = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      long long v = __double2ll_rn(fmin(fmax(xs[q] * up, -kLim), kLim));
+#pragma unroll
+      for (int s = S - 1; s >= 1; s--) {
+        const long long d = (long long)(int8_t)(v & 0xff);
+        w[s] |= (uint32_t)(uint8_t)d << (8 * q);
+        v = (v - d) >> 8;
+      }
+      w[0] |= (uint32_t)(uint8_t)(int8_t)v << (8 * q);
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) *reinterpret_cast<uint32_t*>(d0 + s * plane + k0) = w[s];
+  }
+}
+
 // ---- the contraction -----------------------------------------------------------------------------------------------------
 template <int S>
 __global__ void __launch_bounds__(kOzThreads, 1)
@@ -152,26 +231,27 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   extern __shared__ unsigned char osm_raw[];
   const uint32_t base = (smem_u32(osm_raw) + 1023u) & ~1023u;
   unsigned char* base_ptr = osm_raw + (base - smem_u32(osm_raw));
-  const uint32_t sA = base;                                    // [A_STAGES][S][128 rows][64 B]
-  const uint32_t sB = base + C::A_STAGES * C::A_BYTES;         // [kOzBStages][S][NT rows][64 B]
-  double* s_cs = reinterpret_cast<double*>(base_ptr + C::A_STAGES * C::A_BYTES + kOzBStages * C::B_BYTES);  // [NT] column scales of the tile
-  const uint32_t bars = base + C::A_STAGES * C::A_BYTES + kOzBStages * C::B_BYTES + NT * 8;
+  const uint32_t sA = base;                       // [A_UNITS][SLO planes][128 rows][64 B]
+  const uint32_t sB = base + C::A_RING;           // [kOzBStages][S planes][NT rows][64 B]
+  double* s_cs = reinterpret_cast<double*>(base_ptr + C::A_RING + C::B_RING);  // [NT] column scales of the tile
+  const uint32_t bars = base + C::A_RING + C::B_RING + NT * 8;
   auto fullA = [&](int s) { return bars + 8u * s; };
-  auto emptyA = [&](int s) { return bars + 8u * (4 + s); };
-  auto fullB = [&](int s) { return bars + 8u * (8 + s); };
-  auto emptyB = [&](int s) { return bars + 8u * (10 + s); };
-  auto qfull = [&](int s) { return bars + 8u * (12 + s); };
-  auto qempty = [&](int s) { return bars + 8u * (16 + s); };
-  const uint32_t tmem_full = bars + 8u * 20, tmem_empty = bars + 8u * 21;
-  const uint32_t q_items = bars + 8u * 22;   // int[kOzQueue]
-  const uint32_t tslot = bars + 8u * 24;
+  auto emptyA = [&](int s) { return bars + 8u * (6 + s); };
+  auto fullB = [&](int s) { return bars + 8u * (12 + s); };
+  auto emptyB = [&](int s) { return bars + 8u * (14 + s); };
+  auto qfull = [&](int s) { return bars + 8u * (16 + s); };
+  auto qempty = [&](int s) { return bars + 8u * (20 + s); };
+  auto lvl_full = [&](int l) { return bars + 8u * (24 + l); };    // level l of the tile is complete (tcgen05.commit)
+  auto lvl_empty = [&](int l) { return bars + 8u * (31 + l); };   // level l has been read by the eight epilogue warps
+  const uint32_t q_items = bars + 8u * 38;   // int[kOzQueue]
+  const uint32_t tslot = bars + 8u * 40;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < C::A_STAGES; s++) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < C::A_UNITS; s++) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < kOzBStages; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int s = 0; s < kOzQueue; s++) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 5); }   // MMA thread + 4 epilogue warps
-    mbar_init(tmem_full, 1); mbar_init(tmem_empty, 4);
+    for (int s = 0; s < kOzQueue; s++) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 9); }   // MMA thread + 8 epilogue warps
+    for (int l = 0; l < S; l++) { mbar_init(lvl_full(l), 1); mbar_init(lvl_empty(l), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -210,13 +290,19 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;      // k runs to the end of the diagonal block
         for (int ks = 0; ks < nk; ks++) {
           oz_wait(emptyA(sa), pa ^ 1u);
-          mbar_arrive_expect_tx(fullA(sa), C::A_BYTES);
-          tma_load_3d(sA + sa * C::A_BYTES, &tmR, ks * kOzKB, rb * kOzM, 0, fullA(sa));
-          if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
+          mbar_arrive_expect_tx(fullA(sa), C::A_UNIT_BYTES);
+          tma_load_3d(sA + sa * C::A_UNIT_BYTES, &tmR, ks * kOzKB, rb * kOzM, 0, fullA(sa));
+          if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
           oz_wait(emptyB(sb), pb ^ 1u);
           mbar_arrive_expect_tx(fullB(sb), C::B_BYTES);
           tma_load_3d(sB + sb * C::B_BYTES, &tmW, ks * kOzKB, c0, 0, fullB(sb));
           if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
+          if constexpr (C::SLO < S) {
+            oz_wait(emptyA(sa), pa ^ 1u);
+            mbar_arrive_expect_tx(fullA(sa), C::A_UNIT_BYTES);   // planes past S are out of bounds: zero-filled, still counted
+            tma_load_3d(sA + sa * C::A_UNIT_BYTES, &tmR, ks * kOzKB, rb * kOzM, C::SLO, fullA(sa));
+            if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
+          }
         }
       }
     }
@@ -225,8 +311,12 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, pt = 0;
+      long long t_full = 0, t_lvl = 0, t_q = 0, n_blk = 0;
+      const long long t_begin = clock64();
       for (;;) {
+        long long tq0 = clock64();
         oz_wait(qfull(qslot), qphase);
+        t_q += clock64() - tq0;
         int item;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(q_items + 4u * qslot) : "memory");
         mbar_arrive(qempty(qslot));
@@ -236,43 +326,72 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         oz_decode_item(g, item, jt, rb);
         const int c0 = g.N - NT * (g.T - jt);
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;
-        oz_wait(tmem_empty, pt ^ 1u);   // the epilogue has drained the previous tile
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // One MMA covers SEVERAL slice products: the digit planes of W are stacked in shared memory ([slice][NT rows]) and the
+        // levels are stacked in TMEM ([level][NT columns]), so A_i x [B_j0 ; ... ; B_j1] with N = (j1 - j0 + 1) NT lands
+        // exactly on levels i + j0 .. i + j1.  S (S + 1) / 2 products per K = 32 step become ~S + 3 instructions that
+        // read the A plane from shared memory once each (shared-memory bandwidth, not the tensor pipe, bounds the narrow
+        // form).  Round i completes level i: in the last k block each level is committed on its own barrier as soon as
+        // its round has been issued, so the epilogue overlaps the rest of the block.
         for (int ks = 0; ks < nk; ks++) {
+          long long tf0 = clock64();
           oz_wait(fullA(sa), pa);
           oz_wait(fullB(sb), pb);
+          t_full += clock64() - tf0; n_blk++;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t aS = sA + sa * C::A_BYTES, bS = sB + sb * C::B_BYTES;
+          const int sa_lo = sa;
+          if constexpr (C::SLO < S) { if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; } }
+          const uint32_t aLo = sA + sa_lo * C::A_UNIT_BYTES, aHi = sA + sa * C::A_UNIT_BYTES, bS = sB + sb * C::B_BYTES;
+          const bool first_blk = ks == 0, last_blk = ks == nk - 1;
+          if (first_blk) {
+            long long tl0 = clock64();
 #pragma unroll
-          for (int kk = 0; kk < kOzKB; kk += 32) {
-            // W[n][k] = 0 for k > n: columns c0 + n < k0 are complete, shrink the N extent (multiples of 16 columns)
-            const int k0 = ks * kOzKB + kk;
-            int n0 = 0;
-            if (g.diag_trim && k0 > c0) n0 = min((k0 - c0) & ~15, NT - 16);
-            const uint32_t idesc = umma_idesc_i8(kOzM, NT - n0);
-            const uint32_t first = (ks == 0 && kk == 0) ? 0u : 1u;
+            for (int l = 0; l < S; l++) oz_wait(lvl_empty(l), pt ^ 1u);   // the epilogue has read the previous tile
+            t_lvl += clock64() - tl0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
 #pragma unroll
-            for (int i = 0; i < S; i++)
+          for (int i = 0; i < S; i++) {
+            if (C::SLO < S && i == C::SLO) {   // second unit of R planes; the first one goes back to the producer
+              umma_commit(emptyA(sa_lo));
+              long long tf1 = clock64();
+              oz_wait(fullA(sa), pa);
+              t_full += clock64() - tf1;
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t aP = i < C::SLO ? aLo + i * C::PLANE_BYTES : aHi + (i - C::SLO) * C::PLANE_BYTES;
 #pragma unroll
-              for (int j = 0; j + i < S; j++)
-                umma_i8(tmem + (uint32_t)((i + j) * NT + n0), umma_desc_sw64(aS + i * (kOzM * kOzKB) + kk),
-                        umma_desc_sw64(bS + j * (NT * kOzKB) + n0 * kOzKB + kk), idesc, i == 0 ? first : 1u);
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+              for (int j0 = 0; j0 < S - i; j0 += C::MAX_STACK) {
+                          const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
+                umma_i8(tmem + (uint32_t)((i + j0) * NT), umma_desc_sw64(aP + 32 * h),
+                        umma_desc_sw64(bS + j0 * (NT * kOzKB) + 32 * h), umma_idesc_i8(kOzM, cnt * NT), (first_blk && h == 0 && i == 0) ? 0u : 1u);
+              }
+            }
+            if (last_blk) umma_commit(lvl_full(i));
           }
           umma_commit(emptyA(sa));
           umma_commit(emptyB(sb));
-          if (++sa == C::A_STAGES) { sa = 0; pa ^= 1u; }
+          if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
           if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
         }
-        umma_commit(tmem_full);
         pt ^= 1u;
+      }
+      if (g.prof) {
+        long long* p = g.prof + 8 * blockIdx.x;
+        p[0] = clock64() - t_begin; p[1] = t_full; p[2] = t_lvl; p[3] = t_q; p[4] = n_blk;
       }
     }
   } else {
     // ===================== epilogue: TMEM -> FP64 recombination -> row sum of squares =====================
-    const int lg = warp & 3;                 // TMEM lane group this warp may read
+    // two warps per TMEM lane group (a warp may only read lanes 32 (warp % 4) ..): each takes half of the tile's columns
+    constexpr int NH = NT / 2;
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = lg * 32 + lane;
-    const int etid = tid - 64;               // 0..127
+    const int etid = tid - 64;               // 0..255
     uint32_t pt = 0;
+    long long t_wait = 0, t_tiles = 0, t_ld = 0, t_pre = 0;
     for (;;) {
       oz_wait(qfull(qslot), qphase);
       int item;
@@ -280,40 +399,62 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(qempty(qslot));
       if (++qslot == kOzQueue) { qslot = 0; qphase ^= 1u; }
-      if (item < 0) break;
+      if (item < 0) {
+        if (g.prof && tid == 64) { g.prof[8 * blockIdx.x + 5] = t_wait; g.prof[8 * blockIdx.x + 6] = t_tiles; g.prof[8 * blockIdx.x + 7] = t_ld; g.prof[8 * blockIdx.x + 4] += t_pre << 32; }
+        break;
+      }
+      t_tiles++;
       int jt, rb;
       oz_decode_item(g, item, jt, rb);
       const int c0 = g.N - NT * (g.T - jt);
-      // column scales of this tile (the previous tile's readers are past them: they arrived on tmem_empty after reading)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      long long tp0 = clock64();
+      // column scales of this tile (the previous tile's readers are past them: both barriers below order the rewrite after their last read)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (etid < NT) { const int col = c0 + etid; s_cs[etid] = col >= 0 ? g.colscale[col] : 0.0; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      oz_wait(tmem_full, pt);
-      pt ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      double acc = 0.0;
-      const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < NT; c += 16) {
-        int32_t v[S][16];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      t_pre += clock64() - tp0;
+      // h_n = sum_l 2^-8l acc_l[n], lowest level first (the order in which the levels complete); a level's TMEM columns
+      // are handed back to the MMA issuer as soon as this warp has read them.  int32 -> double through the 2^52 + 2^31
+      // bias (one logic op + one DADD; I2F.F64 runs at a fraction of the FP64 rate).
+      double h[NH];
+      const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NH);
 #pragma unroll
-        for (int l = 0; l < S; l++) tmem_ld16(trow + (uint32_t)(l * NT + c), v[l]);
+      for (int l = 0; l < S; l++) {
+        long long tw0 = clock64();
+        oz_wait(lvl_full(l), pt);
+        t_wait += clock64() - tw0;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const double wl = __longlong_as_double((long long)(1023 - 8 * l) << 52);   // 2^-8l
+        int32_t v[NH];
+        long long tl0 = clock64();
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-          double h = (double)v[S - 1][q];
+        for (int c = 0; c + 16 <= NH; c += 16) tmem_ld16(trow + (uint32_t)(l * NT + c), v + c);   // the whole level in flight
+        if (NH % 16) tmem_ld8(trow + (uint32_t)(l * NT + (NH & ~15)), v + (NH & ~15));
+        tmem_ld_wait();
+        t_ld += clock64() - tl0;
 #pragma unroll
-          for (int l = S - 2; l >= 0; l--) h = fma(h, 0.00390625, (double)v[l][q]);
-          const double y = h * s_cs[c + q];
-          acc = fma(y, y, acc);
+        for (int c = 0; c + 16 <= NH; c += 16) tmem_ld_fence(v + c);
+        if (NH % 16) tmem_ld_fence8(v + (NH & ~15));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lvl_empty(l));   // the level is in registers: its TMEM columns may be overwritten
+#pragma unroll
+        for (int n = 0; n < NH; n++) {
+          const double d = __hiloint2double(0x43300000, v[n] ^ (int)0x80000000) - 4503601774854144.0;
+          h[n] = (l == 0) ? d : fma(d, wl, h[n]);
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
+      pt ^= 1u;
+      double acc = 0.0;
+#pragma unroll
+      for (int n = 0; n < NH; n++) {
+        const double y = h[n] * s_cs[half * NH + n];
+        acc = fma(y, y, acc);
+      }
       const int64_t row = (int64_t)rb * kOzM + row_in_tile;
       if (row < g.B) {
         const double rs = g.rowscale[row] * 0.000244140625;   // 2^eR_b * 2^-12 (fixed-point position of the digit products)
-        g.part[(int64_t)jt * g.B + row] = acc * rs * rs;
+        g.part[(int64_t)(2 * jt + half) * g.B + row] = acc * rs * rs;
       }
     }
   }

@@ -113,13 +113,13 @@ static int make_tmap(cl_ctx* c, CUtensorMap* tm, const double* ptr, int64_t rows
   return CL_OK;
 }
 
-// 3-D int8 tensor [slices][rows][ld bytes] with k extent `cols`, box = {64 B of k, box_rows, slices}, 64-byte swizzle
-static int make_tmap_planes(cl_ctx* c, CUtensorMap* tm, const int8_t* ptr, int64_t cols, int64_t rows, int slices, int64_t ld, int box_rows) {
+// 3-D int8 tensor [slices][rows][ld bytes] with k extent `cols`, box = {64 B of k, box_rows, box_slices}, 64-byte swizzle
+static int make_tmap_planes(cl_ctx* c, CUtensorMap* tm, const int8_t* ptr, int64_t cols, int64_t rows, int slices, int64_t ld, int box_rows, int box_slices) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(c, CL_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slices};
   cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)kOzKB, (cuuint32_t)box_rows, (cuuint32_t)slices};
+  cuuint32_t box[3] = {(cuuint32_t)kOzKB, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -545,7 +545,7 @@ static int ensure_rows(cl_ctx* c, int64_t rows) {
   CUDA_TRY(c, cudaMalloc(&c->d_aux, cap * AUX_COUNT * sizeof(double)));
   if (c->d_W) {
     CUDA_TRY(c, cudaMalloc(&c->d_R, cap * c->ldR * sizeof(double)));
-    const int64_t t_max = std::max<int64_t>(c->T, (c->ds.n_sn + OzCfg<7>::NT - 1) / OzCfg<7>::NT);  // either engine
+    const int64_t t_max = std::max<int64_t>(c->T, 2 * ((c->ds.n_sn + OzCfg<7>::NT - 1) / OzCfg<7>::NT));  // either engine
     CUDA_TRY(c, cudaMalloc(&c->d_part, cap * t_max * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_part_u, cap * c->T * sizeof(double)));
   }
@@ -594,7 +594,17 @@ static int launch_s12(cl_ctx* c, const Stage12Args& a, cudaStream_t st) {
 // digit planes for the tcgen05 engine: W planes once per slice count, residual planes sized like the workspace
 template <int S>
 static int oz_slice_launch(cl_ctx* c, const double* src, int64_t ld_src, int64_t rows, int n, int8_t* dst, double* scale, cudaStream_t st) {
-  k_oz_slice_rows<S><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const int trips = (int)(c->oz_ld / 128);
+  // register-resident rows (one HBM read) when the row is 32-byte aligned and short enough
+  const bool reg_ok = (ld_src % 4 == 0) && (((uintptr_t)src & 31) == 0) && trips <= 16;
+#define OZ_REG(T) k_oz_slice_rows_reg<S, T><<<grid, 256, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale)
+  if (reg_ok && trips <= 8) OZ_REG(8);
+  else if (reg_ok && trips <= 12) OZ_REG(12);
+  else if (reg_ok && trips <= 14) OZ_REG(14);
+  else if (reg_ok) OZ_REG(16);
+  else k_oz_slice_rows<S><<<grid, 256, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale);
+#undef OZ_REG
   c->launches++;
   CUDA_TRY(c, cudaGetLastError());
   return CL_OK;
@@ -618,7 +628,7 @@ static int ensure_planes(cl_ctx* c, int64_t rows, cudaStream_t st) {
     CUDA_TRY(c, cudaMalloc(&c->d_wscale, n * sizeof(double)));
     int rc = oz_slice(c, S, c->d_W, c->ldW, n, n, c->d_Ws, c->d_wscale, st);
     if (rc != CL_OK) return rc;
-    rc = make_tmap_planes(c, &c->tmWs, c->d_Ws, n, n, S, c->oz_ld, oz_tile_cols(S));
+    rc = make_tmap_planes(c, &c->tmWs, c->d_Ws, n, n, S, c->oz_ld, oz_tile_cols(S), S);
     if (rc != CL_OK) return rc;
     c->oz_slices_built = S;
   }
@@ -648,11 +658,18 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   if (rc != CL_OK) return rc;
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev_slice, st));
   CUtensorMap tmRs;
-  rc = make_tmap_planes(c, &tmRs, c->d_Rs, n, rows, S, c->oz_ld, kOzM);
+  rc = make_tmap_planes(c, &tmRs, c->d_Rs, n, rows, S, c->oz_ld, kOzM, S);   // OzCfg<S>::SLO planes per box
   if (rc != CL_OK) return rc;
   OzArgs g{};
   g.B = rows; g.N = n; g.T = c->oz_T; g.n_rb = (int)((rows + kOzM - 1) / kOzM);
   g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter; g.diag_trim = c->opt_diag_trim;
+  g.prof = nullptr;
+  if (c->opt_dbg & 4) {   // cycle counters of the contraction kernel, printed after the launch (profiling only)
+    rc = ensure_scratch(c, 8 * 8 * 1024);
+    if (rc != CL_OK) return rc;
+    g.prof = reinterpret_cast<long long*>(c->d_scratch);
+    CUDA_TRY(c, cudaMemsetAsync(g.prof, 0, 8 * 8 * 1024, st));
+  }
   // row blocks per L2 group: the S digit planes of a group's rows (+ the W planes) stay L2-resident across its column tiles
   int grp = c->opt_group_rb > 0 ? c->opt_group_rb : (int)std::max<int64_t>(8, ((64LL << 20) / ((int64_t)kOzM * c->oz_ld * S)) & ~7LL);
   g.group_rb = std::min(grp, g.n_rb);
@@ -664,6 +681,18 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   else oz_launch<7>(grid, st, tmRs, c->tmWs, g);
   c->launches++;
   CUDA_TRY(c, cudaGetLastError());
+  if (g.prof) {
+    std::vector<long long> h(8 * grid);
+    CUDA_TRY(c, cudaMemcpyAsync(h.data(), g.prof, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    double s[8] = {0};
+    double pre = 0;
+    for (int i = 0; i < grid; i++) { pre += (double)(h[8 * i + 4] >> 32) / grid; h[8 * i + 4] &= 0xffffffffLL; }
+    for (int i = 0; i < grid; i++) for (int j = 0; j < 8; j++) s[j] += (double)h[8 * i + j] / grid;
+    fprintf(stderr, "[oz prof] epilogue warp: tcgen05.ld+wait %.0f cyc, column-scale prologue %.0f cyc\n", s[7], pre);
+    fprintf(stderr, "[oz prof] per CTA: total %.0f cyc, wait smem-full %.0f (%.1f%%), wait level-empty %.0f (%.1f%%), wait queue %.0f, k-blocks %.0f | epilogue warp: wait level-full %.0f (%.1f%%), tiles %.0f\n",
+            s[0], s[1], 100 * s[1] / s[0], s[2], 100 * s[2] / s[0], s[3], s[4], s[5], 100 * s[5] / s[0], s[6]);
+  }
   return CL_OK;
 }
 
@@ -712,7 +741,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   }
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
   FinalizeArgs f{};
-  f.B = rows; f.what = what; f.n_part = planes ? c->oz_T : c->T; f.sn_large = large ? 1 : 0;
+  f.B = rows; f.what = what; f.n_part = planes ? 2 * c->oz_T : c->T; f.sn_large = large ? 1 : 0;
   f.part = c->d_part; f.aux = c->d_aux; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value;
   k_finalize<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(f);
   c->launches++;
