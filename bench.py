@@ -7,7 +7,8 @@ stand-in: the real blob is not shipped with the reference), N = 1701 (all rows; 
 cut the reference actually fits), batch B = 65536 parameter vectors per GPU per step.
 
 One "step" = one pass of the whole hot path (stage 1+2 Friedmann distances + residuals, stage 3 chi-squared
-DMMA GEMM, finalize) over one batch.  `value` is device-resident throughput (inputs already in HBM), `e2e` is
+contraction, finalize) over one batch.  Stage 3 runs on the library's default engine (tcgen05 kind::i8 digit planes, 7
+planes = every bit of the FP64 rows); the FP64 DMMA engine and the 6-plane setting are timed beside it ("engines").  `value` is device-resident throughput (inputs already in HBM), `e2e` is
 the same through the C ABI with host buffers (H2D + D2H inside the timed region).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -32,6 +33,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "likelihood evals/sec (Pantheon+ full-cov, batch 65536)"
 UNIT = "evals/s"
+#: tcgen05.mma kind::i8 issue rate measured on this pool's B200 (profiles/r02_ubench_umma_i8.log), int8 TOP/s
+I8_PEAK_TOPS = 4485.0
+#: DRAM bytes per launch of k_chi2_ozaki<S> from ncu --set full (profiles/), keyed by (planes, N, B)
+OZ_DRAM_BYTES = {}
 
 
 def build_spec(n_sn):
@@ -186,6 +191,9 @@ def main():
     ap.add_argument("--n-sn", type=int, default=1701, choices=[1590, 1701])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (tuning experiments)")
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "dmma"], help="stage-3 engine of the headline run")
+    ap.add_argument("--slices", type=int, default=7, choices=[5, 6, 7], help="int8 digit planes of the tcgen05 engine")
+    ap.add_argument("--no-alt", action="store_true", help="skip timing the other stage-3 engines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -210,6 +218,8 @@ def main():
 
     spec = build_spec(args.n_sn)
     eng = Engine(spec, device=local_rank)
+    eng.set_option("chi2_engine", 1 if args.engine == "tcgen05" else 0)
+    eng.set_option("chi2_slices", args.slices)
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, int(v))
@@ -240,7 +250,7 @@ def main():
         got = d_out[:64].cpu().numpy()
         want = O.Oracle(spec).log_likelihood(host_batches[(args.warmup - 1) % n_rot][:64])
         parity = float(np.max(np.abs(-2 * got - -2 * want) / np.maximum(1.0, 1e-6 * np.abs(2 * want)) ))
-        if not args.opt and not np.all(np.abs(2 * got - 2 * want) <= np.maximum(1e-6, 1e-12 * np.abs(2 * want))):
+        if not args.opt and args.slices >= 6 and not np.all(np.abs(2 * got - 2 * want) <= np.maximum(1e-6, 1e-12 * np.abs(2 * want))):
             raise SystemExit(f"parity check failed before timing: max |dchi2| = {np.max(np.abs(2*got-2*want))}")
 
     # ---- timed region: device-resident ----
@@ -262,6 +272,7 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
     hist = eng.timing_history(min(args.steps, 64))
+    split = np.atleast_2d(np.asarray(eng.stage3_split(min(args.steps, 64))))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -299,36 +310,84 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # ---- the other stage-3 engines on the same batches (rank 0, one GPU): device-resident, 20 steps each ----
+    engines = None
+    if rank == 0 and world == 1 and not args.no_alt and not args.opt:
+        engines = {}
+        ref_out = d_out.clone()
+        for name, e_id, sl in (("dmma_fp64", 0, 7), ("tcgen05_7planes", 1, 7), ("tcgen05_6planes", 1, 6)):
+            eng.set_option("chi2_engine", e_id); eng.set_option("chi2_slices", sl)
+            for i in range(3):
+                step(args.steps - 1)
+            diff = float((d_out - ref_out).abs().max().item()) * 2.0      # |d chi2| against the headline engine, same batch
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for i in range(20):
+                step(i)
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            h, sp = eng.timing_history(20), eng.stage3_split(20)
+            engines[name] = {"evals_per_s": B * 20 / (a0.elapsed_time(a1) * 1e-3), "stage12_ms": float(np.mean(h[:, 0])),
+                             "planes_ms": float(np.mean(sp[:, 0])), "contraction_ms": float(np.mean(sp[:, 1])),
+                             "max_abs_dchi2_vs_headline": diff}
+        eng.set_option("chi2_engine", 1 if args.engine == "tcgen05" else 0); eng.set_option("chi2_slices", args.slices)
+
     if rank == 0:
         N = args.n_sn
         value = B * world * args.steps / (ms * 1e-3)
-        gemm_ms = float(np.mean(hist[:, 1])); s12_ms = float(np.mean(hist[:, 0]))
-        flops = B * (N * N + 2.0 * N)  # algorithmic: forward-substitution-equivalent MACs*2
-        ach = flops / (gemm_ms * 1e-3) / 1e12
+        gemm_ms = float(np.mean(split[:, 1])); planes_ms = float(np.mean(split[:, 0])); s12_ms = float(np.mean(hist[:, 0]))
+        flops = B * (N * N + 2.0 * N)  # algorithmic FP64: forward-substitution-equivalent MACs*2
         pk = measured_peaks()
         hbm_peak = pk.get("hbm_gbs", 6650.0)
         s12_bytes = B * (8.0 * nd + 8.0 * N + 8.0)  # theta in, residual row out, aux
+        if args.engine == "dmma":
+            ach = flops / (gemm_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "k_chi2_gemm (stage 3, FP64 DMMA)", "achieved": ach, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": ach / peak_tf,
+                        "traffic": 1.20e9 if (N == 1701 and B == 65536) else None,
+                        "traffic_note": "DRAM bytes per launch (dram__bytes_read+write, ncu, profiles/r01f_gemm_dram.csv); "
+                                        "algorithmic 0.92e9 (R read once + W + partial sums)",
+                        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                                       "DMMA.8x8x4 issue peak measured 37.1 TFLOP/s (profiles/r01_ubench_fp64.log)",
+                        "algorithmic_flops_per_eval": N * N + 2.0 * N, "avg_kernel_ms": gemm_ms}
+        else:
+            S = args.slices
+            pairs = S * (S + 1) // 2
+            i8_ops = B * pairs * (N * N + N + 0.0)   # algorithmic int8 ops: `pairs` exact digit-plane products of the N(N+1)/2-MAC triangle
+            ach = i8_ops / (gemm_ms * 1e-3) / 1e12
+            i8_peak = I8_PEAK_TOPS
+            roofline = {"bound": "tensor", "kernel": f"k_chi2_ozaki<{S}> (stage 3, tcgen05.mma kind::i8, {pairs} digit-plane products)",
+                        "achieved": ach, "peak": i8_peak, "unit": "TFLOP/s", "frac": ach / i8_peak,
+                        "unit_note": "int8 tensor TOP/s (2 x MAC); the FP64 tensor pipe is not used by this engine",
+                        "traffic": OZ_DRAM_BYTES.get((S, N, B)),
+                        "traffic_note": "DRAM bytes per launch (dram__bytes_read+write, ncu --set full, profiles/); algorithmic = the digit planes "
+                                        f"read once ({S} B per residual) + the W planes = {(S * B * N + S * N * N / 2) / 1e9:.2f}e9",
+                        "peak_source": "tcgen05.mma kind::i8 M=128 N=256 K=32 issue rate measured on this pool's B200 (tools/ubench_umma_i8.cu, "
+                                       "profiles/r02_ubench_umma_i8.log: 136.1 cycles per MMA = 7709 MAC/clk/SM -> 4485 TOP/s at 1965 MHz; nominal 4766)",
+                        "algorithmic_int8_ops_per_eval": pairs * (N * N + N), "avg_kernel_ms": gemm_ms,
+                        "fp64_equivalent": {"achieved_tflops": flops / (gemm_ms * 1e-3) / 1e12, "dgemm_peak_tflops": peak_tf,
+                                            "note": "the same contraction counted in FP64 flops (N^2 + 2N per eval) against cuBLAS DGEMM measured in this run"},
+                        "bound_note": "shared-memory bandwidth (UTCIMMA operand reads + TMA writes) sits just above the tensor pipe for this shape: "
+                                      "DESIGN.md section 4"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, spec, world),
-            "roofline": {"bound": "tensor", "kernel": "k_chi2_gemm (stage 3, FP64 DMMA)", "achieved": ach, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": 1.20e9 if (N == 1701 and B == 65536) else None,
-                         "traffic_note": "DRAM bytes per launch (dram__bytes_read+write, ncu, profiles/r01f_gemm_dram.csv); "
-                                         "algorithmic 0.92e9 (R read once + W + partial sums)",
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                                        "DMMA.8x8x4 issue peak measured 37.1 TFLOP/s (profiles/r01_ubench_fp64.log)",
-                         "algorithmic_flops_per_eval": N * N + 2.0 * N, "avg_kernel_ms": gemm_ms},
+            "dtype": "f64" if args.engine == "dmma" else "f64 (stage 3: exact int8 digit planes, int32 accumulation, FP64 recombination)",
+            "data": "synthetic", "config": workload_config(args, spec, world),
+            "roofline": roofline,
             "roofline_stage12": {"bound": "hbm", "kernel": "k_friedmann_residuals (stage 1+2)", "achieved": s12_bytes / (s12_ms * 1e-3) / 1e9,
                                  "peak": hbm_peak, "unit": "GB/s", "frac": s12_bytes / (s12_ms * 1e-3) / 1e9 / hbm_peak,
                                  "avg_kernel_ms": s12_ms, "note": "FP64-ALU bound, not HBM bound (SURVEY.md T5)"},
-            "stage_ms": {"stage12": s12_ms, "stage3": gemm_ms, "finalize": float(np.mean(hist[:, 2])), "total": float(np.mean(hist[:, 3]))},
+            "stage_ms": {"stage12": s12_ms, "stage3_planes": planes_ms, "stage3_contraction": gemm_ms, "finalize": float(np.mean(hist[:, 2])),
+                         "total": float(np.mean(hist[:, 3]))},
             "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": int(launches), "clocks": clocks, "parity_check": "64 rows vs oracle ok",
-            "engine": eng.describe(),
+            "engine": eng.describe() + f", stage 3: {args.engine}" + (f" {args.slices} planes" if args.engine == "tcgen05" else ""),
         }
+        if engines:
+            line["engines"] = engines
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(spec, host_batches[0])
         print(json.dumps(line), flush=True)

@@ -115,6 +115,36 @@ __device__ __forceinline__ void oz_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
+// Balanced base-256 digits of four fixed-point values at once.  Adding 0x80 at every digit position below the top one
+// turns the carry chain of the recoding d = ((v + 128) & 255) - 128, v <- (v + 128) >> 8 into one 64-bit addition; the
+// digit bytes are then the bytes of the sum with their top bit flipped, and the top digit is what remains above them.
+// w[s] = the four digits of plane s (plane 0 = most significant), one byte per value: a 4 x S byte transpose (PRMT).
+template <int S>
+__device__ __forceinline__ void oz_digits4(const long long (&v)[4], uint32_t (&w)[S]) {
+  constexpr unsigned long long kBias = 0x0080808080808080ULL >> (8 * (8 - S));   // 0x80 in bytes 0 .. S-2
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const unsigned long long u = ((unsigned long long)v[q] + kBias) ^ kBias;
+    lo[q] = (uint32_t)u; hi[q] = (uint32_t)(u >> 32);
+  }
+  uint32_t b[8];
+  {
+    const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[0], lo[1], 0x7362);
+    const uint32_t t2 = __byte_perm(lo[2], lo[3], 0x5140), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+    b[0] = __byte_perm(t0, t2, 0x5410); b[1] = __byte_perm(t0, t2, 0x7632);
+    b[2] = __byte_perm(t1, t3, 0x5410); b[3] = __byte_perm(t1, t3, 0x7632);
+  }
+  {
+    const uint32_t t0 = __byte_perm(hi[0], hi[1], 0x5140), t1 = __byte_perm(hi[0], hi[1], 0x7362);
+    const uint32_t t2 = __byte_perm(hi[2], hi[3], 0x5140), t3 = __byte_perm(hi[2], hi[3], 0x7362);
+    b[4] = __byte_perm(t0, t2, 0x5410); b[5] = __byte_perm(t0, t2, 0x7632);
+    b[6] = __byte_perm(t1, t3, 0x5410); b[7] = __byte_perm(t1, t3, 0x7632);
+  }
+#pragma unroll
+  for (int s = 0; s < S; s++) w[s] = b[S - 1 - s];
+}
+
 // ---- slicing: fp64 rows -> S int8 digit planes + one power-of-two scale per row --------------------------------------
 // dst[s][row][ld] (int8), scale[row] = 2^e with |x| < 2^e for the whole row.  One warp per row.
 template <int S>
@@ -139,25 +169,14 @@ __global__ void __launch_bounds__(256) k_oz_slice_rows(const double* __restrict_
   // four consecutive k per lane -> one 32-bit store per digit plane
   for (int k0 = 4 * lane; k0 < ld_dst; k0 += 128) {
     uint32_t w[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) w[s] = 0u;
+    long long v[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int k = k0 + q;
-      long long v = 0;
-      if (k < n) {
-        double t = x[k] * up;
-        t = fmin(fmax(t, -kLim), kLim);   // |v| <= 2^FRAC_BITS for finite rows; garbage rows are clamped
-        v = __double2ll_rn(t);
-      }
-#pragma unroll
-      for (int s = S - 1; s >= 1; s--) {
-        const long long d = (long long)(int8_t)(v & 0xff);
-        w[s] |= (uint32_t)(uint8_t)d << (8 * q);
-        v = (v - d) >> 8;
-      }
-      w[0] |= (uint32_t)(uint8_t)(int8_t)v << (8 * q);
+      v[q] = 0;
+      if (k < n) v[q] = __double2ll_rn(fmin(fmax(x[k] * up, -kLim), kLim));   // |v| <= 2^FRAC_BITS for finite rows; garbage rows are clamped
     }
+    oz_digits4<S>(v, w);
 #pragma unroll
     for (int s = 0; s < S; s++) *reinterpret_cast<uint32_t*>(d0 + s * plane + k0) = w[s];
   }
@@ -204,19 +223,10 @@ __global__ void __launch_bounds__(256) k_oz_slice_rows_reg(const double* __restr
     if (k0 >= ld_dst) break;
     const double xs[4] = {xa[t].x, xa[t].y, xb[t].x, xb[t].y};
     uint32_t w[S];
+    long long v[4];
 #pragma unroll
-    for (int s = 0; s < S; s++) w[s] = 0u;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      long long v = __double2ll_rn(fmin(fmax(xs[q] * up, -kLim), kLim));
-#pragma unroll
-      for (int s = S - 1; s >= 1; s--) {
-        const long long d = (long long)(int8_t)(v & 0xff);
-        w[s] |= (uint32_t)(uint8_t)d << (8 * q);
-        v = (v - d) >> 8;
-      }
-      w[0] |= (uint32_t)(uint8_t)(int8_t)v << (8 * q);
-    }
+    for (int q = 0; q < 4; q++) v[q] = __double2ll_rn(fmin(fmax(xs[q] * up, -kLim), kLim));
+    oz_digits4<S>(v, w);
 #pragma unroll
     for (int s = 0; s < S; s++) *reinterpret_cast<uint32_t*>(d0 + s * plane + k0) = w[s];
   }

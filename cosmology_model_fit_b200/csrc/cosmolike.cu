@@ -31,7 +31,7 @@ struct cl_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   static constexpr int kRing = 64;      // timing history: one event set per evaluation call
-  cudaEvent_t evring[kRing][6] = {};
+  cudaEvent_t evring[kRing][7] = {};   // [6]: between forming the digit planes and the contraction (stage 3 split)
   cudaEvent_t* ev = evring[0];
   int64_t n_timed = 0;
   DevSpec ds{};
@@ -55,7 +55,7 @@ struct cl_ctx {
   int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0;
   int* d_counter = nullptr;
   // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
-  int opt_engine = CL_CHI2_ENGINE_DMMA, opt_slices = 6, opt_diag_trim = 1;
+  int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_diag_trim = 1;
   int oz_slices_built = 0;           // S the W planes were built for (0 = none)
   int oz_T = 0;                      // column tiles of the sliced kernel
   int64_t oz_ld = 0;                 // bytes per row of a digit plane
@@ -63,7 +63,6 @@ struct cl_ctx {
   double *d_wscale = nullptr, *d_rscale = nullptr;
   int64_t oz_cap_rows = 0;
   CUtensorMap tmWs{};
-  cudaEvent_t ev_slice = nullptr;
   std::string err, desc;
   std::mutex mu;
 };
@@ -299,7 +298,6 @@ extern "C" int cl_destroy(cl_ctx* c) {
   for (double* p : {c->d_theta, c->d_out, c->d_R, c->d_aux, c->d_part, c->d_part_u, c->d_scratch, c->d_W, c->d_u}) if (p) cudaFree(p);
   if (c->d_counter) cudaFree(c->d_counter);
   for (void* p : {(void*)c->d_Ws, (void*)c->d_Rs, (void*)c->d_wscale, (void*)c->d_rscale}) if (p) cudaFree(p);
-  if (c->ev_slice) cudaEventDestroy(c->ev_slice);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   for (auto& r : c->evring) for (auto& e : r) if (e) cudaEventDestroy(e);
@@ -333,7 +331,6 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
   CTRY(cudaSetDevice(device));
   CTRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& r : c->evring) for (auto& e : r) CTRY(cudaEventCreate(&e));
-  CTRY(cudaEventCreate(&c->ev_slice));
 
   DevSpec& d = c->ds;
   const cl_spec& s = *spec;
@@ -656,7 +653,7 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   const int S = c->opt_slices, n = c->ds.n_sn;
   rc = oz_slice(c, S, c->d_R, c->ldR, rows, n, c->d_Rs, c->d_rscale, st);
   if (rc != CL_OK) return rc;
-  if (record) CUDA_TRY(c, cudaEventRecord(c->ev_slice, st));
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
   CUtensorMap tmRs;
   rc = make_tmap_planes(c, &tmRs, c->d_Rs, n, rows, S, c->oz_ld, kOzM, S);   // OzCfg<S>::SLO planes per box
   if (rc != CL_OK) return rc;
@@ -714,7 +711,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
     rc = run_stage3_planes(c, rows, st, record);
     if (rc != CL_OK) return rc;
   } else if (large) {
-    if (record) CUDA_TRY(c, cudaEventRecord(c->ev_slice, st));
+    if (record) CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
     CUtensorMap tmR;
     rc = make_tmap(c, &tmR, c->d_R, rows, c->ds.n_sn, c->ldR);
     if (rc != CL_OK) return rc;
@@ -909,16 +906,20 @@ extern "C" int cl_last_timing(cl_ctx* c, double ms[4]) {
   return timing_of(c, c->n_timed - 1, ms);
 }
 
-extern "C" int cl_stage3_split(cl_ctx* c, double ms[2]) {
-  if (!c || !ms) return CL_E_INVALID;
-  if (c->n_timed == 0 || !c->d_W) return fail(c, CL_E_INVALID, "no large-SN evaluation has been timed yet");
+extern "C" int cl_stage3_split(cl_ctx* c, int n, double* ms) {
+  if (!c || !ms || n < 0) return CL_E_INVALID;
+  if (!c->d_W) return fail(c, CL_E_INVALID, "the spec has no large SN block");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaEvent_t* ev = c->evring[(c->n_timed - 1) % cl_ctx::kRing];
-  CUDA_TRY(c, cudaEventSynchronize(ev[5]));
-  float t;
-  CUDA_TRY(c, cudaEventElapsedTime(&t, ev[2], c->ev_slice)); ms[0] = t;
-  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev_slice, ev[3])); ms[1] = t;
-  return CL_OK;
+  int avail = (int)std::min<int64_t>(c->n_timed, cl_ctx::kRing);
+  int k = std::min(n, avail);
+  for (int i = 0; i < k; i++) {
+    cudaEvent_t* ev = c->evring[(c->n_timed - k + i) % cl_ctx::kRing];
+    CUDA_TRY(c, cudaEventSynchronize(ev[5]));
+    float t;
+    CUDA_TRY(c, cudaEventElapsedTime(&t, ev[2], ev[6])); ms[2 * i] = t;
+    CUDA_TRY(c, cudaEventElapsedTime(&t, ev[6], ev[3])); ms[2 * i + 1] = t;
+  }
+  return k;
 }
 
 extern "C" int cl_timing_history(cl_ctx* c, int n, double* ms) {

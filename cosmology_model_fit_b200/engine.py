@@ -70,7 +70,7 @@ def load_library():
     lib.cl_sn_residuals.argtypes = [ctxp, _dp, i64, i64, _dp]
     lib.cl_last_timing.argtypes = [ctxp, C.c_double * 4]
     lib.cl_timing_history.argtypes = [ctxp, C.c_int, _dp]
-    lib.cl_stage3_split.argtypes = [ctxp, C.c_double * 2]
+    lib.cl_stage3_split.argtypes = [ctxp, C.c_int, _dp]
     lib.cl_launch_count.argtypes = [ctxp]
     lib.cl_launch_count.restype = i64
     lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
@@ -228,11 +228,14 @@ class Engine:
         self._check(self.lib.cl_last_timing(self._ctx, ms))
         return {"stage12_ms": ms[0], "stage3_ms": ms[1], "finalize_ms": ms[2], "total_ms": ms[3]}
 
-    def stage3_split(self):
-        """(ms forming the int8 digit planes of the residual rows, ms in the contraction kernel) of the last evaluation."""
-        ms = (C.c_double * 2)()
-        self._check(self.lib.cl_stage3_split(self._ctx, ms))
-        return ms[0], ms[1]
+    def stage3_split(self, n=1):
+        """[k, 2] array (ms forming the int8 digit planes of the residual rows, ms in the contraction kernel) of the
+        last k <= n evaluations, oldest first; the single pair for n == 1."""
+        buf = np.zeros((max(n, 1), 2))
+        k = self.lib.cl_stage3_split(self._ctx, int(n), _p(buf))
+        if k < 0:
+            self._check(k)
+        return tuple(buf[0]) if n == 1 else buf[:k]
 
     def timing_history(self, n):
         """[k, 4] array (stage12, stage3, finalize, total ms) of the last k <= n evaluations, oldest first."""

@@ -32,7 +32,9 @@ extern "C" {
  *   DMMA    — FP64 tensor pipe (mma.sync f64), bit-stable FP64 contraction;
  *   TCGEN05 — 5th-generation tensor cores: the residual rows and W = L^-1 are split into "chi2_slices" (5..7, default 6)
  *             int8 digit planes, multiplied exactly with tcgen05.mma kind::i8 (int32 accumulators in TMEM) and recombined in
- *             FP64; 6 planes carry 46 bits per row: |d chi2| / chi2 ~ 3e-13. */
+ *             FP64.  7 planes (default) carry all 53 bits of every row: same accuracy class as the FP64 engine
+ *             (|d chi2| ~ 1e-10 at chi2 ~ 6e4); 6 planes carry 46 bits: |d chi2| / chi2 ~ 2e-12, 30 % faster.
+ * Default: TCGEN05 with 7 planes.  sn_moments always uses DMMA. */
 enum { CL_CHI2_ENGINE_DMMA = 0, CL_CHI2_ENGINE_TCGEN05 = 1 };
 
 /* error codes */
@@ -247,9 +249,9 @@ int cl_sn_residuals(cl_ctx* ctx, const double* theta, int64_t B, int64_t ld, dou
  * ms[0] stage 1+2 (Friedmann distances + residuals), ms[1] stage 3 (chi-squared GEMM), ms[2] finalize,
  * ms[3] total device time incl. copies for cl_eval.  Blocks until the events have completed. */
 int cl_last_timing(cl_ctx* ctx, double ms[4]);
-/* Split of ms[1] for the most recent evaluation: ms[0] = forming the int8 digit planes of the residual rows (0 with the
- * DMMA engine), ms[1] = the contraction kernel itself. */
-int cl_stage3_split(cl_ctx* ctx, double ms[2]);
+/* Split of ms[1] for the most recent n evaluations, oldest first: ms[i][0] = forming the int8 digit planes of the residual
+ * rows (0 with the DMMA engine), ms[i][1] = the contraction kernel itself.  Returns the number of entries written. */
+int cl_stage3_split(cl_ctx* ctx, int n, double* ms);
 /* Same for the most recent n evaluations (the library keeps the last 64), oldest first: ms[i][4].
  * Returns the number of entries written (<= n) or a negative error. */
 int cl_timing_history(cl_ctx* ctx, int n, double* ms);
