@@ -38,7 +38,7 @@ template <int S> struct OzCfg {
   static constexpr int PLANE_BYTES = kOzM * kOzKB;
   static constexpr int A_UNIT_BYTES = SLO * PLANE_BYTES;
   static constexpr int B_BYTES = S * NT * kOzKB;
-  static constexpr int A_UNITS = (3 * A_UNIT_BYTES + kOzBStages * B_BYTES <= 222 * 1024) ? 3 : 2;
+  static constexpr int A_UNITS = (3 * A_UNIT_BYTES + kOzBStages * B_BYTES <= 224 * 1024) ? 3 : 2;   // 7 planes: 3 x 56 KB + 2 x 28 KB = 224 KB, 231296 B with the rest (limit 232448)
   static constexpr int A_RING = A_UNITS * A_UNIT_BYTES, B_RING = kOzBStages * B_BYTES;
   static constexpr int SMEM = 1024 + A_RING + B_RING + NT * 8 + 384;
   static constexpr int FRAC_BITS = 6 + 8 * (S - 1);

@@ -55,7 +55,7 @@ struct cl_ctx {
   int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0;
   int* d_counter = nullptr;
   // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
-  int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_diag_trim = 1;
+  int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_diag_trim = 1, opt_slice_tpb = 128;
   int oz_slices_built = 0;           // S the W planes were built for (0 = none)
   int oz_T = 0;                      // column tiles of the sliced kernel
   int64_t oz_ld = 0;                 // bytes per row of a digit plane
@@ -523,6 +523,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
     if (value != CL_CHI2_ENGINE_DMMA && value != CL_CHI2_ENGINE_TCGEN05) return fail(c, CL_E_INVALID, "chi2_engine must be 0 (FP64 DMMA) or 1 (tcgen05 int8 digit planes)");
     c->opt_engine = (int)value; return CL_OK;
   }
+  if (n == "chi2_slice_tpb") { if (value != 64 && value != 128 && value != 256) return fail(c, CL_E_INVALID, "chi2_slice_tpb must be 64, 128 or 256"); c->opt_slice_tpb = (int)value; return CL_OK; }
   if (n == "chi2_slices") {
     if (value < 5 || value > 7) return fail(c, CL_E_INVALID, "chi2_slices must be 5, 6 or 7");
     c->opt_slices = (int)value; return CL_OK;
@@ -591,16 +592,17 @@ static int launch_s12(cl_ctx* c, const Stage12Args& a, cudaStream_t st) {
 // digit planes for the tcgen05 engine: W planes once per slice count, residual planes sized like the workspace
 template <int S>
 static int oz_slice_launch(cl_ctx* c, const double* src, int64_t ld_src, int64_t rows, int n, int8_t* dst, double* scale, cudaStream_t st) {
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const int tpb = c->opt_slice_tpb;   // threads per block of the slicing kernel (one warp per row)
+  const unsigned grid = (unsigned)((rows + tpb / 32 - 1) / (tpb / 32));
   const int trips = (int)(c->oz_ld / 128);
   // register-resident rows (one HBM read) when the row is 32-byte aligned and short enough
   const bool reg_ok = (ld_src % 4 == 0) && (((uintptr_t)src & 31) == 0) && trips <= 16;
-#define OZ_REG(T) k_oz_slice_rows_reg<S, T><<<grid, 256, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale)
+#define OZ_REG(T) k_oz_slice_rows_reg<S, T><<<grid, tpb, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale)
   if (reg_ok && trips <= 8) OZ_REG(8);
   else if (reg_ok && trips <= 12) OZ_REG(12);
   else if (reg_ok && trips <= 14) OZ_REG(14);
   else if (reg_ok) OZ_REG(16);
-  else k_oz_slice_rows<S><<<grid, 256, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale);
+  else k_oz_slice_rows<S><<<grid, tpb, 0, st>>>(src, ld_src, rows, n, dst, c->oz_ld, scale);
 #undef OZ_REG
   c->launches++;
   CUDA_TRY(c, cudaGetLastError());
