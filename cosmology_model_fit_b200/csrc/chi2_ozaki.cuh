@@ -40,7 +40,7 @@ template <int S> struct OzCfg {
   static constexpr int B_BYTES = S * NT * kOzKB;
   static constexpr int A_UNITS = (3 * A_UNIT_BYTES + kOzBStages * B_BYTES <= 224 * 1024) ? 3 : 2;   // 7 planes: 3 x 56 KB + 2 x 28 KB = 224 KB, 231296 B with the rest (limit 232448)
   static constexpr int A_RING = A_UNITS * A_UNIT_BYTES, B_RING = kOzBStages * B_BYTES;
-  static constexpr int SMEM = 1024 + A_RING + B_RING + NT * 8 + 384;
+  static constexpr int SMEM = 1024 + A_RING + B_RING + 2 * NT * 8 + 384;
   static constexpr int FRAC_BITS = 6 + 8 * (S - 1);
   static constexpr int MAX_STACK = 256 / NT;   // digit planes of W one MMA may cover (N <= 256)
 };
@@ -53,6 +53,8 @@ struct OzArgs {
   double* part;            // [2 T][B] partial sums of squares (one plane per half column tile)
   const double* rowscale;  // [B] 2^eR_b
   const double* colscale;  // [N] 2^eW_n
+  double* part_u;          // nullable [2 T][B]: partial sums of y_n u_n (offset moments)
+  const double* u;         // [N] u = W 1
   int* counter;            // dynamic scheduling counter (zeroed before the launch)
   int group_rb;            // row blocks per L2 group
   int diag_trim;           // 1: shrink the MMA N extent inside the diagonal block
@@ -244,7 +246,8 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const uint32_t sA = base;                       // [A_UNITS][SLO planes][128 rows][64 B]
   const uint32_t sB = base + C::A_RING;           // [kOzBStages][S planes][NT rows][64 B]
   double* s_cs = reinterpret_cast<double*>(base_ptr + C::A_RING + C::B_RING);  // [NT] column scales of the tile
-  const uint32_t bars = base + C::A_RING + C::B_RING + NT * 8;
+  double* s_u = s_cs + NT;                                                     // [NT] u of the tile's columns (moments)
+  const uint32_t bars = base + C::A_RING + C::B_RING + 2 * NT * 8;
   auto fullA = [&](int s) { return bars + 8u * s; };
   auto emptyA = [&](int s) { return bars + 8u * (6 + s); };
   auto fullB = [&](int s) { return bars + 8u * (12 + s); };
@@ -420,7 +423,11 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       long long tp0 = clock64();
       // column scales of this tile (the previous tile's readers are past them: both barriers below order the rewrite after their last read)
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (etid < NT) { const int col = c0 + etid; s_cs[etid] = col >= 0 ? g.colscale[col] : 0.0; }
+      if (etid < NT) {
+        const int col = c0 + etid;
+        s_cs[etid] = col >= 0 ? g.colscale[col] : 0.0;
+        if (g.part_u) s_u[etid] = col >= 0 ? g.u[col] : 0.0;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       t_pre += clock64() - tp0;
       // h_n = sum_l 2^-8l acc_l[n], lowest level first (the order in which the levels complete); a level's TMEM columns
@@ -460,11 +467,18 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       for (int n = 0; n < NH; n++) {
         const double y = h[n] * s_cs[half * NH + n];
         acc = fma(y, y, acc);
+        h[n] = y;
+      }
+      double acc_u = 0.0;
+      if (g.part_u) {
+#pragma unroll
+        for (int n = 0; n < NH; n++) acc_u = fma(h[n], s_u[half * NH + n], acc_u);
       }
       const int64_t row = (int64_t)rb * kOzM + row_in_tile;
       if (row < g.B) {
         const double rs = g.rowscale[row] * 0.000244140625;   // 2^eR_b * 2^-12 (fixed-point position of the digit products)
         g.part[(int64_t)(2 * jt + half) * g.B + row] = acc * rs * rs;
+        if (g.part_u) g.part_u[(int64_t)(2 * jt + half) * g.B + row] = acc_u * rs;
       }
     }
   }

@@ -545,7 +545,7 @@ static int ensure_rows(cl_ctx* c, int64_t rows) {
     CUDA_TRY(c, cudaMalloc(&c->d_R, cap * c->ldR * sizeof(double)));
     const int64_t t_max = std::max<int64_t>(c->T, 2 * ((c->ds.n_sn + OzCfg<7>::NT - 1) / OzCfg<7>::NT));  // either engine
     CUDA_TRY(c, cudaMalloc(&c->d_part, cap * t_max * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc(&c->d_part_u, cap * c->T * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_part_u, cap * t_max * sizeof(double)));
   }
   c->cap_rows = cap;
   return CL_OK;
@@ -649,7 +649,7 @@ static void oz_launch(int grid, cudaStream_t st, const CUtensorMap& tmR, const C
 }
 
 // stage 3 with the tcgen05 engine: slice the residual rows, then the int8 contraction
-static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool record) {
+static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool record, bool moments) {
   int rc = ensure_planes(c, rows, st);
   if (rc != CL_OK) return rc;
   const int S = c->opt_slices, n = c->ds.n_sn;
@@ -662,6 +662,7 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   OzArgs g{};
   g.B = rows; g.N = n; g.T = c->oz_T; g.n_rb = (int)((rows + kOzM - 1) / kOzM);
   g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter; g.diag_trim = c->opt_diag_trim;
+  g.part_u = moments ? c->d_part_u : nullptr; g.u = c->d_u;
   g.prof = nullptr;
   if (c->opt_dbg & 4) {   // cycle counters of the contraction kernel, printed after the launch (profiling only)
     rc = ensure_scratch(c, 8 * 8 * 1024);
@@ -708,9 +709,10 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   rc = launch_s12(c, a, st);
   if (rc != CL_OK) return rc;
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
-  const bool planes = large && !moments && c->opt_engine == CL_CHI2_ENGINE_TCGEN05;
+  // int32 level accumulators hold S products of |d_i d_j| <= 2^14 over n_sn terms: exact up to n_sn = 2^31 / (7 * 2^14) = 18724
+  const bool planes = large && c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384;
   if (planes) {
-    rc = run_stage3_planes(c, rows, st, record);
+    rc = run_stage3_planes(c, rows, st, record, moments);
     if (rc != CL_OK) return rc;
   } else if (large) {
     if (record) CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
@@ -802,7 +804,8 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
     if (moments) {
       // out[b] = (yy, yu, uu): reduce the partial planes on the host side of the ABI is avoided: reuse finalize
       // (yy, yu, uu) from the SN partial planes alone
-      k_sum_parts<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(c->d_part, c->d_part_u, c->T, rows, c->uu, d_res);
+      const int n_part = (c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384) ? 2 * c->oz_T : c->T;
+      k_sum_parts<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(c->d_part, c->d_part_u, n_part, rows, c->uu, d_res);
       c->launches++;
       CUDA_TRY(c, cudaGetLastError());
     }

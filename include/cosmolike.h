@@ -34,7 +34,7 @@ extern "C" {
  *             int8 digit planes, multiplied exactly with tcgen05.mma kind::i8 (int32 accumulators in TMEM) and recombined in
  *             FP64.  7 planes (default) carry all 53 bits of every row: same accuracy class as the FP64 engine
  *             (|d chi2| ~ 1e-10 at chi2 ~ 6e4); 6 planes carry 46 bits: |d chi2| / chi2 ~ 2e-12, 30 % faster.
- * Default: TCGEN05 with 7 planes.  sn_moments always uses DMMA. */
+ * Default: TCGEN05 with 7 planes. */
 enum { CL_CHI2_ENGINE_DMMA = 0, CL_CHI2_ENGINE_TCGEN05 = 1 };
 
 /* error codes */

@@ -125,10 +125,18 @@ def test_full_size_batch_against_fp64_engine(engines, slices):
 
 
 def test_components_and_moments_with_the_tcgen05_engine(engines):
-    """components() goes through the sliced contraction, sn_moments() (y.y, y.u, u.u) stays on the FP64 engine."""
+    """components() and sn_moments() (y.y, y.u, u.u: the two-dot epilogue of SURVEY N3) through the sliced contraction."""
     g = golden("bao_desi_cmb_pantheon")
     e, ref = engines("bao_desi_cmb_pantheon", 7), engines("bao_desi_cmb_pantheon", 0)
     a, b = e.components(g["theta"]), ref.components(g["theta"])
     assert np.max(np.abs(a - b)) < 1e-6
-    m = engines("sn_pantheon", 7).sn_moments(golden("sn_pantheon")["theta"])
-    assert np.array_equal(m, engines("sn_pantheon", 0).sn_moments(golden("sn_pantheon")["theta"]))
+    th = golden("sn_pantheon")["theta"]
+    m, m0 = engines("sn_pantheon", 7).sn_moments(th), engines("sn_pantheon", 0).sn_moments(th)
+    assert np.max(np.abs(m - m0) / np.abs(m0)) < 1e-12
+    m6 = engines("sn_pantheon", 6).sn_moments(th)
+    assert np.max(np.abs(m6 - m0) / np.abs(m0)) < 1e-10
+    # chi2(M) = yy - 2 M yu + M^2 uu is what chi_squared() returns (cancellation: M ~ -19.5 enters squared)
+    chi2 = engines("sn_pantheon", 7).chi_squared(th)
+    M = th[:, 0]
+    direct = m[:, 0] - 2 * M * m[:, 1] + M * M * m[:, 2]
+    assert np.max(np.abs(chi2 - direct) / np.abs(direct)) < 1e-9
