@@ -682,7 +682,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         double extra = 0.0, ccnorm = 0.0;
         if (s.n_cc > 0) {
           double f = s.col_fcc >= 0 ? th[s.col_fcc] : 1.0;
-          extra += f * f * v[3];
+          extra += (s.cc_norm_sign < 0.0 ? 1.0 / (f * f) : f * f) * v[3];   // error-inflation form: chi2 * f ** -2 (ohd/cc_pantheon.py:63)
           if (s.cc_norm_sign != 0.0) ccnorm = s.n_cc * log(2 * M_PI) + s.cc_logdet - s.cc_norm_sign * 2 * s.n_cc * log(f);
         }
         for (int g = 0; g < s.n_gc; g++) {

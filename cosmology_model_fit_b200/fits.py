@@ -102,6 +102,29 @@ def sn_union3_1(sn, z_turn=0.2):
     return _sn_block(sp, sn, S.SN_INVCOV, z_turn, 0, 2)
 
 
+def _sn_cmb(sn, form, z_turn, consts, bounds=None):
+    consts = consts or S.cmb_planck_act()
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0]), bounds=bounds)
+    return _sn_block(sp, sn, form, z_turn, 0, 4)
+
+
+def sn_pantheon_cmb(sn, consts=None):
+    """sn/pantheon_cmb.py: theta = (M, H0, obh2, och2, v); full LCDM; Pantheon+ (Cholesky) + compressed CMB 3x3; box prior."""
+    bounds = np.array([(-20.0, -19.0), (60.0, 75.0), (0.010, 0.030), (0.010, 0.25), (-2.5, 2.5)])  # sn/pantheon_cmb.py:86-94
+    return _sn_cmb(sn, S.SN_CHOLESKY, 0.15, consts, bounds)
+
+
+def sn_des5y_cmb(sn, consts=None):
+    """sn/des5y_cmb.py: theta = (dM, H0, obh2, och2, v); DES-Dovekie (Cholesky, step at z_cmb <= 0.11) + CMB 3x3."""
+    return _sn_cmb(sn, S.SN_CHOLESKY, 0.11, consts)
+
+
+def sn_union3_1_cmb(sn, consts=None):
+    """sn/union3_1_cmb.py: theta = (dM, H0, obh2, och2, v); Union3.1 (d @ inv_cov @ d, step at 0.2) + CMB 3x3."""
+    return _sn_cmb(sn, S.SN_INVCOV, 0.2, consts)
+
+
 # --------------------------------------------------------------------------------------------- cmb/*
 def cmb_cmb(consts=None):
     """cmb/cmb.py: theta = (H0, obh2, och2); compressed CMB only."""
@@ -179,6 +202,59 @@ def bao_desi_des5y_bbn_theta_star(sn, desi, consts=None, with_v=False, z_turn=0.
                         col_w0=4, cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=w,
                         z_grid=_grid(sn[0], desi[0]), bounds=np.array(bounds), gauss_prior=((2, *BBN_SCHONEBERG),))
     _sn_block(sp, sn, S.SN_CHOLESKY, z_turn, 0, 5 if with_v else None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def _la_only(consts):
+    """chi2 = (l_A - l_A_model)^2 / cov[1, 1] (bao/desi_bbn_theta_star.py:96-99): a 3x3 weight with one non-zero entry."""
+    w = np.zeros((3, 3))
+    w[1, 1] = 1.0 / consts.covariance[1, 1]
+    return w
+
+
+def bao_desi_bbn_theta_star(desi, consts=None):
+    """bao/desi_bbn_theta_star.py: theta = (H0, obh2, och2, w0); full thawing; Planck (PR3) module, l_A-only term; exact D_H;
+    BBN Gaussian on omega_b through the nautilus prior (:118)."""
+    consts = consts or S.cmb_planck()
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_FULL, de_model=S.DE_THAWING, col_H0=0, col_obh2=1, col_och2=2, col_w0=3,
+                        cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=_la_only(consts), z_grid=_grid(desi[0]),
+                        gauss_prior=((1, *BBN_SCHONEBERG),))
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_union3_bbn_theta_star(sn, desi_fs_lya, consts=None, des_y6=DES_Y6_BAO):
+    """bao/desi_union3_bbn_theta_star.py: theta = (dM, H0, obh2, och2, v); full LCDM; Union3.1 (inv_cov, step at 0.2);
+    DESI FS-Lya + DES-Y6 BAO (15 points, F_AP rows, exact D_H); l_A-only term; BBN prior on omega_b (:168)."""
+    consts = consts or S.cmb_planck_act()
+    bao = concat_bao(desi_fs_lya, des_y6)
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=_la_only(consts), z_grid=_grid(sn[0], bao[0]),
+                        gauss_prior=((2, *BBN_SCHONEBERG),))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 0, 4)
+    return _bao_block(sp, bao, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_union3_cc_theta_star(sn, desi, cc, consts=None):
+    """bao/desi_union3_cc_theta_star.py: theta = (f_cc, dM, H0, obh2, och2, v); full LCDM; Union3.1 + DESI (exact D_H) + l_A
+    + CC (f^2 chi2 with normalisation); nautilus vectorized=True, batch log_likelihood returns float32 (:142-147)."""
+    consts = consts or S.cmb_planck_act()
+    sp = LikelihoodSpec(ndim=6, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=2, col_obh2=3, col_och2=4,
+                        cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=_la_only(consts), z_grid=_grid(sn[0], desi[0]))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 1, 5)
+    _cc_block(sp, cc, 0)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_des5y_cc_theta_star(sn, desi, cc, consts=None):
+    """bao/desi_des5y_cc_theta_star.py: theta = (f_cc, dM, H0, obh2, och2, w0); full thawing; DES-Dovekie (Cholesky, no
+    velocity term) + DESI (exact D_H) + l_A + CC; box prior (:133-151)."""
+    consts = consts or S.cmb_planck_act()
+    bounds = np.array([(0.5, 2.5), (-0.60, 0.60), (50.0, 85.0), (0.005, 0.035), (0.05, 0.30), (-1.0, -1 / 3)])
+    sp = LikelihoodSpec(ndim=6, family=S.FAMILY_FULL, de_model=S.DE_THAWING, col_H0=2, col_obh2=3, col_och2=4, col_w0=5,
+                        cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB, cmb_weight=_la_only(consts), z_grid=_grid(sn[0], desi[0]),
+                        bounds=bounds)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 1, None)
+    _cc_block(sp, cc, 0)
     return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
 
 
@@ -268,6 +344,49 @@ def sn_pantheon_dipole(sn, ra, dec, survey_id, ra_fixed_deg=217, dec_fixed_deg=-
     return sp
 
 
+def bao_desi_fs_lya(desi_fs_lya):
+    """bao/desi_fs_lya.py: theta = (h, Om, w0); late thawing; DESI DR2 full-shape + Lya table (F_AP rows); r_d = 147.09; pchip D_H."""
+    sp = LikelihoodSpec(ndim=3, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=0, H0_scale=100.0, col_Om=1, col_w0=2,
+                        z_grid=_grid(desi_fs_lya[0]))
+    return _bao_block(sp, desi_fs_lya, S.DH_PCHIP, S.RD_FIXED, 147.09)
+
+
+def bao_desi_cc(desi, cc):
+    """bao/desi_cc.py: theta = (f_cc, H0, r_d, Om, w0); late thawing; exact D_H; sampled r_d; CC with f^2 chi2 + normalisation."""
+    bounds = np.array([(0.5, 2.5), (45.0, 90.0), (120.0, 175.0), (0.1, 0.7), (-1.0, 0.0)])  # bao/desi_cc.py:106-114
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=3, col_w0=4,
+                        z_grid=_grid(desi[0]), bounds=bounds)
+    _cc_block(sp, cc, 0)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=2)
+
+
+def _sn_bao_rd(sn, desi, form, z_turn):
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=2, col_Om=3, z_grid=_grid(sn[0], desi[0]),
+                        gauss_prior=((1, 147.09, 0.26),))  # nautilus prior norm(147.09, 0.26) on r_d (bao/desi_des5y_rd.py:125)
+    _sn_block(sp, sn, form, z_turn, 0, 4)
+    return _bao_block(sp, desi, S.DH_PCHIP, S.RD_PARAM, col_rd=1)
+
+
+def bao_desi_des5y_rd(sn, desi):
+    """bao/desi_des5y_rd.py: theta = (dM, r_d, H0, Om, v); late LCDM; DES-Dovekie (Cholesky, step at 0.10563); pchip D_H."""
+    return _sn_bao_rd(sn, desi, S.SN_CHOLESKY, 0.10563)
+
+
+def bao_desi_union3_rd(sn, desi):
+    """bao/desi_union3_rd.py: theta = (dM, r_d, H0, Om, v); late LCDM; Union3.1 (inv_cov, step at 0.2); pchip D_H."""
+    return _sn_bao_rd(sn, desi, S.SN_INVCOV, 0.2)
+
+
+def bao_desi_pantheon_rd(sn, desi):
+    """bao/desi_pantheon_rd.py: theta = (M, H0, Om, r_d, w0); late thawing; Pantheon+ (Cholesky, no velocity term); exact D_H;
+    box prior + Gaussian r_d prior (147.14, 0.29) (:109-113)."""
+    bounds = np.array([(-20.0, -19.0), (50.0, 100.0), (0.2, 0.7), (144.0, 150.0), (-1.0, -1 / 3)])  # :76-84
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=2, col_w0=4,
+                        z_grid=_grid(sn[0], desi[0]), bounds=bounds, gauss_prior=((3, 147.14, 0.29),))
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=3)
+
+
 def bao_desi_omh2(desi):
     """bao/desi_omh2.py: theta = (r_d, H0, omega_m, w0); late thawing with Om = omega_m / h^2; r_d sampled; exact D_H."""
     sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=2, Om_is_physical=True, col_w0=3,
@@ -307,3 +426,23 @@ def ohd_cc(cc):
                           cc_z=z, cc_H=H, cc_inv_cov=np.linalg.inv(cov), col_fcc=2,
                           cc_logdet=float(np.linalg.slogdet(cov)[1]), cc_norm_sign=1.0,
                           z_grid=LikelihoodSpec.make_grid(float(np.max(z))))
+
+
+def ohd_cc_cmb(cc, consts=None):
+    """ohd/cc_cmb.py: theta = (H0, obh2, och2, f_cc); full LCDM; CC (f^2 chi2 + normalisation) + compressed CMB 3x3."""
+    consts = consts or S.cmb_planck_act()
+    bounds = np.array([(63.0, 73.0), (0.0210, 0.0235), (0.05, 0.30), (0.30, 2.75)])  # ohd/cc_cmb.py:38-45
+    sp = LikelihoodSpec(ndim=4, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=0, col_obh2=1, col_och2=2,
+                        cmb_consts=consts, cmb_mode=consts.mode, bounds=bounds, log_prior_norm=0.0,
+                        z_grid=LikelihoodSpec.make_grid(float(np.max(cc[0]))))
+    return _cc_block(sp, cc, 3)
+
+
+def ohd_cc_pantheon(sn, cc):
+    """ohd/cc_pantheon.py: theta = (f_cc, H0, M, Om, w0); late thawing; Pantheon+ (Cholesky, no velocity term) + CC with
+    f_cc inflating the errors: chi2_cc * f ** -2 and + 2 N ln f in the normalisation (:63, :92)."""
+    bounds = np.array([(0.1, 1.5), (55, 80), (-20, -19), (0.15, 0.70), (-1.0, -1 / 3)], dtype=np.float64)  # :68-77
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=3, col_w0=4, z_grid=_grid(sn[0]),
+                        bounds=bounds)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 2, None)
+    return _cc_block(sp, cc, 0, norm_sign=-1.0)

@@ -175,7 +175,8 @@ typedef struct cl_spec {
   int32_t col_fcc;          /* -1: f = 1 */
   double cc_logdet;         /* log det C_cc */
   double cc_norm_sign;      /* log L gets -0.5*(n ln 2pi + logdet) + cc_norm_sign * n ln f;
-                               +1 in ohd/cc.py:33, -1 in ohd/cc_pantheon.py:92 (0 disables the normalisation) */
+                               +1: chi2_cc = f^2 d^T C^-1 d (ohd/cc.py:25,33); -1: f inflates the errors, chi2_cc = f^-2 d^T C^-1 d
+                               (ohd/cc_pantheon.py:63,92); 0 disables the normalisation (chi2_cc = f^2 ...) */
 
   /* ---- extra Gaussian chi2 terms ((theta[col]-mean)/sigma)^2, e.g. H0 TRGB
          (bao/desi_cmb_pantheon_H0trgb.py:124) ---- */

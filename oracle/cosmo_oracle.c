@@ -380,7 +380,8 @@ static void eval_one(const cl_spec* s, const double* th, work_t* w, int grid_bui
     double f = s->col_fcc >= 0 ? th[s->col_fcc] : 1.0;
     double* d = w->vec + CL_MAX_BAO;
     for (int k = 0; k < s->n_cc; k++) d[k] = s->cc_H[k] - H_of_z(s, &c, s->cc_z[k]);
-    o->extra += f * f * quad_form(s->cc_inv_cov, d, s->n_cc);
+    /* cc_norm_sign < 0: f inflates the errors, chi2 * f ** -2 (ohd/cc_pantheon.py:63); otherwise f^2 * chi2 (ohd/cc.py:25) */
+    o->extra += (s->cc_norm_sign < 0.0 ? 1.0 / (f * f) : f * f) * quad_form(s->cc_inv_cov, d, s->n_cc);
     if (s->cc_norm_sign != 0.0)
       o->cc_norm = s->n_cc * log(2 * M_PI) + s->cc_logdet - s->cc_norm_sign * 2 * s->n_cc * log(f);
   }

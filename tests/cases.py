@@ -59,6 +59,20 @@ SPECS = {
     "ohd_cc_union3": lambda: fits.ohd_cc_union3(union3(), cc()),
     "bao_desi_omh2": lambda: fits.bao_desi_omh2(desi()),
     "bao_desi_union3_obh2_theta_star": lambda: fits.bao_desi_union3_obh2_theta_star(union3(), desi()),
+    "sn_pantheon_cmb": lambda: fits.sn_pantheon_cmb(pantheon()),
+    "sn_des5y_cmb": lambda: fits.sn_des5y_cmb(des()),
+    "sn_union3_1_cmb": lambda: fits.sn_union3_1_cmb(union3()),
+    "ohd_cc_cmb": lambda: fits.ohd_cc_cmb(cc()),
+    "ohd_cc_pantheon": lambda: fits.ohd_cc_pantheon(pantheon(), cc()),
+    "bao_desi_fs_lya": lambda: fits.bao_desi_fs_lya(desi_fs()),
+    "bao_desi_cc": lambda: fits.bao_desi_cc(desi(), cc()),
+    "bao_desi_des5y_rd": lambda: fits.bao_desi_des5y_rd(des(), desi()),
+    "bao_desi_union3_rd": lambda: fits.bao_desi_union3_rd(union3(), desi()),
+    "bao_desi_pantheon_rd": lambda: fits.bao_desi_pantheon_rd(pantheon(), desi()),
+    "bao_desi_bbn_theta_star": lambda: fits.bao_desi_bbn_theta_star(desi()),
+    "bao_desi_union3_bbn_theta_star": lambda: fits.bao_desi_union3_bbn_theta_star(union3(), desi_fs()),
+    "bao_desi_union3_cc_theta_star": lambda: fits.bao_desi_union3_cc_theta_star(union3(), desi(), cc()),
+    "bao_desi_des5y_cc_theta_star": lambda: fits.bao_desi_des5y_cc_theta_star(des(), desi(), cc()),
 }
 
 #: cases whose golden file has a plain chi2[n] for theta[n]
@@ -66,7 +80,16 @@ CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cm
               "bao_desi_des5y_bbn_theta_star", "bao_desi_cmb_pantheon", "bao_desi_cmb_des5y",
               "ohd_cc", "bao_desi_bbn", "bao_desi_pantheon_cc", "sn_pantheon_dipole_xyz",
               "sn_pantheon_and_sh0es", "bao_desi_cmb_pantheon_H0trgb", "bao_desi_cmb", "bao_desi_union3_obh2_theta_star",
-              "sn_pantheon_dipole", "ohd_cc_des5y", "ohd_cc_union3", "bao_desi_omh2"]
+              "sn_pantheon_dipole", "ohd_cc_des5y", "ohd_cc_union3", "bao_desi_omh2",
+              "sn_pantheon_cmb", "sn_des5y_cmb", "sn_union3_1_cmb", "ohd_cc_cmb", "ohd_cc_pantheon",
+              "bao_desi_fs_lya", "bao_desi_cc", "bao_desi_des5y_rd", "bao_desi_union3_rd", "bao_desi_pantheon_rd",
+              "bao_desi_bbn_theta_star", "bao_desi_union3_bbn_theta_star", "bao_desi_union3_cc_theta_star",
+              "bao_desi_des5y_cc_theta_star"]
+
+#: cases generated with the generic helper whose golden file also holds log_likelihood / log_probability rows
+GENERIC_LOGLIKE_CASES = ["ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_union3_cc_theta_star", "bao_desi_des5y_cc_theta_star"]
+GENERIC_LOGP_CASES = ["sn_pantheon_cmb", "ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_pantheon_rd",
+                      "bao_desi_des5y_cc_theta_star"]
 
 
 def spec(name):

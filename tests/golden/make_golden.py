@@ -442,14 +442,31 @@ def case_bao_desi_union3_obh2_theta_star():
     return dict(theta=theta, chi2=chi2, chi2_cmb=c_cmb, bounds=bounds, z_grid=ref.z_grid)
 
 
-def _generic(module, bounds, extra=lambda ref, theta: {}, n=24, loglike=False):
+def _stub_plotting(*names):
+    """Plot helpers some scripts import at module level (matplotlib is not installed; they are not on the path)."""
+    for name in names:
+        m = types.ModuleType(name)
+        m.plot_predictions = m.plot_cc_predictions = lambda *a, **k: None
+        sys.modules[name] = m
+
+
+def _generic(module, bounds, extra=lambda ref, theta: {}, n=24, loglike=False, logp=False):
     import importlib
     ref = importlib.import_module(module)
-    bounds = np.asarray(bounds, dtype=np.float64)
+    bounds = np.asarray(bounds if bounds is not None else ref.bounds, dtype=np.float64)
     theta = uniform_theta(bounds, n)
     out = dict(theta=theta, chi2=np.array([ref.chi_squared(t) for t in theta]), bounds=bounds)
     if loglike:
         out["loglike"] = np.array([ref.log_likelihood(t) for t in theta])
+    if logp:  # the script's own log_probability incl. rows outside its box prior (first / last parameter past a bound)
+        lo, hi = np.asarray(ref.bounds, dtype=np.float64).T
+        mid = 0.5 * (lo + hi)
+        o1, o2 = mid.copy(), mid.copy()
+        o1[0] = hi[0] + 0.1 * (hi[0] - lo[0]); o2[-1] = lo[-1] - 0.1 * (hi[-1] - lo[-1])
+        inside = uniform_theta(np.asarray(ref.bounds, dtype=np.float64), 6, seed=77)
+        tp = np.vstack([inside, o1, o2])
+        out["theta_logp"] = tp
+        out["logp"] = np.array([float(ref.log_probability(t)) for t in tp])
     for name in ("z_grid", "grid"):
         if hasattr(ref, name):
             out["z_grid"] = getattr(ref, name)
@@ -482,6 +499,100 @@ def case_bao_desi_omh2():
     """bao/desi_omh2.py: theta = (r_d, H0, omega_m, w0); Om = omega_m / h^2; thawing."""
     _enter_reference()
     return _generic("bao.desi_omh2", [(120, 160), (50.0, 85.0), (0.138, 0.148), (-1.0, -1 / 3)])
+
+
+def case_sn_pantheon_cmb():
+    """sn/pantheon_cmb.py: theta = (M, H0, obh2, och2, v); Pantheon+ + compressed CMB, box prior."""
+    _stub_pantheon()
+    _enter_reference()
+    return _generic("sn.pantheon_cmb", None, logp=True)
+
+
+def case_sn_des5y_cmb():
+    """sn/des5y_cmb.py: theta = (dM, H0, obh2, och2, v); DES-Dovekie + compressed CMB."""
+    _stub_des()
+    _enter_reference()
+    return _generic("sn.des5y_cmb", [(-0.7, 0.7), (55, 75), (0.01, 0.03), (0.01, 0.25), (-4.5, 4.5)])
+
+
+def case_sn_union3_1_cmb():
+    """sn/union3_1_cmb.py: theta = (dM, H0, obh2, och2, v); Union3.1 + compressed CMB."""
+    _enter_reference()
+    return _generic("sn.union3_1_cmb", [(-1.0, 1.0), (60.0, 75.0), (0.01, 0.03), (0.01, 0.25), (-9.0, 9.0)])
+
+
+def case_ohd_cc_cmb():
+    """ohd/cc_cmb.py: theta = (H0, obh2, och2, f_cc); CC + compressed CMB; log_prior = 0 inside the box."""
+    _enter_reference()
+    return _generic("ohd.cc_cmb", None, loglike=True, logp=True)
+
+
+def case_ohd_cc_pantheon():
+    """ohd/cc_pantheon.py: theta = (f_cc, H0, M, Om, w0); thawing; Pantheon+ + CC with f_cc inflating the errors."""
+    _stub_pantheon()
+    _stub_plotting("sn.plotting", "ohd.plot_predictions")
+    _enter_reference()
+    return _generic("ohd.cc_pantheon", None, loglike=True, logp=True)
+
+
+def case_bao_desi_fs_lya():
+    """bao/desi_fs_lya.py: theta = (h, Om, w0); thawing; FS+Lya table with F_AP rows; fixed r_d; pchip D_H."""
+    _enter_reference()
+    return _generic("bao.desi_fs_lya", [(0.5, 0.8), (0.1, 0.8), (-1.0, 0.0)])
+
+
+def case_bao_desi_cc():
+    """bao/desi_cc.py: theta = (f_cc, H0, r_d, Om, w0); BAO + cosmic chronometers."""
+    _enter_reference()
+    return _generic("bao.desi_cc", None, loglike=True, logp=True)
+
+
+def case_bao_desi_des5y_rd():
+    """bao/desi_des5y_rd.py: theta = (dM, r_d, H0, Om, v)."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_rd", [(-0.4, 0.4), (146.0, 148.2), (50.0, 85.0), (0.1, 0.6), (-4.5, 4.5)])
+
+
+def case_bao_desi_union3_rd():
+    """bao/desi_union3_rd.py: theta = (dM, r_d, H0, Om, v)."""
+    _enter_reference()
+    return _generic("bao.desi_union3_rd", [(-1.0, 1.0), (146.0, 148.2), (50.0, 85.0), (0.1, 0.6), (-8.0, 8.0)])
+
+
+def case_bao_desi_pantheon_rd():
+    """bao/desi_pantheon_rd.py: theta = (M, H0, Om, r_d, w0); Gaussian r_d prior inside log_prior."""
+    _stub_pantheon()
+    _enter_reference()
+    return _generic("bao.desi_pantheon_rd", None, logp=True)
+
+
+def case_bao_desi_bbn_theta_star():
+    """bao/desi_bbn_theta_star.py: theta = (H0, obh2, och2, w0); thawing; Planck PR3 constants; l_A-only term."""
+    _enter_reference()
+    return _generic("bao.desi_bbn_theta_star", [(50.0, 90.0), (0.019, 0.025), (0.05, 0.30), (-1.0, 0.0)])
+
+
+def case_bao_desi_union3_bbn_theta_star():
+    """bao/desi_union3_bbn_theta_star.py: theta = (dM, H0, obh2, och2, v); 15 BAO points incl. F_AP, exact D_H."""
+    _enter_reference()
+    return _generic("bao.desi_union3_bbn_theta_star", [(-1.0, 1.0), (50.0, 90.0), (0.019, 0.025), (0.05, 0.30), (-8.5, 8.5)])
+
+
+def case_bao_desi_union3_cc_theta_star():
+    """bao/desi_union3_cc_theta_star.py: theta = (f_cc, dM, H0, obh2, och2, v); float32 batch log_likelihood."""
+    _enter_reference()
+    def extra(ref, theta):
+        return dict(loglike=np.array([ref.log_likelihood_single(t) for t in theta]),
+                    loglike32=ref.log_likelihood(np.ascontiguousarray(theta)))
+    return _generic("bao.desi_union3_cc_theta_star", [(0.2, 3.0), (-1.0, 1.0), (50.0, 85.0), (0.003, 0.050), (0.05, 0.30), (-10.5, 4.5)], extra)
+
+
+def case_bao_desi_des5y_cc_theta_star():
+    """bao/desi_des5y_cc_theta_star.py: theta = (f_cc, dM, H0, obh2, och2, w0); thawing; box prior."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_cc_theta_star", None, loglike=True, logp=True)
 
 
 def case_interpolator():

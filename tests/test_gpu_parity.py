@@ -358,3 +358,21 @@ def test_full_size_linearity_property(engines):
     second = (cp - 2 * c0 + cm) / d**2
     assert np.all(np.isfinite(c0))
     assert np.max(np.abs(second - 2 * uu) / (2 * uu)) < 1e-6
+
+
+from cases import GENERIC_LOGLIKE_CASES, GENERIC_LOGP_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", GENERIC_LOGLIKE_CASES)
+def test_generic_log_likelihood(engines, name):
+    g = golden(name)
+    chi2_close(-2 * engines(name).log_likelihood(g["theta"]), -2 * g["loglike"])
+
+
+@pytest.mark.parametrize("name", GENERIC_LOGP_CASES)
+def test_generic_log_probability(engines, name):
+    g = golden(name)
+    lp = engines(name).log_probability(g["theta_logp"])
+    assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"])) and not np.isnan(lp).any()
+    fin = np.isfinite(g["logp"])
+    chi2_close(-2 * lp[fin], -2 * g["logp"][fin])

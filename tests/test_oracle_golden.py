@@ -134,3 +134,26 @@ def test_threads_do_not_change_results():
     g = golden("sn_pantheon")
     o = O.Oracle(spec("sn_pantheon"))
     assert np.array_equal(o.chi_squared(g["theta"], nthreads=1), o.chi_squared(g["theta"], nthreads=4))
+
+
+from cases import GENERIC_LOGLIKE_CASES, GENERIC_LOGP_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", GENERIC_LOGLIKE_CASES)
+def test_generic_log_likelihood(name):
+    """log_likelihood incl. the cosmic-chronometer normalisation term in both sign conventions (ohd/cc.py:33,
+    ohd/cc_pantheon.py:92)."""
+    import oracle.oracle as O
+    g = golden(name)
+    assert np.max(np.abs(O.Oracle(spec(name)).log_likelihood(g["theta"]) - g["loglike"])) < CHI2_ATOL
+
+
+@pytest.mark.parametrize("name", GENERIC_LOGP_CASES)
+def test_generic_log_probability(name):
+    """The script's own log_probability: box prior (-inf rows are never evaluated) + its normalisation constant."""
+    import oracle.oracle as O
+    g = golden(name)
+    lp = O.Oracle(spec(name)).log_probability(g["theta_logp"])
+    assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"])) and np.isneginf(g["logp"]).sum() == 2
+    fin = np.isfinite(g["logp"])
+    assert np.max(np.abs(lp[fin] - g["logp"][fin])) < CHI2_ATOL
