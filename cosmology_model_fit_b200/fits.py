@@ -387,6 +387,68 @@ def bao_desi_pantheon_rd(sn, desi):
     return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=3)
 
 
+def _sn_bao_omh2(sn, desi, form, z_turn):
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=2, col_Om=3, Om_is_physical=True,
+                        z_grid=_grid(sn[0], desi[0]), gauss_prior=((3, 0.1430, 0.0011),))  # nautilus prior on omega_m (:117 / :132)
+    _sn_block(sp, sn, form, z_turn, 0, 4)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=1)
+
+
+def bao_desi_union3_omh2(sn, desi):
+    """bao/desi_union3_omh2.py: theta = (dM, r_d, H0, omega_m, v); late LCDM with Om = omega_m / h^2; Union3.1 (step at 0.2)."""
+    return _sn_bao_omh2(sn, desi, S.SN_INVCOV, 0.2)
+
+
+def bao_desi_des5y_omh2(sn, desi):
+    """bao/desi_des5y_omh2.py: theta = (dM, r_d, H0, omega_m, v); late LCDM with Om = omega_m / h^2; DES-Dovekie (step at 0.10563)."""
+    return _sn_bao_omh2(sn, desi, S.SN_CHOLESKY, 0.10563)
+
+
+def _sub_weight(matrix, rows, invert):
+    """3x3 CMB weight from a row/column sub-selection: the inverse of the sub-covariance (invert=True; bao/
+    desi_union3_omh2_theta_star.py:17) or the sub-block of the full inverse (bao/desi_des5y_obh2_theta_star.py:104)."""
+    w = np.zeros((3, 3))
+    sub = np.asarray(matrix)[np.ix_(rows, rows)]
+    w[np.ix_(rows, rows)] = np.linalg.inv(sub) if invert else sub
+    return w
+
+
+def bao_desi_union3_omh2_theta_star(sn, desi, consts=None):
+    """bao/desi_union3_omh2_theta_star.py: theta = (dM, H0, obh2, och2, v); full LCDM; early-LCDM compression rows
+    (theta*, omega_m) with the inverse of their 2x2 sub-covariance; Union3.1 (step at 0.2); exact D_H."""
+    consts = consts or S.cmb_early_lcdm()
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, cmb_weight=_sub_weight(consts.covariance, [0, 2], True),
+                        z_grid=_grid(sn[0], desi[0]))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 0, 4)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_pantheon_obh2_theta_star(sn, desi, consts=None):
+    """bao/desi_pantheon_obh2_theta_star.py: theta = (M, H0, obh2, och2, w0); full thawing; early-LCDM rows (theta*, omega_b);
+    Pantheon+ (Cholesky, no velocity term); exact D_H; box prior."""
+    consts = consts or S.cmb_early_lcdm()
+    bounds = np.array([(-20.0, -19.0), (50.0, 90.0), (0.0, 0.05), (0.05, 0.30), (-1.0, -1 / 3)])  # :108-116
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_THAWING, col_H0=1, col_obh2=2, col_och2=3, col_w0=4,
+                        cmb_consts=consts, cmb_mode=consts.mode, cmb_weight=_sub_weight(consts.covariance, [0, 1], True),
+                        z_grid=_grid(sn[0], desi[0]), bounds=bounds)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_des5y_obh2_theta_star(sn, desi, consts=None):
+    """bao/desi_des5y_obh2_theta_star.py: theta = (dM, H0, obh2, och2, w0); full thawing; Planck+ACT rows (l_A, omega_b)
+    weighted by the SUB-BLOCK of the full inverse covariance (:104); DES-Dovekie (Cholesky, no velocity term); box prior."""
+    consts = consts or S.cmb_planck_act()
+    bounds = np.array([(-0.4, 0.4), (50.0, 90.0), (0.010, 0.030), (0.05, 0.30), (-1.0, -1 / 3)])  # :110-118
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_THAWING, col_H0=1, col_obh2=2, col_och2=3, col_w0=4,
+                        cmb_consts=consts, cmb_mode=S.CMB_R_LA_WB,
+                        cmb_weight=_sub_weight(np.linalg.inv(consts.covariance), [1, 2], False),
+                        z_grid=_grid(sn[0], desi[0]), bounds=bounds)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
 def bao_desi_omh2(desi):
     """bao/desi_omh2.py: theta = (r_d, H0, omega_m, w0); late thawing with Om = omega_m / h^2; r_d sampled; exact D_H."""
     sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=2, Om_is_physical=True, col_w0=3,

@@ -73,6 +73,11 @@ SPECS = {
     "bao_desi_union3_bbn_theta_star": lambda: fits.bao_desi_union3_bbn_theta_star(union3(), desi_fs()),
     "bao_desi_union3_cc_theta_star": lambda: fits.bao_desi_union3_cc_theta_star(union3(), desi(), cc()),
     "bao_desi_des5y_cc_theta_star": lambda: fits.bao_desi_des5y_cc_theta_star(des(), desi(), cc()),
+    "bao_desi_union3_omh2": lambda: fits.bao_desi_union3_omh2(union3(), desi()),
+    "bao_desi_des5y_omh2": lambda: fits.bao_desi_des5y_omh2(des(), desi()),
+    "bao_desi_union3_omh2_theta_star": lambda: fits.bao_desi_union3_omh2_theta_star(union3(), desi()),
+    "bao_desi_pantheon_obh2_theta_star": lambda: fits.bao_desi_pantheon_obh2_theta_star(pantheon(), desi()),
+    "bao_desi_des5y_obh2_theta_star": lambda: fits.bao_desi_des5y_obh2_theta_star(des(), desi()),
 }
 
 #: cases whose golden file has a plain chi2[n] for theta[n]
@@ -84,12 +89,13 @@ CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cm
               "sn_pantheon_cmb", "sn_des5y_cmb", "sn_union3_1_cmb", "ohd_cc_cmb", "ohd_cc_pantheon",
               "bao_desi_fs_lya", "bao_desi_cc", "bao_desi_des5y_rd", "bao_desi_union3_rd", "bao_desi_pantheon_rd",
               "bao_desi_bbn_theta_star", "bao_desi_union3_bbn_theta_star", "bao_desi_union3_cc_theta_star",
-              "bao_desi_des5y_cc_theta_star"]
+              "bao_desi_des5y_cc_theta_star", "bao_desi_union3_omh2", "bao_desi_des5y_omh2", "bao_desi_union3_omh2_theta_star",
+              "bao_desi_pantheon_obh2_theta_star", "bao_desi_des5y_obh2_theta_star"]
 
 #: cases generated with the generic helper whose golden file also holds log_likelihood / log_probability rows
 GENERIC_LOGLIKE_CASES = ["ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_union3_cc_theta_star", "bao_desi_des5y_cc_theta_star"]
 GENERIC_LOGP_CASES = ["sn_pantheon_cmb", "ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_pantheon_rd",
-                      "bao_desi_des5y_cc_theta_star"]
+                      "bao_desi_des5y_cc_theta_star", "bao_desi_pantheon_obh2_theta_star", "bao_desi_des5y_obh2_theta_star"]
 
 
 def spec(name):

@@ -595,6 +595,39 @@ def case_bao_desi_des5y_cc_theta_star():
     return _generic("bao.desi_des5y_cc_theta_star", None, loglike=True, logp=True)
 
 
+def case_bao_desi_union3_omh2():
+    """bao/desi_union3_omh2.py: theta = (dM, r_d, H0, omega_m, v)."""
+    _enter_reference()
+    return _generic("bao.desi_union3_omh2", [(-1.0, 1.0), (120, 160), (50.0, 85.0), (0.138, 0.148), (-12.0, 5.0)])
+
+
+def case_bao_desi_des5y_omh2():
+    """bao/desi_des5y_omh2.py: theta = (dM, r_d, H0, omega_m, v)."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_omh2", [(-0.5, 0.5), (120.0, 165.0), (50.0, 90.0), (0.138, 0.148), (-5.5, 2.5)])
+
+
+def case_bao_desi_union3_omh2_theta_star():
+    """bao/desi_union3_omh2_theta_star.py: early-LCDM rows (theta*, omega_m), inverse of the sub-covariance."""
+    _enter_reference()
+    return _generic("bao.desi_union3_omh2_theta_star", [(-1.0, 1.0), (50.0, 90.0), (0.01, 0.04), (0.05, 0.3), (-8.5, 8.5)])
+
+
+def case_bao_desi_pantheon_obh2_theta_star():
+    """bao/desi_pantheon_obh2_theta_star.py: early-LCDM rows (theta*, omega_b); thawing; box prior."""
+    _stub_pantheon()
+    _enter_reference()
+    return _generic("bao.desi_pantheon_obh2_theta_star", None, logp=True)
+
+
+def case_bao_desi_des5y_obh2_theta_star():
+    """bao/desi_des5y_obh2_theta_star.py: Planck+ACT rows (l_A, omega_b) with the sub-block of the full inverse."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_obh2_theta_star", None, logp=True)
+
+
 def case_interpolator():
     """interpolator.py known answers on non-uniform and monotone/non-monotone data (pchip + hermite)."""
     _enter_reference()
