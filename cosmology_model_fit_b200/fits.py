@@ -449,6 +449,76 @@ def bao_desi_des5y_obh2_theta_star(sn, desi, consts=None):
     return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
 
 
+def bao_desi_union3_bbn(sn, desi, des_y6=DES_Y6_BAO):
+    """bao/desi_union3_bbn.py: theta = (H0, Om, obh2, v, dM); late LCDM; DESI + DES-Y6 BAO (14 points, exact D_H) with the
+    r_drag fit written out in the script; Union3.1 (inv_cov, step at 0.2); BBN prior on omega_b (:154)."""
+    bao = concat_bao(desi, des_y6)
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=0, col_Om=1, col_obh2=2,
+                        cmb_consts=S.cmb_rdrag_plain(), z_grid=_grid(sn[0], bao[0]), gauss_prior=((2, *BBN_SCHONEBERG),))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 4, 3)
+    return _bao_block(sp, bao, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_des5y_bbn(sn, desi):
+    """bao/desi_des5y_bbn.py: theta = (H0, Om, obh2, w0, dM); late thawing; DESI BAO through its Cholesky factor (:17; the
+    same quadratic form as inv_cov), exact D_H, in-script r_drag fit; DES-Dovekie (Cholesky, no velocity term); BBN prior."""
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=0, col_Om=1, col_obh2=2, col_w0=3,
+                        cmb_consts=S.cmb_rdrag_plain(), z_grid=_grid(sn[0], desi[0]), gauss_prior=((2, *BBN_SCHONEBERG),))
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 4, None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_des5y_H0trgb(sn, desi):
+    """bao/desi_des5y_H0trgb.py: theta = (dM, H0, r_d, Om, w0); late thawing; sampled r_d; exact D_H; DES-Dovekie (Cholesky, no
+    velocity term); box prior with the TRGB H0 Gaussian inside log_prior (:96-101)."""
+    bounds = np.array([(-0.5, 0.5), (56.0, 85.0), (120.0, 160.0), (0.1, 0.7), (-1.0, -1 / 3)])  # :84-92
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=3, col_w0=4,
+                        z_grid=_grid(sn[0], desi[0]), bounds=bounds, gauss_prior=((1, *H0_TRGB),))
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.0, 0, None)
+    return _bao_block(sp, desi, S.DH_EXACT, S.RD_PARAM, col_rd=2)
+
+
+def _cmb_sn_bao_H0trgb(sn, desi, form, z_turn, consts, sixdf):
+    consts = consts or S.cmb_planck_act()
+    bao = concat_bao(desi, sixdf)   # the 6dF point has its own chi2 term in the script: block-diagonal covariance
+    sp = LikelihoodSpec(ndim=5, family=S.FAMILY_FULL, de_model=S.DE_LCDM, col_H0=1, col_obh2=2, col_och2=3,
+                        cmb_consts=consts, cmb_mode=consts.mode, z_grid=_grid(sn[0], desi[0]), gauss_chi2=((1, *H0_TRGB),))
+    _sn_block(sp, sn, form, z_turn, 0, 4)
+    return _bao_block(sp, bao, S.DH_EXACT, S.RD_FIT)
+
+
+def bao_desi_cmb_des5y_H0trgb(sn, desi, consts=None, sixdf=SIXDF_BAO):
+    """bao/desi_cmb_des5y_H0trgb.py: theta = (dM, H0, obh2, och2, v); full LCDM; DES-Dovekie (Cholesky, step at 0.11) + DESI +
+    6dF (separate chi2 term) + CMB 3x3 + TRGB H0 chi2 term (:150)."""
+    return _cmb_sn_bao_H0trgb(sn, desi, S.SN_CHOLESKY, 0.11, consts, sixdf)
+
+
+def bao_desi_cmb_union3_H0trgb(sn, desi, consts=None, sixdf=SIXDF_BAO):
+    """bao/desi_cmb_union3_H0trgb.py: theta = (dM, H0, obh2, och2, v); full LCDM; Union3.1 (inv_cov, step at 0.2) + DESI + 6dF +
+    CMB 3x3 + TRGB H0 chi2 term."""
+    return _cmb_sn_bao_H0trgb(sn, desi, S.SN_INVCOV, 0.2, consts, sixdf)
+
+
+def bao_desi_des5y_cc(sn, desi_fs_lya, cc):
+    """bao/desi_des5y_cc.py: theta = (f_cc, dM, H0, r_d, Om, v); late LCDM; DES-Dovekie (Cholesky, step at 0.10563) + DESI FS-Lya
+    (exact D_H, F_AP rows) + CC through its Cholesky factor with f^2 and the normalisation; box prior."""
+    bounds = np.array([(0.5, 2.5), (-0.55, 0.55), (50.0, 80.0), (110.0, 175.0), (0.2, 0.7), (-4.5, 4.5)])  # :108-117
+    sp = LikelihoodSpec(ndim=6, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=2, col_Om=4, z_grid=_grid(sn[0], desi_fs_lya[0]),
+                        bounds=bounds)
+    _sn_block(sp, sn, S.SN_CHOLESKY, 0.10563, 1, 5)
+    _cc_block(sp, cc, 0)
+    return _bao_block(sp, desi_fs_lya, S.DH_EXACT, S.RD_PARAM, col_rd=3)
+
+
+def bao_desi_fs_lya_union3_cc(sn, desi_fs_lya, cc):
+    """bao/desi_fs_lya_union3_cc.py: theta = (f_cc, dM, H0, r_d, Om, v); late LCDM; Union3.1 (inv_cov, step at 0.2) + DESI FS-Lya
+    (exact D_H, F_AP rows) + CC (f^2 inv_cov) with the normalisation."""
+    sp = LikelihoodSpec(ndim=6, family=S.FAMILY_LATE, de_model=S.DE_LCDM, col_H0=2, col_Om=4, z_grid=_grid(sn[0], desi_fs_lya[0]))
+    _sn_block(sp, sn, S.SN_INVCOV, 0.2, 1, 5)
+    _cc_block(sp, cc, 0)
+    return _bao_block(sp, desi_fs_lya, S.DH_EXACT, S.RD_PARAM, col_rd=3)
+
+
 def bao_desi_omh2(desi):
     """bao/desi_omh2.py: theta = (r_d, H0, omega_m, w0); late thawing with Om = omega_m / h^2; r_d sampled; exact D_H."""
     sp = LikelihoodSpec(ndim=4, family=S.FAMILY_LATE, de_model=S.DE_THAWING, col_H0=1, col_Om=2, Om_is_physical=True, col_w0=3,

@@ -205,6 +205,15 @@ def cmb_early_lcdm():
         (1.00329735, 0.99968141, 1.00232108, 0.9893333), cov_scale=1e-9)
 
 
+def cmb_rdrag_plain():
+    """The r_drag fit written out inside bao/desi_union3_bbn.py:31-45 and bao/desi_des5y_bbn.py:22-42 (arXiv:2106.00428 eq. 8
+    without the per-module rescaling exponents of cmb/data_*_compression.py): omega_b ** 1, omega_m ** 1."""
+    k = cmb_planck()
+    k.name = "rdrag_plain"
+    k.rdrag = (1.0, 1.0)
+    return k
+
+
 CMB_MODULES = {"planck_act": cmb_planck_act, "act": cmb_act, "planck": cmb_planck, "planck_lens": cmb_planck_lens,
                "early_lcdm": cmb_early_lcdm}
 

@@ -78,6 +78,13 @@ SPECS = {
     "bao_desi_union3_omh2_theta_star": lambda: fits.bao_desi_union3_omh2_theta_star(union3(), desi()),
     "bao_desi_pantheon_obh2_theta_star": lambda: fits.bao_desi_pantheon_obh2_theta_star(pantheon(), desi()),
     "bao_desi_des5y_obh2_theta_star": lambda: fits.bao_desi_des5y_obh2_theta_star(des(), desi()),
+    "bao_desi_union3_bbn": lambda: fits.bao_desi_union3_bbn(union3(), desi()),
+    "bao_desi_des5y_bbn": lambda: fits.bao_desi_des5y_bbn(des(), desi()),
+    "bao_desi_des5y_H0trgb": lambda: fits.bao_desi_des5y_H0trgb(des(), desi()),
+    "bao_desi_cmb_des5y_H0trgb": lambda: fits.bao_desi_cmb_des5y_H0trgb(des(), desi()),
+    "bao_desi_cmb_union3_H0trgb": lambda: fits.bao_desi_cmb_union3_H0trgb(union3(), desi()),
+    "bao_desi_des5y_cc": lambda: fits.bao_desi_des5y_cc(des(), desi_fs(), cc()),
+    "bao_desi_fs_lya_union3_cc": lambda: fits.bao_desi_fs_lya_union3_cc(union3(), desi_fs(), cc()),
 }
 
 #: cases whose golden file has a plain chi2[n] for theta[n]
@@ -90,12 +97,16 @@ CHI2_CASES = ["sn_pantheon", "sn_union3_1", "sn_des5y", "bao_desi", "bao_desi_cm
               "bao_desi_fs_lya", "bao_desi_cc", "bao_desi_des5y_rd", "bao_desi_union3_rd", "bao_desi_pantheon_rd",
               "bao_desi_bbn_theta_star", "bao_desi_union3_bbn_theta_star", "bao_desi_union3_cc_theta_star",
               "bao_desi_des5y_cc_theta_star", "bao_desi_union3_omh2", "bao_desi_des5y_omh2", "bao_desi_union3_omh2_theta_star",
-              "bao_desi_pantheon_obh2_theta_star", "bao_desi_des5y_obh2_theta_star"]
+              "bao_desi_pantheon_obh2_theta_star", "bao_desi_des5y_obh2_theta_star",
+              "bao_desi_union3_bbn", "bao_desi_des5y_bbn", "bao_desi_des5y_H0trgb", "bao_desi_cmb_des5y_H0trgb",
+              "bao_desi_cmb_union3_H0trgb", "bao_desi_des5y_cc", "bao_desi_fs_lya_union3_cc"]
 
 #: cases generated with the generic helper whose golden file also holds log_likelihood / log_probability rows
-GENERIC_LOGLIKE_CASES = ["ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_union3_cc_theta_star", "bao_desi_des5y_cc_theta_star"]
+GENERIC_LOGLIKE_CASES = ["ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_union3_cc_theta_star", "bao_desi_des5y_cc_theta_star",
+                         "bao_desi_des5y_cc", "bao_desi_fs_lya_union3_cc"]
 GENERIC_LOGP_CASES = ["sn_pantheon_cmb", "ohd_cc_cmb", "ohd_cc_pantheon", "bao_desi_cc", "bao_desi_pantheon_rd",
-                      "bao_desi_des5y_cc_theta_star", "bao_desi_pantheon_obh2_theta_star", "bao_desi_des5y_obh2_theta_star"]
+                      "bao_desi_des5y_cc_theta_star", "bao_desi_pantheon_obh2_theta_star", "bao_desi_des5y_obh2_theta_star",
+                      "bao_desi_des5y_H0trgb", "bao_desi_des5y_cc"]
 
 
 def spec(name):

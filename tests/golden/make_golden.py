@@ -628,6 +628,52 @@ def case_bao_desi_des5y_obh2_theta_star():
     return _generic("bao.desi_des5y_obh2_theta_star", None, logp=True)
 
 
+def case_bao_desi_union3_bbn():
+    """bao/desi_union3_bbn.py: theta = (H0, Om, obh2, v, dM); r_drag fit written out in the script."""
+    _enter_reference()
+    return _generic("bao.desi_union3_bbn", [(55, 80), (0.10, 0.65), (0.019, 0.025), (-12.0, 5.0), (-1.0, 1.0)])
+
+
+def case_bao_desi_des5y_bbn():
+    """bao/desi_des5y_bbn.py: theta = (H0, Om, obh2, w0, dM); BAO chi2 through the Cholesky factor."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_bbn", [(55, 80), (0.10, 0.65), (0.019, 0.025), (-1.0, -1 / 3), (-0.5, 0.5)])
+
+
+def case_bao_desi_des5y_H0trgb():
+    """bao/desi_des5y_H0trgb.py: theta = (dM, H0, r_d, Om, w0); TRGB H0 Gaussian inside log_prior."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_H0trgb", None, logp=True)
+
+
+def case_bao_desi_cmb_des5y_H0trgb():
+    """bao/desi_cmb_des5y_H0trgb.py: theta = (dM, H0, obh2, och2, v); separate 6dF term, TRGB H0 term in chi2."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_cmb_des5y_H0trgb", [(-0.5, 0.5), (60.0, 75.0), (0.010, 0.030), (0.01, 0.25), (-6.0, 2.0)])
+
+
+def case_bao_desi_cmb_union3_H0trgb():
+    """bao/desi_cmb_union3_H0trgb.py: theta = (dM, H0, obh2, och2, v)."""
+    _enter_reference()
+    return _generic("bao.desi_cmb_union3_H0trgb", [(-1.0, 1.0), (60.0, 75.0), (0.010, 0.030), (0.01, 0.25), (-9.5, 3.5)])
+
+
+def case_bao_desi_des5y_cc():
+    """bao/desi_des5y_cc.py: theta = (f_cc, dM, H0, r_d, Om, v); box prior."""
+    _stub_des()
+    _enter_reference()
+    return _generic("bao.desi_des5y_cc", None, loglike=True, logp=True)
+
+
+def case_bao_desi_fs_lya_union3_cc():
+    """bao/desi_fs_lya_union3_cc.py: theta = (f_cc, dM, H0, r_d, Om, v)."""
+    _enter_reference()
+    return _generic("bao.desi_fs_lya_union3_cc", [(0.01, 3.0), (-1, 1), (45, 90), (100, 200), (0.2, 0.50), (-8.5, 8.5)], loglike=True)
+
+
 def case_interpolator():
     """interpolator.py known answers on non-uniform and monotone/non-monotone data (pchip + hermite)."""
     _enter_reference()
