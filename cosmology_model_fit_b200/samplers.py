@@ -109,3 +109,124 @@ def laplace_log_evidence(log_prob_fn, theta_map, step=1e-4, scales=None):
     if sign <= 0:
         raise ValueError("Hessian is not negative definite at theta_map")
     return float(lp[0] + 0.5 * d * np.log(2 * np.pi) - 0.5 * logdet), H
+
+
+class BoxPrior:
+    """Independent priors as the reference's nautilus scripts declare them (`prior.add_parameter(name, dist=(lo, hi))` or
+    `dist=norm(loc, scale)`, e.g. bao/desi_bbn_theta_star.py:117-120): uniform on [lo, hi] per column, optionally Gaussian
+    on some columns.  `transform` maps the unit cube to theta."""
+
+    def __init__(self, bounds, gauss=None):
+        self.bounds = np.asarray(bounds, dtype=np.float64)
+        self.ndim = self.bounds.shape[0]
+        self.gauss = dict(gauss or {})
+
+    def transform(self, u):
+        from scipy.special import ndtri
+        lo, hi = self.bounds[:, 0], self.bounds[:, 1]
+        theta = lo + np.asarray(u, dtype=np.float64) * (hi - lo)
+        for col, (mean, sigma) in self.gauss.items():
+            theta[:, col] = mean + sigma * ndtri(np.clip(u[:, col], 1e-300, 1.0 - 1e-16))
+        return theta
+
+
+class NestedSampler:
+    """Batched nested sampling sized for the GPU likelihood (the reference drives nautilus,
+    `bao/desi_cmb_pantheon.py:154-170`, whose stock batches are ~100 points).
+
+    Static nested sampling with `n_replace` deletions per iteration: the worst K live points are removed one at a time
+    (live count n, n-1, ..., n-K+1, so ln X shrinks by 1/n, 1/(n-1), ...), then K replacements are drawn uniformly from
+    the prior region above the K-th threshold.  Replacements come from rejection sampling inside one bounding ellipsoid
+    of the live points in the unit cube (enlarged; enough for the unimodal posteriors of these fits) and every likelihood
+    call evaluates `batch` (>= 65536 by default) proposals at once; accepted proposals are used in the order drawn.
+    The same seed with the CPU oracle or the CUDA engine as `log_like_fn` follows the same path up to accept/reject flips
+    at the 1e-9 level."""
+
+    def __init__(self, prior, log_like_fn, n_live=2000, n_replace=None, batch=65536, enlarge=1.3, seed=0, min_batch=1024):
+        self.prior, self.log_like_fn = prior, log_like_fn
+        self.ndim = prior.ndim
+        self.n_live = int(n_live)
+        self.n_replace = int(n_replace or max(1, n_live // 5))
+        if not 1 <= self.n_replace < self.n_live:
+            raise ValueError("n_replace must be in [1, n_live)")
+        self.batch, self.enlarge, self.min_batch = int(batch), float(enlarge), int(min_batch)
+        self._acc = 0.5       # running estimate of the acceptance of ellipsoid proposals
+        self.rng = np.random.default_rng(seed)
+        self.n_calls = 0      # likelihood calls (batches)
+        self.n_evals = 0      # likelihood evaluations (rows)
+
+    def _ll(self, u):
+        theta = np.ascontiguousarray(self.prior.transform(u))
+        self.n_calls += 1
+        self.n_evals += len(theta)
+        ll = np.asarray(self.log_like_fn(theta), dtype=np.float64)
+        if np.isnan(ll).any():
+            raise ValueError("log_like_fn returned NaN")
+        return theta, ll
+
+    def _ellipsoid(self, u_live):
+        """Bounding ellipsoid of the live points: mean, Cholesky factor of the covariance scaled to contain all of them."""
+        mu = u_live.mean(0)
+        cov = np.cov(u_live, rowvar=False).reshape(self.ndim, self.ndim) + 1e-18 * np.eye(self.ndim)
+        L = np.linalg.cholesky(cov)
+        d = np.linalg.solve(L, (u_live - mu).T)
+        r2 = float(np.max(np.sum(d * d, axis=0)))
+        return mu, L * np.sqrt(r2) * self.enlarge ** (1.0 / self.ndim)
+
+    def _draw(self, mu, L, n):
+        z = self.rng.standard_normal((n, self.ndim))
+        z *= (self.rng.random(n) ** (1.0 / self.ndim) / np.linalg.norm(z, axis=1))[:, None]   # uniform in the unit ball
+        u = mu + z @ L.T
+        return u[np.all((u > 0.0) & (u < 1.0), axis=1)]
+
+    def run(self, dlogz=0.01, max_iter=100000):
+        n, K, d = self.n_live, self.n_replace, self.ndim
+        u = self.rng.random((n, d))
+        theta, ll = self._ll(u)
+        log_x = 0.0                       # ln of the enclosed prior volume
+        logz = -np.inf
+        h_num = 0.0                       # sum of w_i L_i ln L_i for the information H
+        dead_theta, dead_logw, dead_ll = [], [], []
+        # ln(X_{i-1} - X_i) for one deletion at live count m: ln X_{i-1} + ln(1 - exp(-1/m))
+        for it in range(max_iter):
+            order = np.argsort(ll, kind="stable")
+            worst = order[:K]
+            for j, idx in enumerate(worst):
+                m = n - j
+                logw = log_x + np.log1p(-np.exp(-1.0 / m)) + ll[idx]
+                dead_theta.append(theta[idx]); dead_logw.append(logw); dead_ll.append(ll[idx])
+                logz = np.logaddexp(logz, logw)
+                log_x -= 1.0 / m
+            thresh = ll[worst[-1]]
+            keep = order[K:]
+            mu, L = self._ellipsoid(u[keep])
+            new_u, new_theta, new_ll = [], [], []
+            need = K
+            while need > 0:
+                # enough proposals for the points still needed at the acceptance seen so far, never more than `batch`
+                n_prop = int(min(self.batch, max(self.min_batch, 1.2 * need / max(self._acc, 1e-4))))
+                cand = self._draw(mu, L, n_prop)
+                if len(cand) == 0:
+                    continue
+                th_c, ll_c = self._ll(cand)
+                good = np.flatnonzero(ll_c > thresh)
+                self._acc = 0.5 * self._acc + 0.5 * max(len(good), 1) / n_prop
+                ok = good[:need]
+                new_u.append(cand[ok]); new_theta.append(th_c[ok]); new_ll.append(ll_c[ok])
+                need -= len(ok)
+            u = np.vstack([u[keep]] + new_u)
+            theta = np.vstack([theta[keep]] + new_theta)
+            ll = np.concatenate([ll[keep]] + new_ll)
+            # remaining evidence bounded by max(L_live) X
+            if np.max(ll) + log_x < logz + np.log(dlogz):
+                break
+        # the live points share the remaining volume
+        logw_live = log_x - np.log(n) + ll
+        logz = np.logaddexp(logz, np.logaddexp.reduce(logw_live))
+        all_theta = np.vstack([np.array(dead_theta), theta])
+        all_logw = np.concatenate([np.array(dead_logw), logw_live])
+        all_ll = np.concatenate([np.array(dead_ll), ll])
+        w = np.exp(all_logw - logz)
+        info = float(np.sum(w * all_ll) - logz)            # H = int P ln(L/Z)
+        return {"logz": float(logz), "logz_err": float(np.sqrt(max(info, 0.0) / n)), "information": info, "n_iter": it + 1,
+                "n_calls": self.n_calls, "n_evals": self.n_evals, "samples": all_theta, "weights": w, "log_like": all_ll}

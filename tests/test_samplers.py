@@ -3,7 +3,7 @@ CPU oracle with the same seed it gives posterior means that agree within Monte C
 import numpy as np
 import pytest
 
-from cosmology_model_fit_b200.samplers import EnsembleSampler, laplace_log_evidence
+from cosmology_model_fit_b200.samplers import BoxPrior, NestedSampler, EnsembleSampler, laplace_log_evidence
 
 
 def test_recovers_gaussian_posterior():
@@ -52,3 +52,59 @@ def test_config0_posterior_means_gpu_vs_oracle():
     # the chains are in fact identical until an accept/reject decision flips at the 1e-9 level
     same = np.all(s_gpu.chain == s_cpu.chain, axis=(1, 2))
     assert same[:20].all()
+
+
+def test_nested_sampler_gaussian_evidence():
+    """Correlated 4-d Gaussian well inside its prior box: ln Z = -ln(box volume); posterior mean recovered; one Gaussian-prior
+    column handled through the unit-cube transform."""
+    d = 4
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((d, d))
+    C = A @ A.T * 0.01 + 0.02 * np.eye(d)
+    Ci = np.linalg.inv(C)
+    mu = np.array([0.3, -0.2, 0.1, 0.5])
+    norm = -0.5 * (d * np.log(2 * np.pi) + np.linalg.slogdet(C)[1])
+
+    def ll(t):
+        r = t - mu
+        return norm - 0.5 * np.einsum("ij,jk,ik->i", r, Ci, r)
+
+    bounds = np.array([(-3.0, 3.0)] * d)
+    ns = NestedSampler(BoxPrior(bounds), ll, n_live=1000, n_replace=200, batch=16384, seed=5)
+    res = ns.run(dlogz=0.01)
+    want = -np.sum(np.log(bounds[:, 1] - bounds[:, 0]))
+    assert abs(res["logz"] - want) < 4 * res["logz_err"] + 0.02, (res["logz"], want, res["logz_err"])
+    mean = (res["weights"][:, None] * res["samples"]).sum(0)
+    assert np.all(np.abs(mean - mu) < 0.02)
+    assert abs(res["weights"].sum() - 1.0) < 1e-9
+    # Gaussian prior on column 0 (scipy.stats.norm in the reference's nautilus priors): Z = int N(x0; m, s) L dx
+    pr = BoxPrior(bounds, gauss={0: (0.25, 0.2)})
+    res2 = NestedSampler(pr, ll, n_live=1000, n_replace=200, batch=16384, seed=6).run(dlogz=0.01)
+    # analytic: marginal of the likelihood in x0 is N(mu0, C00) (other columns integrate against 1/6 each)
+    s2 = C[0, 0] + 0.2**2
+    want2 = -0.5 * np.log(2 * np.pi * s2) - 0.5 * (mu[0] - 0.25) ** 2 / s2 - 3 * np.log(6.0)
+    assert abs(res2["logz"] - want2) < 4 * res2["logz_err"] + 0.02, (res2["logz"], want2)
+
+
+@pytest.mark.gpu
+def test_nested_sampling_gpu_vs_oracle_and_laplace():
+    """Config 3 shape at small scale (sn/union3_1.py likelihood, 22 SNe: the oracle is fast): same seed, CUDA engine vs CPU
+    oracle as the likelihood -> same evidence; and the evidence agrees with the Laplace approximation around the mode."""
+    import oracle.oracle as O
+    from cases import spec
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.samplers import laplace_log_evidence
+    sp = spec("sn_union3_1")
+    bounds = np.array([(-0.5, 0.5), (0.1, 0.6), (-8.0, 4.0)])
+    prior = BoxPrior(bounds)
+    orc = O.Oracle(sp)
+    with Engine(sp) as eng:
+        r_gpu = NestedSampler(prior, eng.log_likelihood, n_live=600, n_replace=150, batch=65536, seed=11).run(dlogz=0.05)
+        r_cpu = NestedSampler(prior, lambda th: orc.log_likelihood(th, nthreads=0), n_live=600, n_replace=150, batch=65536, seed=11).run(dlogz=0.05)
+        assert abs(r_gpu["logz"] - r_cpu["logz"]) < 1e-6 or abs(r_gpu["logz"] - r_cpu["logz"]) < 3 * r_cpu["logz_err"]
+        assert r_gpu["n_iter"] == r_cpu["n_iter"]
+        # Laplace: ln Z ~ ln L_max + d/2 ln 2pi - 1/2 ln det(-H) - ln(prior volume)
+        best = r_gpu["samples"][np.argmax(r_gpu["log_like"])]
+        lz, _ = laplace_log_evidence(eng.log_likelihood, best, step=1e-3, scales=np.array([0.05, 0.05, 1.0]))
+        lz -= np.sum(np.log(bounds[:, 1] - bounds[:, 0]))
+    assert abs(r_gpu["logz"] - lz) < 0.35 + 3 * r_gpu["logz_err"], (r_gpu["logz"], lz, r_gpu["logz_err"])
