@@ -133,17 +133,17 @@ __device__ __forceinline__ double E2_of_zp1(const DevSpec& s, const Cosmo& c, do
 // expensive pieces out of the 4000-node loop: ln(1+z_i) turns the wCDM / CPL power into one exp (instead of pow + exp +
 // a division), and Omnu_z(z_i) replaces five square roots per node in the FULL family.
 template <int FAM, int DE>
-__device__ __forceinline__ double E2_at_node(const DevSpec& s, const Cosmo& c, int i, double zp1) {
+__device__ __forceinline__ double E2_at_node(const Cosmo& c, double zp1, double ln1pz_i, double omnu_i) {
   const double cubed = zp1 * zp1 * zp1;
   double f = 1.0;  // dark-energy density factor
-  if (DE == CL_DE_WCDM) f = exp(3 * (1.0 + c.w0) * __ldg(s.grid_ln1pz + i));
+  if (DE == CL_DE_WCDM) f = exp(3 * (1.0 + c.w0) * ln1pz_i);
   if (DE == CL_DE_CPL)  // z/(1+z) = 1 - 1/(1+z)
-    f = exp(fma(3 * (1 + c.w0 + c.wa), __ldg(s.grid_ln1pz + i), -3 * c.wa * (1.0 - rcp_pos(zp1))));
+    f = exp(fma(3 * (1 + c.w0 + c.wa), ln1pz_i, -3 * c.wa * (1.0 - rcp_pos(zp1))));
   if (DE == CL_DE_THAWING) f = fde<DE>(c, zp1 - 1.0, zp1, cubed);
   if (FAM == CL_FAMILY_LATE) return c.Om * cubed + ((DE == CL_DE_LCDM) ? (1.0 - c.Om) : (1.0 - c.Om) * f);
   // massive neutrinos: the theta-independent Omnu_z(z_i) comes from the static node table
   const double de = (DE == CL_DE_LCDM) ? c.Ode : c.Ode * f;
-  return c.Or * (cubed * zp1) + c.Obc * cubed + de + c.Onu * __ldg(s.grid_omnu + i);
+  return c.Or * (cubed * zp1) + c.Obc * cubed + de + c.Onu * omnu_i;
 }
 template <int FAM, int DE>
 __device__ __forceinline__ double E2_of_z(const DevSpec& s, const Cosmo& c, double z) {
@@ -398,13 +398,44 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       if (a.dbg & 1) {
         run = 1.0;
       } else if (s.grid_uniform) {
+        // Static node tables (ln(1+z_i), Omnu_z(z_i)).  A thread owns 16 CONSECUTIVE nodes, so reading the tables from global
+        // memory directly costs 32 sectors per warp load; instead each warp copies its 512 entries with coalesced loads
+        // into the .x / .y halves of the very grid slots its threads are about to fill (a slot is read one step before
+        // it is overwritten), and only the 17th node of a chunk, which lives in the neighbour's first slot, is read
+        // from global memory.
+        constexpr bool kTabLn = DE == CL_DE_WCDM || DE == CL_DE_CPL, kTabOm = FAM == CL_FAMILY_FULL;
+        if (kTabLn || kTabOm) {
+#pragma unroll 4
+          for (int it = 0; it < kPPT; it++) {
+            const int node = warp * (32 * kPPT) + 32 * it + lane;
+            if (node < G + 17) {
+              const uint32_t slot = gd_addr + (uint32_t)pad_idx(node) * 16u;
+              if (kTabLn) asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot), "d"(__ldg(s.grid_ln1pz + node)) : "memory");
+              if (kTabOm) asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot + 8u), "d"(__ldg(s.grid_omnu + node)) : "memory");
+            }
+          }
+          __syncwarp();
+        }
+        auto tab = [&](int k, double& ln, double& om) {   // table entries of node i0 + k, k = 0..16 (compile-time after unrolling)
+          ln = 0.0; om = 0.0;
+          if (k < kPPT) {
+            if (kTabLn) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ln) : "r"(dst + 16u * k) : "memory");
+            if (kTabOm) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(om) : "r"(dst + 16u * k + 8u) : "memory");
+          } else {
+            if (kTabLn) ln = __ldg(s.grid_ln1pz + i0 + k);
+            if (kTabOm) om = __ldg(s.grid_omnu + i0 + k);
+          }
+        };
         const double Ks = c.K * s.step, zp1_0 = fma((double)i0, s.step, 1.0);
-        double prev = Ks * rsqrt_pos(E2_at_node<FAM, DE>(s, c, i0, zp1_0));
+        double ln_i, om_i;
+        tab(0, ln_i, om_i);
+        double prev = Ks * rsqrt_pos(E2_at_node<FAM, DE>(c, zp1_0, ln_i, om_i));
         if (i0 + kPPT < G) {  // all 17 nodes inside the grid
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
             const double zp1 = fma((double)(k + 1), s.step, zp1_0);  // 1 + z_grid[i0+k+1] to 1 ulp
-            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(s, c, i0 + k + 1, zp1));
+            tab(k + 1, ln_i, om_i);
+            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(c, zp1, ln_i, om_i));
             sts_d2(dst + 16u * k, run, prev);
             run = fma(prev + nxt, 0.5, run);
             prev = nxt;
@@ -413,7 +444,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
             const double zp1 = fma((double)(k + 1), s.step, zp1_0);
-            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(s, c, i0 + k + 1, zp1));
+            tab(k + 1, ln_i, om_i);
+            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(c, zp1, ln_i, om_i));
             if (i0 + k < G) sts_d2(dst + 16u * k, run, prev);
             if (i0 + k + 1 < G) run = fma(prev + nxt, 0.5, run);
             prev = nxt;
