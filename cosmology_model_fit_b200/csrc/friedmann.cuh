@@ -586,13 +586,15 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
             else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
           }
           const double DM = hermite_dm(s, sm.gd, sm.off, zq);
+          // 5 log10 through the shared-memory table of the fast path (|err| < 4e-16) for normal positive arguments
+          auto log5 = [&](double x) { return (x > 1e-300 && x < 1e300) ? fast_5log10(x, tab_addr) : 5.0 * log10(x); };
           double mu;
           if (s.sn_mu_fixed != nullptr && isfinite(__ldg(s.sn_mu_fixed + i))) {
             // SH0ES calibrator: fixed distance modulus, mu_corr = 5 log10(D_M(z_cosmo)/D_M(z_cmb)) still applies
             mu = __ldg(s.sn_mu_fixed + i);
-            if (s.n_vel > 0) mu += 5.0 * log10(DM / hermite_dm(s, sm.gd, sm.off, p0.x));
+            if (s.n_vel > 0) mu += log5(DM / hermite_dm(s, sm.gd, sm.off, p0.x));
           } else {
-            mu = 25.0 + 5 * log10(p1.x * DM);
+            mu = 25.0 + log5(p1.x * DM);
           }
           double lin = 0.0;
           for (int k = 0; k < s.n_lin; k++) lin += th[s.col_lin[k]] * __ldg(s.sn_lin_t + (size_t)k * n_sn + i);
