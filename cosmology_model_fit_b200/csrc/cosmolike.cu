@@ -671,7 +671,7 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
     CUDA_TRY(c, cudaMemsetAsync(g.prof, 0, 8 * 8 * 1024, st));
   }
   // row blocks per L2 group: the S digit planes of a group's rows (+ the W planes) stay L2-resident across its column tiles
-  int grp = c->opt_group_rb > 0 ? c->opt_group_rb : (int)std::max<int64_t>(8, ((64LL << 20) / ((int64_t)kOzM * c->oz_ld * S)) & ~7LL);
+  int grp = c->opt_group_rb > 0 ? c->opt_group_rb : (int)std::max<int64_t>(8, ((28LL << 20) / ((int64_t)kOzM * c->oz_ld * S)) & ~7LL);
   g.group_rb = std::min(grp, g.n_rb);
   CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
   const int64_t items = (int64_t)g.n_rb * g.T;
