@@ -9,11 +9,12 @@
 // recombined in FP64 by the epilogue: y_bn = 2^(eR_b + eW_n - 12) sum_l 2^-8l acc_l.  With S = 6 (46 bits, 21 slice
 // products) the result agrees with the FP64 contraction to ~3e-13 relative (|d chi2| ~ 3e-9 at chi2 ~ 4e4).
 //
-// Kernel: persistent CTAs, 6 warps.  warp 0 = scheduler + TMA producer (3-D boxes {64 B of k, rows, S slices}, 64-byte
-// swizzle, separate shared-memory rings for the R slices (A, 128 rows) and the W slices (B, NT rows)); warp 1 = TMEM
-// allocator + single-thread MMA issuer; warps 2-5 = epilogue (tcgen05.ld, FP64 recombination, row sum of squares).
+// Kernel: persistent CTAs, 10 warps.  warp 0 = scheduler + TMA producer (3-D boxes {64 B of k, rows, S planes}, 64-byte
+// swizzle, separate shared-memory rings for the R planes (A, 128 rows) and the W planes (B, NT rows)); warp 1 = TMEM
+// allocator + single-thread MMA issuer (one MMA covers up to 256 / NT stacked planes of W); warps 2-9 = epilogue
+// (tcgen05.ld one level at a time, FP64 recombination, row sum of squares, per-level hand-over to the MMA issuer).
 // Triangular structure as in chi2_gemm.cuh: column tiles aligned to the end of the matrix, k stops at the diagonal
-// block, and inside the diagonal block the MMA N extent shrinks past the columns that are already complete.
+// block (the zeros of W above the diagonal inside that block are simply multiplied: ~4 % of the executed products).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -57,7 +58,6 @@ struct OzArgs {
   const double* u;         // [N] u = W 1
   int* counter;            // dynamic scheduling counter (zeroed before the launch)
   int group_rb;            // row blocks per L2 group
-  int diag_trim;           // 1: shrink the MMA N extent inside the diagonal block
   long long* prof;         // nullable [grid][8]: cycle counters of the MMA issuer and of one epilogue warp
 };
 

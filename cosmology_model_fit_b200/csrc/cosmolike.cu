@@ -55,7 +55,7 @@ struct cl_ctx {
   int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0;
   int* d_counter = nullptr;
   // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
-  int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_diag_trim = 1, opt_slice_tpb = 128;
+  int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_slice_tpb = 128;
   int oz_slices_built = 0;           // S the W planes were built for (0 = none)
   int oz_T = 0;                      // column tiles of the sliced kernel
   int64_t oz_ld = 0;                 // bytes per row of a digit plane
@@ -518,7 +518,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "dbg") { c->opt_dbg = (int)value; return CL_OK; }
   if (n == "gemm_dynamic") { c->opt_gemm_dynamic = value ? 1 : 0; return CL_OK; }
   if (n == "gemm_group_rb") { c->opt_group_rb = (int)value; return CL_OK; }
-  if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; c->opt_diag_trim = value ? 1 : 0; return CL_OK; }
+  if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }   // DMMA engine only
   if (n == "chi2_engine") {
     if (value != CL_CHI2_ENGINE_DMMA && value != CL_CHI2_ENGINE_TCGEN05) return fail(c, CL_E_INVALID, "chi2_engine must be 0 (FP64 DMMA) or 1 (tcgen05 int8 digit planes)");
     c->opt_engine = (int)value; return CL_OK;
@@ -661,7 +661,7 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   if (rc != CL_OK) return rc;
   OzArgs g{};
   g.B = rows; g.N = n; g.T = c->oz_T; g.n_rb = (int)((rows + kOzM - 1) / kOzM);
-  g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter; g.diag_trim = c->opt_diag_trim;
+  g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter;
   g.part_u = moments ? c->d_part_u : nullptr; g.u = c->d_u;
   g.prof = nullptr;
   if (c->opt_dbg & 4) {   // cycle counters of the contraction kernel, printed after the launch (profiling only)

@@ -88,7 +88,7 @@ def test_rows_are_independent_of_the_batch(engines, slices):
         e2.set_option("chi2_slices", slices)
         e2.set_option("max_rows_per_pass", 256)
         assert np.array_equal(e2.chi_squared(theta), full)
-        e2.set_option("gemm_diag_skip", 0)      # full-width MMAs inside the diagonal block: same integers
+        e2.set_option("gemm_group_rb", 8)       # another L2 group order of the items: same integers
         assert np.array_equal(e2.chi_squared(theta), full)
         e2.set_option("gemm_ctas", 3)           # three persistent CTAs walk all items
         assert np.array_equal(e2.chi_squared(theta), full)
