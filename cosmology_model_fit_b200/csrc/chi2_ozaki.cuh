@@ -157,14 +157,16 @@ __global__ void __launch_bounds__(256) k_oz_slice_rows(const double* __restrict_
   if (row >= rows) return;
   const double* x = src + row * ld_src;
   double mx = 0.0;
-  for (int k = lane; k < n; k += 32) mx = fmax(mx, fabs(x[k]));   // fmax drops NaN: stale rows of skipped thetas stay harmless
+  bool bad = false;   // a NaN / Inf residual (log10 of a non-positive distance, as in the reference) must give chi2 = NaN
+  for (int k = lane; k < n; k += 32) { const double a = fabs(x[k]); bad |= !(a <= 1.7e308); mx = fmax(mx, a); }
 #pragma unroll
   for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  bad = __any_sync(0xffffffffu, bad);
   int e = 0;
   if (mx > 0.0 && mx < 1.7e308) e = ilogb(mx) + 1;
   e = max(e, -900);
   const double up = __longlong_as_double((long long)(1023 + OzCfg<S>::FRAC_BITS - e) << 52);   // 2^(FRAC_BITS - e)
-  if (lane == 0) scale[row] = __longlong_as_double((long long)(1023 + e) << 52);
+  if (lane == 0) scale[row] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)(1023 + e) << 52);
   constexpr double kLim = 1.01 * (double)(1ULL << OzCfg<S>::FRAC_BITS);
   const int64_t plane = rows * ld_dst;
   int8_t* d0 = dst + row * ld_dst;
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(256) k_oz_slice_rows_reg(const double* __restr
   const double* x = src + row * ld_src;
   double2 xa[TRIPS], xb[TRIPS];
   double mx = 0.0;
+  bool bad = false;   // NaN / Inf residual -> chi2 = NaN (see k_oz_slice_rows)
 #pragma unroll
   for (int t = 0; t < TRIPS; t++) {
     const int k0 = 4 * lane + 128 * t;
@@ -207,15 +210,18 @@ __global__ void __launch_bounds__(256) k_oz_slice_rows_reg(const double* __restr
       if (k0 + 1 < n) xa[t].y = x[k0 + 1];
       if (k0 + 2 < n) xb[t].x = x[k0 + 2];
     }
-    mx = fmax(fmax(mx, fmax(fabs(xa[t].x), fabs(xa[t].y))), fmax(fabs(xb[t].x), fabs(xb[t].y)));
+    const double a0 = fabs(xa[t].x), a1 = fabs(xa[t].y), a2 = fabs(xb[t].x), a3 = fabs(xb[t].y);
+    bad |= !(a0 <= 1.7e308) | !(a1 <= 1.7e308) | !(a2 <= 1.7e308) | !(a3 <= 1.7e308);
+    mx = fmax(fmax(mx, fmax(a0, a1)), fmax(a2, a3));
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  bad = __any_sync(0xffffffffu, bad);
   int e = 0;
   if (mx > 0.0 && mx < 1.7e308) e = ilogb(mx) + 1;
   e = max(e, -900);
   const double up = __longlong_as_double((long long)(1023 + OzCfg<S>::FRAC_BITS - e) << 52);
-  if (lane == 0) scale[row] = __longlong_as_double((long long)(1023 + e) << 52);
+  if (lane == 0) scale[row] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)(1023 + e) << 52);
   constexpr double kLim = 1.01 * (double)(1ULL << OzCfg<S>::FRAC_BITS);
   const int64_t plane = rows * ld_dst;
   int8_t* d0 = dst + row * ld_dst;

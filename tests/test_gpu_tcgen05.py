@@ -140,3 +140,19 @@ def test_components_and_moments_with_the_tcgen05_engine(engines):
     M = th[:, 0]
     direct = m[:, 0] - 2 * M * m[:, 1] + M * M * m[:, 2]
     assert np.max(np.abs(chi2 - direct) / np.abs(direct)) < 1e-9
+
+
+def test_nan_residuals_propagate(engines):
+    """A peculiar-velocity amplitude far outside the prior makes z_cosmo negative for the nearest SNe: log10 of a negative
+    distance is NaN in the reference (sn/pantheon.py:43-54) and chi2 must be NaN with either engine, not a finite number
+    assembled from clamped digits; the other rows of the batch are unaffected."""
+    import oracle.oracle as O
+    g = golden("sn_pantheon")
+    theta = g["theta"][:8].copy()
+    theta[3, 3] = 60.0      # 6000 km/s: z_pec = 0.02 > min(z_cmb) = 0.01
+    want = O.Oracle(spec("sn_pantheon")).chi_squared(theta)
+    assert np.isnan(want[3]) and np.isfinite(np.delete(want, 3)).all()
+    for slices in (0, 6, 7):
+        got = engines("sn_pantheon", slices).chi_squared(theta)
+        assert np.isnan(got[3]), slices
+        close(np.delete(got, 3), np.delete(want, 3), slices or 7)
