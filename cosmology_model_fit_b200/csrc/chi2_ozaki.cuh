@@ -361,13 +361,6 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
           if constexpr (C::SLO < S) { if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; } }
           const uint32_t aLo = sA + sa_lo * C::A_UNIT_BYTES, aHi = sA + sa * C::A_UNIT_BYTES, bS = sB + sb * C::B_BYTES;
           const bool first_blk = ks == 0, last_blk = ks == nk - 1;
-          if (first_blk) {
-            long long tl0 = clock64();
-#pragma unroll
-            for (int l = 0; l < S; l++) oz_wait(lvl_empty(l), pt ^ 1u);   // the epilogue has read the previous tile
-            t_lvl += clock64() - tl0;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          }
 #pragma unroll
           for (int i = 0; i < S; i++) {
             if (C::SLO < S && i == C::SLO) {   // second unit of R planes; the first one goes back to the producer
@@ -382,7 +375,16 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             for (int h = 0; h < 2; h++) {
 #pragma unroll
               for (int j0 = 0; j0 < S - i; j0 += C::MAX_STACK) {
-                          const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
+                const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
+                if (first_blk && i == 0 && h == 0) {
+                  // first touch of levels j0 .. j0 + cnt - 1 in this tile: the epilogue must have read the previous tile's
+                  // values of exactly these levels (it drains them lowest first, so the first stack rarely waits)
+                  long long tl0 = clock64();
+#pragma unroll
+                  for (int l = j0; l < j0 + cnt; l++) oz_wait(lvl_empty(l), pt ^ 1u);
+                  t_lvl += clock64() - tl0;
+                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 umma_i8(tmem + (uint32_t)((i + j0) * NT), umma_desc_sw64(aP + 32 * h),
                         umma_desc_sw64(bS + j0 * (NT * kOzKB) + 32 * h), umma_idesc_i8(kOzM, cnt * NT), (first_blk && h == 0 && i == 0) ? 0u : 1u);
               }
