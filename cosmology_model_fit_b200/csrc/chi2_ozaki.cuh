@@ -26,7 +26,8 @@ namespace cosmolike {
 
 constexpr int kOzM = 128;      // theta rows per tile (TMEM lanes)
 constexpr int kOzKB = 64;      // bytes of k per pipeline block (= TMA inner box = swizzle span), two K=32 MMAs
-constexpr int kOzThreads = 320;   // producer warp, MMA warp, 8 epilogue warps
+constexpr int kOzThreads = 352;   // producer warp, MMA warp A, 8 epilogue warps, MMA warp B
+constexpr int kOzIssuerB = 10;     // warp index of the second MMA issuer
 constexpr int kOzQueue = 4;
 constexpr int kOzBStages = 2;
 
@@ -59,6 +60,7 @@ struct OzArgs {
   int* counter;            // dynamic scheduling counter (zeroed before the launch)
   int group_rb;            // row blocks per L2 group
   long long* prof;         // nullable [grid][8]: cycle counters of the MMA issuer and of one epilogue warp
+  int dbg_skip;            // timing experiments (results invalid): bit 0 skip the B loads, bit 1 skip the A loads after the first blocks
 };
 
 __device__ __forceinline__ void oz_decode_item(const OzArgs& g, int64_t item, int& jt, int& rb) {
@@ -87,6 +89,17 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int M, int N) {
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// The same with the descriptors given by their low words (start address >> 4 | LBO field): the high word of every
+// descriptor of this kernel is the constant {SBO = 512 B, version 1, 64-byte swizzle}.  One thread issues every MMA of the
+// CTA, so the instructions spent per issue bound the kernel: with the address fields precomputed per ring slot an issue is
+// two integer adds instead of two shift / mask / or chains.
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_i8_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n}\n"
+               ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw64) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -264,13 +277,15 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   auto lvl_empty = [&](int l) { return bars + 8u * (31 + l); };   // level l has been read by the eight epilogue warps
   const uint32_t q_items = bars + 8u * 38;   // int[kOzQueue]
   const uint32_t tslot = bars + 8u * 40;
+  const uint32_t touched = bars + 8u * 41;   // issuer A has issued the first-touch MMAs of the tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < C::A_UNITS; s++) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < kOzBStages; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int s = 0; s < kOzQueue; s++) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 9); }   // MMA thread + 8 epilogue warps
-    for (int l = 0; l < S; l++) { mbar_init(lvl_full(l), 1); mbar_init(lvl_empty(l), 8); }
+    for (int s = 0; s < C::A_UNITS; s++) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 2); }   // released by both issuers' commits
+    for (int s = 0; s < kOzBStages; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 2); }
+    mbar_init(touched, 1);
+    for (int s = 0; s < kOzQueue; s++) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 10); }   // 2 MMA threads + 8 epilogue warps
+    for (int l = 0; l < S; l++) { mbar_init(lvl_full(l), 2); mbar_init(lvl_empty(l), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -309,12 +324,18 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;      // k runs to the end of the diagonal block
         for (int ks = 0; ks < nk; ks++) {
           oz_wait(emptyA(sa), pa ^ 1u);
-          mbar_arrive_expect_tx(fullA(sa), C::A_UNIT_BYTES);
-          tma_load_3d(sA + sa * C::A_UNIT_BYTES, &tmR, ks * kOzKB, rb * kOzM, 0, fullA(sa));
+          if ((g.dbg_skip & 2) && ks >= 3) mbar_arrive(fullA(sa));
+          else {
+            mbar_arrive_expect_tx(fullA(sa), C::A_UNIT_BYTES);
+            tma_load_3d(sA + sa * C::A_UNIT_BYTES, &tmR, ks * kOzKB, rb * kOzM, 0, fullA(sa));
+          }
           if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
           oz_wait(emptyB(sb), pb ^ 1u);
-          mbar_arrive_expect_tx(fullB(sb), C::B_BYTES);
-          tma_load_3d(sB + sb * C::B_BYTES, &tmW, ks * kOzKB, c0, 0, fullB(sb));
+          if ((g.dbg_skip & 1) && ks >= 2) mbar_arrive(fullB(sb));
+          else {
+            mbar_arrive_expect_tx(fullB(sb), C::B_BYTES);
+            tma_load_3d(sB + sb * C::B_BYTES, &tmW, ks * kOzKB, c0, 0, fullB(sb));
+          }
           if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
           if constexpr (C::SLO < S) {
             oz_wait(emptyA(sa), pa ^ 1u);
@@ -325,9 +346,22 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
+  } else if (warp == 1 || warp == kOzIssuerB) {
+    // ===================== MMA issuers (two threads) =====================
+    // One MMA covers SEVERAL slice products: the digit planes of W are stacked in shared memory ([plane][NT rows]) and the
+    // levels are stacked in TMEM ([level][NT columns]), so A_i x [B_j0 ; ... ; B_j1] with N = (j1 - j0 + 1) NT lands exactly
+    // on levels i + j0 .. i + j1.  S (S + 1) / 2 products per K = 32 step become ~S + 3 instructions that read the A plane
+    // from shared memory once each (shared-memory bandwidth, not the tensor pipe, bounds the narrow form).  Round i completes
+    // level i: in the last k block each level is committed on its own barrier as soon as its round has been issued, so the
+    // epilogue overlaps the rest of the block.
+    // A tcgen05.mma costs its issuing thread ~100 cycles of dependent uniform-datapath work while the pipe needs ~90 per
+    // instruction of this schedule, so the issue is split: thread A (warp 1) issues the first K = 32 half of every block,
+    // thread B (warp kOzIssuerB) the second.  Integer accumulation commutes; the only order that matters is that A's
+    // first-touch MMAs of a tile (accumulate = 0) enter the pipe before B's first MMAs of that tile: B waits for `touched`,
+    // on which A arrives after issuing round 0 of the tile's first block (the pipe executes in issue order).  Every
+    // tcgen05.commit only tracks the MMAs of its own thread, so the release barriers count two arrivals.
     if (lane == 0) {
+      const int H = warp == 1 ? 0 : 1;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, pt = 0;
       long long t_full = 0, t_lvl = 0, t_q = 0, n_blk = 0;
@@ -345,50 +379,38 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         oz_decode_item(g, item, jt, rb);
         const int c0 = g.N - NT * (g.T - jt);
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;
-        // One MMA covers SEVERAL slice products: the digit planes of W are stacked in shared memory ([slice][NT rows]) and the
-        // levels are stacked in TMEM ([level][NT columns]), so A_i x [B_j0 ; ... ; B_j1] with N = (j1 - j0 + 1) NT lands
-        // exactly on levels i + j0 .. i + j1.  S (S + 1) / 2 products per K = 32 step become ~S + 3 instructions that
-        // read the A plane from shared memory once each (shared-memory bandwidth, not the tensor pipe, bounds the narrow
-        // form).  Round i completes level i: in the last k block each level is committed on its own barrier as soon as
-        // its round has been issued, so the epilogue overlaps the rest of the block.
         for (int ks = 0; ks < nk; ks++) {
           long long tf0 = clock64();
           oz_wait(fullA(sa), pa);
           oz_wait(fullB(sb), pb);
           t_full += clock64() - tf0; n_blk++;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int sa_lo = sa;
-          if constexpr (C::SLO < S) { if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; } }
-          const uint32_t aLo = sA + sa_lo * C::A_UNIT_BYTES, aHi = sA + sa * C::A_UNIT_BYTES, bS = sB + sb * C::B_BYTES;
           const bool first_blk = ks == 0, last_blk = ks == nk - 1;
+          // descriptor low words of this block's ring slots, at this thread's K = 32 half
+          const uint32_t aD0 = umma_desc_lo(sA + sa * C::A_UNIT_BYTES + 32 * H), bD0 = umma_desc_lo(sB + sb * C::B_BYTES + 32 * H);
+          if (first_blk && H == 1) {
+            oz_wait(touched, pt);   // A has issued the accumulate = 0 MMAs of this tile
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
 #pragma unroll
           for (int i = 0; i < S; i++) {
-            if (C::SLO < S && i == C::SLO) {   // second unit of R planes; the first one goes back to the producer
-              umma_commit(emptyA(sa_lo));
-              long long tf1 = clock64();
-              oz_wait(fullA(sa), pa);
-              t_full += clock64() - tf1;
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            const uint32_t aP = i < C::SLO ? aLo + i * C::PLANE_BYTES : aHi + (i - C::SLO) * C::PLANE_BYTES;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int j0 = 0; j0 < S - i; j0 += C::MAX_STACK) {
+              const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
+              if (first_blk && i == 0 && H == 0) {
+                // first touch of levels j0 .. j0 + cnt - 1 in this tile: the epilogue must have read the previous tile's
+                // values of exactly these levels (it drains them lowest first, so the first stack rarely waits)
+                long long tl0 = clock64();
 #pragma unroll
-              for (int j0 = 0; j0 < S - i; j0 += C::MAX_STACK) {
-                const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
-                if (first_blk && i == 0 && h == 0) {
-                  // first touch of levels j0 .. j0 + cnt - 1 in this tile: the epilogue must have read the previous tile's
-                  // values of exactly these levels (it drains them lowest first, so the first stack rarely waits)
-                  long long tl0 = clock64();
-#pragma unroll
-                  for (int l = j0; l < j0 + cnt; l++) oz_wait(lvl_empty(l), pt ^ 1u);
-                  t_lvl += clock64() - tl0;
-                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                umma_i8(tmem + (uint32_t)((i + j0) * NT), umma_desc_sw64(aP + 32 * h),
-                        umma_desc_sw64(bS + j0 * (NT * kOzKB) + 32 * h), umma_idesc_i8(kOzM, cnt * NT), (first_blk && h == 0 && i == 0) ? 0u : 1u);
+                for (int l = j0; l < j0 + cnt; l++) oz_wait(lvl_empty(l), pt ^ 1u);
+                t_lvl += clock64() - tl0;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               }
+              umma_i8_lo(tmem + (uint32_t)((i + j0) * NT), aD0 + (uint32_t)((i * C::PLANE_BYTES) >> 4),
+                         bD0 + (uint32_t)((j0 * (NT * kOzKB)) >> 4), umma_idesc_i8(kOzM, cnt * NT),
+                         (first_blk && H == 0 && i == 0) ? 0u : 1u);
             }
+            if (first_blk && i == 0 && H == 0) mbar_arrive(touched);
             if (last_blk) umma_commit(lvl_full(i));
           }
           umma_commit(emptyA(sa));
@@ -398,7 +420,7 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         }
         pt ^= 1u;
       }
-      if (g.prof) {
+      if (g.prof && H == 0) {
         long long* p = g.prof + 8 * blockIdx.x;
         p[0] = clock64() - t_begin; p[1] = t_full; p[2] = t_lvl; p[3] = t_q; p[4] = n_blk;
       }

@@ -663,6 +663,7 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   g.B = rows; g.N = n; g.T = c->oz_T; g.n_rb = (int)((rows + kOzM - 1) / kOzM);
   g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter;
   g.part_u = moments ? c->d_part_u : nullptr; g.u = c->d_u;
+  g.dbg_skip = (c->opt_dbg >> 4) & 3;   // dbg bits 4, 5: skip the W / R plane loads (timing experiments, results invalid)
   g.prof = nullptr;
   if (c->opt_dbg & 4) {   // cycle counters of the contraction kernel, printed after the launch (profiling only)
     rc = ensure_scratch(c, 8 * 8 * 1024);

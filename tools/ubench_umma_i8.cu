@@ -308,6 +308,105 @@ static void run_tma(int nsm, const int8_t* d, int64_t K, int64_t rows_total, int
          bytes / (ms * 1e-3) * 1e-12, bytes / (ms * 1e-3) / nsm / 1.965e9, st);
 }
 
+
+// ---------------------------------------------------------------- (4) the contraction's MMA schedule, operands resident
+// One "block" = two K = 32 halves x rounds i = 0..S-1 x stacks of up to 256 / NT planes of W (chi2_ozaki.cuh).
+// VARIANT 0: as in the kernel (round i accumulates into levels i..S-1); 1: every MMA gets its own TMEM columns where they
+// fit (no accumulator overlap between consecutive MMAs); 2: all MMAs read A plane 0 (same shared-memory lines).
+template <int NT, int S, int VARIANT>
+__global__ void __launch_bounds__(128, 1) k_sched(int iters, long long* cycles) {
+  extern __shared__ unsigned char raw[];
+  constexpr int KB = 64;
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  constexpr uint32_t A_BYTES = S * 128 * KB, B_BYTES = S * NT * KB;
+  const uint32_t sA = base, sB = base + A_BYTES, bars = sB + ((B_BYTES + 1023u) & ~1023u), tslot = bars + 64;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t o = tid * 4; o < A_BYTES + B_BYTES; o += 128 * 4) {
+    uint32_t v = 0x01010101u * (o & 3);
+    if (VARIANT == 5) { v = (o + 12345u) * 2654435761u; v ^= v >> 15; v *= 2246822519u; v ^= v >> 13; }   // random digits: full data toggling
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + o), "r"(v));
+  }
+  if (tid == 0) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 32), "r"(0u) : "memory"); mbar_init(bars, 1); mbar_init(bars + 8, 1); mbar_init(bars + 16, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+  constexpr int MAXST = 256 / NT;
+  if (tid == 0) {
+    long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; it++) {
+      int slot = 0;
+#pragma unroll
+      for (int i = 0; i < S; i++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int j0 = 0; j0 < S - i; j0 += MAXST) {
+            const int cnt = (S - i - j0) < MAXST ? (S - i - j0) : MAXST;
+            uint32_t dcol = (uint32_t)((i + j0) * NT);
+            if (VARIANT == 1) { dcol = (uint32_t)((slot * 256) % 512); if (dcol + cnt * NT > 512) dcol = 0; slot++; }
+            const int ai = VARIANT == 2 ? 0 : i;
+            umma_i8(tmem + dcol, umma_desc(sA + ai * 128 * KB + 32 * h, KB), umma_desc(sB + j0 * NT * KB + 32 * h, KB), umma_idesc_i8(128, cnt * NT), 1u);
+          }
+      if (VARIANT == 6) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // 6: one fence per block
+      if (VARIANT == 3 || VARIANT == 4) umma_commit(bars + 8);    // 3: one, 4: two tcgen05.commit per block (nobody waits on them)
+      if (VARIANT == 4) umma_commit(bars + 16);
+      if ((it & 3) == 3 || it == iters - 1) {
+        umma_commit(bars);
+        if (!mbar_wait(bars, ph)) { cycles[blockIdx.x] = -1; break; }
+        ph ^= 1u;
+      }
+    }
+    long long t1 = clock64();
+    if (cycles[blockIdx.x] != -1) cycles[blockIdx.x] = t1 - t0;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 32), "r"(1u) : "memory");   // stop flag for the side warps
+  } else if ((VARIANT == 7 || VARIANT == 8) && warp >= 1) {
+    // side warps imitating the epilogue while the MMAs run: 7 = tcgen05.ld of TMEM columns, 8 = FP64 / INT arithmetic
+    double acc[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+    uint32_t stop = 0, col = 0;
+    while (!stop) {
+      if (VARIANT == 7) {
+        uint32_t v[8];
+        for (int q = 0; q < 16; q++) { tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + 448u + ((col + 8 * q) & 63u), v); acc[q & 7] += (double)v[0]; }
+        col += 128;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; q++) acc[q & 7] = fma(acc[q & 7], 1.0000001, 0.5);
+      }
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(stop) : "r"(bars + 32) : "memory");
+    }
+    if (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7] == 0.123) cycles[blockIdx.x] = 7;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+template <int NT, int S, int VARIANT>
+static void run_sched(int nsm) {
+  long long* dC; CK(cudaMalloc(&dC, nsm * 8)); CK(cudaMemset(dC, 0, nsm * 8));
+  size_t smem = 1024 + S * 128 * 64 + ((S * NT * 64 + 1023) & ~1023) + 256;
+  CK(cudaFuncSetAttribute(k_sched<NT, S, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int iters = 400;
+  k_sched<NT, S, VARIANT><<<nsm, 128, smem>>>(8, dC);
+  CK(cudaDeviceSynchronize());
+  k_sched<NT, S, VARIANT><<<nsm, 128, smem>>>(iters, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> c(nsm); CK(cudaMemcpy(c.data(), dC, nsm * 8, cudaMemcpyDeviceToHost));
+  const int pairs = S * (S + 1) / 2;
+  fflush(stdout);
+  printf("sched NT=%3d S=%d variant %d: %8.1f cycles per K=64 block (tensor floor %d, %d products)%s\n", NT, S, VARIANT, (double)c[0] / iters, pairs * NT, pairs,
+         c[0] < 0 ? "  TIMEOUT" : "");
+  cudaFree(dC);
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int nsm = prop.multiProcessorCount;
@@ -321,6 +420,11 @@ int main(int argc, char** argv) {
   ok &= run_check<128, 80, 2>(256);
   ok &= run_check<32, 256, 1>(128);
   if (!ok) { printf("descriptor check FAILED; skipping rates\n"); return 3; }
+  if (argc > 2) { int v = atoi(argv[2]); if (v == 6) run_sched<64, 7, 6>(nsm); if (v == 7) run_sched<64, 7, 7>(nsm); if (v == 8) run_sched<64, 7, 8>(nsm); fflush(stdout); return 0; }
+  run_sched<64, 7, 0>(nsm); run_sched<64, 7, 1>(nsm); run_sched<64, 7, 2>(nsm); run_sched<64, 7, 3>(nsm); run_sched<64, 7, 4>(nsm); run_sched<64, 7, 5>(nsm);
+  run_sched<80, 6, 0>(nsm); run_sched<80, 6, 1>(nsm); run_sched<80, 6, 2>(nsm);
+  fflush(stdout);
+  if (argc > 1) return 0;
   run_rate<32, 64, 6>(nsm); run_rate<32, 80, 6>(nsm); run_rate<64, 64, 6>(nsm); run_rate<64, 80, 6>(nsm);
   run_rate<32, 128, 3>(nsm); run_rate<32, 256, 2>(nsm); run_rate<128, 256, 1>(nsm);
   run_rate<32, 80, 6>(1); run_rate<32, 256, 2>(1);
