@@ -139,7 +139,10 @@ __device__ __forceinline__ double E2_at_node(const Cosmo& c, double zp1, double 
   if (DE == CL_DE_WCDM) f = exp(3 * (1.0 + c.w0) * ln1pz_i);
   if (DE == CL_DE_CPL)  // z/(1+z) = 1 - 1/(1+z)
     f = exp(fma(3 * (1 + c.w0 + c.wa), ln1pz_i, -3 * c.wa * (1.0 - rcp_pos(zp1))));
-  if (DE == CL_DE_THAWING) f = fde<DE>(c, zp1 - 1.0, zp1, cubed);
+  if (DE == CL_DE_THAWING) {  // (2 a^-3 / ((1 + w0) + (1 - w0) a^-3))^2 with the reciprocal to 1 ulp instead of an IEEE division per node
+    const double q = (2 * cubed) * rcp_pos(fma(1.0 - c.w0, cubed, 1.0 + c.w0));
+    f = q * q;
+  }
   if (FAM == CL_FAMILY_LATE) return c.Om * cubed + ((DE == CL_DE_LCDM) ? (1.0 - c.Om) : (1.0 - c.Om) * f);
   // massive neutrinos: the theta-independent Omnu_z(z_i) comes from the static node table
   const double de = (DE == CL_DE_LCDM) ? c.Ode : c.Ode * f;
