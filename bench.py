@@ -373,7 +373,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if args.engine == "dmma" else "f64 (stage 3: exact int8 digit planes, int32 accumulation, FP64 recombination)",
+            "dtype": "f64",
+            "dtype_note": "all stages FP64" if args.engine == "dmma" else
+                          "FP64 throughout; stage 3 multiplies exact int8 digit planes of the FP64 operands (int32 accumulation, FP64 recombination)",
             "data": "synthetic", "config": workload_config(args, spec, world),
             "roofline": roofline,
             "roofline_stage12": {"bound": "hbm", "kernel": "k_friedmann_residuals (stage 1+2)", "achieved": s12_bytes / (s12_ms * 1e-3) / 1e9,
