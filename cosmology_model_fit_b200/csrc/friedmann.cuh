@@ -261,12 +261,20 @@ __device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, dou
   const double ih = s.grid_uniform ? s.inv_step : 1.0;
   if (xq <= grid_z(s, 0)) return gd[0].y * ih;
   if (xq >= grid_z(s, G - 1)) return gd[pad_idx(G - 1)].y * ih;
-  int lo = 0, hi = G;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (grid_z(s, mid) < xq) lo = mid + 1; else hi = mid;
+  int i;
+  if (s.grid_uniform) {
+    // np.searchsorted(x, xq) - 1 on the np.linspace grid: x_i < xq <= x_(i+1); start from floor(xq / step) and fix up
+    i = min(max((int)(xq * s.inv_step), 0), G - 2);
+    while (i > 0 && grid_z(s, i) >= xq) i--;
+    while (i < G - 2 && grid_z(s, i + 1) < xq) i++;
+  } else {
+    int lo = 0, hi = G;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (grid_z(s, mid) < xq) lo = mid + 1; else hi = mid;
+    }
+    i = lo - 1;
   }
-  const int i = lo - 1;
   double xi = grid_z(s, i);
   double h_i = grid_z(s, i + 1) - xi;
   double t = (xq - xi) / h_i;
