@@ -4,6 +4,9 @@
 //      accumulators in TMEM, several "levels" (column ranges) per tile, read back with tcgen05.ld.
 //  (2) issue rate of tcgen05.mma M=128 x N x K=32 (int8) for N = 64, 80, 128, 256 with operands resident in smem.
 //  (3) chip-wide TMA load bandwidth from L2 for the same boxes (inner extent 32 / 64 / 128 bytes).
+//  (4) the contraction's stacked-plane MMA schedule with resident operands: cycles per 64-byte k block against the pipe floor;
+//      variants: 1 non-overlapping accumulators, 2 one A plane, 3 / 4 one / two tcgen05.commit per block, 5 random operand data,
+//      6 a tcgen05.fence per block (`ubench_umma_i8 sched 6`); 7 / 8 (side warps) are unfinished experiments: they hang.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o ubench_umma_i8 ubench_umma_i8.cu
 #include <cuda.h>
 #include <cuda_runtime.h>
