@@ -6,7 +6,7 @@
 //  (3) chip-wide TMA load bandwidth from L2 for the same boxes (inner extent 32 / 64 / 128 bytes).
 //  (4) the contraction's stacked-plane MMA schedule with resident operands: cycles per 64-byte k block against the pipe floor;
 //      variants: 1 non-overlapping accumulators, 2 one A plane, 3 / 4 one / two tcgen05.commit per block, 5 random operand data,
-//      6 a tcgen05.fence per block (`ubench_umma_i8 sched 6`); 7 / 8 (side warps) are unfinished experiments: they hang.
+//      6 a tcgen05.fence per block (`ubench_umma_i8 sched 6`).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o ubench_umma_i8 ubench_umma_i8.cu
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(128, 1) k_sched(int iters, long long* cycles) 
     if (VARIANT == 5) { v = (o + 12345u) * 2654435761u; v ^= v >> 15; v *= 2246822519u; v ^= v >> 13; }   // random digits: full data toggling
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + o), "r"(v));
   }
-  if (tid == 0) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 32), "r"(0u) : "memory"); mbar_init(bars, 1); mbar_init(bars + 8, 1); mbar_init(bars + 16, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 8, 1); mbar_init(bars + 16, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
@@ -369,23 +369,6 @@ __global__ void __launch_bounds__(128, 1) k_sched(int iters, long long* cycles) 
     }
     long long t1 = clock64();
     if (cycles[blockIdx.x] != -1) cycles[blockIdx.x] = t1 - t0;
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 32), "r"(1u) : "memory");   // stop flag for the side warps
-  } else if ((VARIANT == 7 || VARIANT == 8) && warp >= 1) {
-    // side warps imitating the epilogue while the MMAs run: 7 = tcgen05.ld of TMEM columns, 8 = FP64 / INT arithmetic
-    double acc[8] = {1, 2, 3, 4, 5, 6, 7, 8};
-    uint32_t stop = 0, col = 0;
-    while (!stop) {
-      if (VARIANT == 7) {
-        uint32_t v[8];
-        for (int q = 0; q < 16; q++) { tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + 448u + ((col + 8 * q) & 63u), v); acc[q & 7] += (double)v[0]; }
-        col += 128;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 64; q++) acc[q & 7] = fma(acc[q & 7], 1.0000001, 0.5);
-      }
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(stop) : "r"(bars + 32) : "memory");
-    }
-    if (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7] == 0.123) cycles[blockIdx.x] = 7;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -423,7 +406,7 @@ int main(int argc, char** argv) {
   ok &= run_check<128, 80, 2>(256);
   ok &= run_check<32, 256, 1>(128);
   if (!ok) { printf("descriptor check FAILED; skipping rates\n"); return 3; }
-  if (argc > 2) { int v = atoi(argv[2]); if (v == 6) run_sched<64, 7, 6>(nsm); if (v == 7) run_sched<64, 7, 7>(nsm); if (v == 8) run_sched<64, 7, 8>(nsm); fflush(stdout); return 0; }
+  if (argc > 2) { int v = atoi(argv[2]); if (v == 6) run_sched<64, 7, 6>(nsm); fflush(stdout); return 0; }
   run_sched<64, 7, 0>(nsm); run_sched<64, 7, 1>(nsm); run_sched<64, 7, 2>(nsm); run_sched<64, 7, 3>(nsm); run_sched<64, 7, 4>(nsm); run_sched<64, 7, 5>(nsm);
   run_sched<80, 6, 0>(nsm); run_sched<80, 6, 1>(nsm); run_sched<80, 6, 2>(nsm);
   fflush(stdout);
