@@ -586,24 +586,44 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         double vamp[CL_MAX_VEL];
 #pragma unroll
         for (int k = 0; k < CL_MAX_VEL; k++) vamp[k] = k < s.n_vel ? s.vel_scale * th[s.col_vel[k]] : 0.0;
+        // D_M(zq): inside a np.linspace grid the same collapsed (quadratic) Hermite segment as the fast path, the literal
+        // reference formulas otherwise
+        const bool uni = s.grid_uniform != 0;
+        const double inv_step_g = s.inv_step, z_last_g = s.z_last;
+        const int imax_g = G - 2;
+        const uint32_t off_addr_g = s12_smem_u32(sm.off);
+        auto dm_of = [&](double zq) -> double {
+          if (uni && zq > 1e-9 && zq < z_last_g) {
+            const double kMagicG = 6755399441055744.0;
+            const double w = fma(zq, inv_step_g, -0.5) + kMagicG;
+            const int j = min(__double2loint(w), imax_g);
+            const double t = fma(zq, inv_step_g, -(w - kMagicG));
+            const double2 n0 = lds_d2(gd_addr + ((uint32_t)(j + (j >> 4)) << 4));
+            const double2 n1 = lds_d2(gd_addr + ((uint32_t)(j + 1 + ((j + 1) >> 4)) << 4));
+            double base;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(base) : "r"(off_addr_g + ((uint32_t)(j >> 4) << 3)));
+            return fma(t, fma(0.5 * t, n1.y - n0.y, n0.y), n0.x + base);
+          }
+          return hermite_dm(s, sm.gd, sm.off, zq);
+        };
         for (int i = tid; i < n_sn; i += kS12Threads) {
           const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);  // {z_cmb, w0}, {1+z_hel, obs}
           double zq = p0.x;
           if (s.n_vel > 0) {
             double v_km_s = 0.0;
             for (int k = 0; k < s.n_vel; k++) v_km_s += vamp[k] * __ldg(s.sn_vel_w + (size_t)k * n_sn + i);
-            const double z_pec = v_km_s / kC_KMS;
-            if (s.vel_mode == CL_VEL_DIVIDE) zq = -1.0 + (1.0 + p0.x) / (1.0 + z_pec);
+            const double z_pec = v_km_s * (1.0 / kC_KMS);
+            if (s.vel_mode == CL_VEL_DIVIDE) zq = fma(1.0 + p0.x, rcp_pos(1.0 + z_pec), -1.0);   // |z_pec| << 1: 1 + z_pec > 0
             else zq = fmax((1.0 + p0.x) * (1.0 + z_pec) - 1.0, 1e-8);
           }
-          const double DM = hermite_dm(s, sm.gd, sm.off, zq);
+          const double DM = dm_of(zq);
           // 5 log10 through the shared-memory table of the fast path (|err| < 4e-16) for normal positive arguments
           auto log5 = [&](double x) { return (x > 1e-300 && x < 1e300) ? fast_5log10(x, tab_addr) : 5.0 * log10(x); };
           double mu;
           if (s.sn_mu_fixed != nullptr && isfinite(__ldg(s.sn_mu_fixed + i))) {
             // SH0ES calibrator: fixed distance modulus, mu_corr = 5 log10(D_M(z_cosmo)/D_M(z_cmb)) still applies
             mu = __ldg(s.sn_mu_fixed + i);
-            if (s.n_vel > 0) mu += log5(DM / hermite_dm(s, sm.gd, sm.off, p0.x));
+            if (s.n_vel > 0) mu += log5(DM) - log5(dm_of(p0.x));
           } else {
             mu = 25.0 + log5(p1.x * DM);
           }
