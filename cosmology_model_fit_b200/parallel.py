@@ -95,6 +95,8 @@ class ShardedEngine:
     def _unpad(self, flat, B, rows_max):
         if self.world == 1:
             return np.array(flat[:B])
+        if rows_max * self.world == B:   # equal shards: the gathered vector is already in row order
+            return np.array(flat[:B])
         out = np.empty(B)
         for r in range(self.world):
             lo, hi = shard_bounds(B, r, self.world)
