@@ -156,3 +156,19 @@ def test_nan_residuals_propagate(engines):
         got = engines("sn_pantheon", slices).chi_squared(theta)
         assert np.isnan(got[3]), slices
         close(np.delete(got, 3), np.delete(want, 3), slices or 7)
+
+
+def test_stage3_split_timing(engines):
+    """cl_stage3_split: planes + contraction add up to the stage-3 time of cl_last_timing; zero planes time with the DMMA
+    engine."""
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    theta = uniform_theta(golden("sn_pantheon")["bounds"], 4096, seed=1)
+    for slices in (7, 0):
+        e = engines("sn_pantheon", slices)
+        e.chi_squared(theta)
+        planes, contraction = e.stage3_split()
+        t = e.last_timing()
+        assert contraction > 0 and abs(planes + contraction - t["stage3_ms"]) < 1e-3
+        assert (planes > 0.005) == bool(slices)
+    hist = engines("sn_pantheon", 7).stage3_split(3)
+    assert hist.shape[1] == 2 and len(hist) >= 1
