@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "chi2_gemm.cuh"
 
@@ -47,6 +48,29 @@ template <int S> struct OzCfg {
   static constexpr int MAX_STACK = 256 / NT;   // digit planes of W one MMA may cover (N <= 256)
 };
 
+// Level groups of the phased MMA order (see the issuer): groups are listed from the TOP level down, every group holds at
+// most MAX_STACK levels so that the A_0 stack of a group touches all of its levels with one instruction.
+#ifndef OZ_PHASES
+#define OZ_PHASES 1
+#endif
+#ifndef OZ_HEAD
+#define OZ_HEAD 2
+#endif
+constexpr int kOzHead = OZ_HEAD;   // k blocks of a new tile issued group-major while the epilogue still drains the previous tile
+template <int S> struct OzGroups {
+#if OZ_PHASES == 3
+  static constexpr int NG = 3;
+  __host__ __device__ static constexpr int lo(int g) { return S == 7 ? (g == 0 ? 5 : g == 1 ? 3 : 0) : S == 6 ? (g == 0 ? 4 : g == 1 ? 2 : 0) : (g == 0 ? 3 : g == 1 ? 1 : 0); }
+#elif OZ_PHASES == 2
+  static constexpr int NG = 2;
+  __host__ __device__ static constexpr int lo(int g) { return S == 7 ? (g == 0 ? 4 : 0) : S == 6 ? (g == 0 ? 3 : 0) : (g == 0 ? 3 : 1); }
+#else
+  static constexpr int NG = 1;
+  __host__ __device__ static constexpr int lo(int) { return 0; }
+#endif
+  __host__ __device__ static constexpr int hi(int g) { return g == 0 ? S - 1 : lo(g - 1) - 1; }
+};
+
 struct OzArgs {
   int64_t B;               // rows of R in this pass
   int N;                   // SN count
@@ -60,18 +84,41 @@ struct OzArgs {
   int* counter;            // dynamic scheduling counter (zeroed before the launch)
   int group_rb;            // row blocks per L2 group
   long long* prof;         // nullable [grid][8]: cycle counters of the MMA issuer and of one epilogue warp
+  long long* trace;        // nullable [1 + 16384]: event trace of CTA 0 (count, then (code << 44) | clock), dbg bit 3
   int dbg_skip;            // timing experiments (results invalid): bit 0 skip the B loads, bit 1 skip the A loads after the first blocks
 };
 
-__device__ __forceinline__ void oz_decode_item(const OzArgs& g, int64_t item, int& jt, int& rb) {
+// OZ_PROF=1 compiles the cycle counters (dbg bit 2) and the event trace (dbg bit 3) in; the production build carries neither
+#ifndef OZ_PROF
+#define OZ_PROF 0
+#endif
+__device__ __forceinline__ long long oz_clock() {
+#if OZ_PROF
+  return clock64();
+#else
+  return 0;
+#endif
+}
+// event trace of CTA 0: three writers (issuer A, issuer B, epilogue warp 2 lane 0), each with its own region and its own
+// running index (plain stores: no round trip on the traced thread)
+constexpr int kOzTraceCap = 1400;   // events per warp (11 regions)
+__device__ __forceinline__ void oz_trace(const OzArgs& g, int& idx, int code) {
+  if (OZ_PROF && g.trace && blockIdx.x == 0 && idx < kOzTraceCap) {
+    const int role = threadIdx.x >> 5;
+    g.trace[1 + role * kOzTraceCap + idx] = ((long long)code << 44) | (clock64() & ((1LL << 44) - 1));
+    idx++;
+  }
+}
+__device__ __forceinline__ void oz_decode_item(const OzArgs& g, int item, int& jt, int& rb) {   // items < 2^31 (checked on the host)
   const int per_group = g.group_rb * g.T;
   const int n_full = g.n_rb / g.group_rb;
-  int grp = (int)(item / per_group);
+  int grp = item / per_group;
   int r, width;
-  if (grp < n_full) { r = (int)(item % per_group); width = g.group_rb; }
-  else { grp = n_full; r = (int)(item - (int64_t)n_full * per_group); width = g.n_rb - n_full * g.group_rb; }
-  jt = g.T - 1 - r / width;
-  rb = grp * g.group_rb + r % width;
+  if (grp < n_full) { r = item - grp * per_group; width = g.group_rb; }
+  else { grp = n_full; r = item - n_full * per_group; width = g.n_rb - n_full * g.group_rb; }
+  const int q = r / width;
+  jt = g.T - 1 - q;
+  rb = grp * g.group_rb + (r - q * width);
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
@@ -114,6 +161,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_fence4(int32_t* v) { asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]) :: "memory"); }
 __device__ __forceinline__ void tmem_ld_fence8(int32_t* v) {
   asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
 }
@@ -127,6 +178,35 @@ __device__ __forceinline__ void tmem_ld_fence(int32_t* v) {
 // bounded spin: a wrong descriptor or a lost arrival traps (the context dies with an error) instead of hanging the GPU
 __device__ __forceinline__ void oz_wait(uint32_t bar, uint32_t parity) {
   for (long long i = 0; i < (1LL << 28); i++) if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+
+// long waits (the epilogue's first level of a tile, the producer's ring slots): poll with a pause in between, so that the
+// barrier unit stays free for the threads on the critical path
+__device__ __forceinline__ void oz_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (long long i = 0; i < (1LL << 26); i++) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(ns);
+  }
+  __trap();
+}
+#ifndef OZ_EPI_POLL
+#define OZ_EPI_POLL 2
+#endif
+#ifndef OZ_MERGE_TOP
+#define OZ_MERGE_TOP 0
+#endif
+#ifndef OZ_SPIN_NS
+#define OZ_SPIN_NS 40
+#endif
+// latency-critical waits of the tile hand-over: non-blocking test_wait in a tight loop (try_wait may park the thread)
+__device__ __forceinline__ void oz_spin(uint32_t bar, uint32_t parity) {
+  for (long long i = 0; i < (1LL << 28); i++) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(OZ_SPIN_NS);
+  }
   __trap();
 }
 
@@ -277,13 +357,13 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   auto lvl_empty = [&](int l) { return bars + 8u * (31 + l); };   // level l has been read by the eight epilogue warps
   const uint32_t q_items = bars + 8u * 38;   // int[kOzQueue]
   const uint32_t tslot = bars + 8u * 40;
-  const uint32_t touched = bars + 8u * 41;   // issuer A has issued the first-touch MMAs of the tile
+  auto touched = [&](int gq) { return bars + 8u * (41 + gq); };   // issuer A has issued the first-touch MMAs of level group gq
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::A_UNITS; s++) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 2); }   // released by both issuers' commits
     for (int s = 0; s < kOzBStages; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 2); }
-    mbar_init(touched, 1);
+    for (int q = 0; q < OzGroups<S>::NG; q++) mbar_init(touched(q), 1);
     for (int s = 0; s < kOzQueue; s++) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 10); }   // 2 MMA threads + 8 epilogue warps
     for (int l = 0; l < S; l++) { mbar_init(lvl_full(l), 2); mbar_init(lvl_empty(l), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -304,33 +384,57 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   uint32_t qphase = 0;
 
   if (warp == 0) {
+#if OZ_PROF
+    // observer (profiling build): lane 1 records when the LAST level of every tile completes (the end of the tile's MMAs)
+    if (lane == 1 && g.trace && blockIdx.x == 0) {
+      int tr_i = 0;
+      uint32_t p = 0;
+      for (int n = 0; n < kOzTraceCap; n++) {
+        bool seen = false;
+        for (long long i = 0; i < (1LL << 24) && !seen; i++) {
+          uint32_t ok;
+          asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(lvl_full(S - 1)), "r"(p) : "memory");
+          seen = ok != 0;
+        }
+        if (!seen) break;
+        oz_trace(g, tr_i, 70);
+        p ^= 1u;
+      }
+    }
+#endif
     // ===================== scheduler + TMA producer =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      // The item counter is read one tile AHEAD: the atomic's round trip (148 CTAs on one address), the decode and the TMA
+      // latency of a new tile's first blocks otherwise follow the previous tile's last load back to back, and the three-slot
+      // ring only hides two blocks of that (it showed as the issuers waiting ~20 % of their time for the first blocks of a tile).
+      int next = atomicAdd(g.counter, 1);
       for (;;) {
-        const int64_t item = atomicAdd(g.counter, 1);
+        const int item = next;
         const bool done = item >= total;
+        if (!done) next = atomicAdd(g.counter, 1);   // in flight while this tile's loads are issued
         oz_wait(qempty(qslot), qphase ^ 1u);
-        asm volatile("st.shared.s32 [%0], %1;" ::"r"(q_items + 4u * qslot), "r"(done ? -1 : (int)item) : "memory");
+        int jt = 0, rb = 0;
+        if (!done) oz_decode_item(g, item, jt, rb);
+        // the decoded item goes through the queue ((jt << 24) | rb): the 64-bit divisions stay off the consumers' paths
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(q_items + 4u * qslot), "r"(done ? -1 : ((jt << 24) | rb)) : "memory");
         mbar_arrive(qfull(qslot));
         if (++qslot == kOzQueue) { qslot = 0; qphase ^= 1u; }
         if (done) break;
-        int jt, rb;
-        oz_decode_item(g, item, jt, rb);
         const int c0 = g.N - NT * (g.T - jt);              // first column of the tile (< 0 only for jt == 0: TMA zero-fills)
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;      // k runs to the end of the diagonal block
         for (int ks = 0; ks < nk; ks++) {
-          oz_wait(emptyA(sa), pa ^ 1u);
+          oz_wait_relaxed(emptyA(sa), pa ^ 1u, 50);
           if ((g.dbg_skip & 2) && ks >= 3) mbar_arrive(fullA(sa));
           else {
             mbar_arrive_expect_tx(fullA(sa), C::A_UNIT_BYTES);
             tma_load_3d(sA + sa * C::A_UNIT_BYTES, &tmR, ks * kOzKB, rb * kOzM, 0, fullA(sa));
           }
           if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
-          oz_wait(emptyB(sb), pb ^ 1u);
+          oz_wait_relaxed(emptyB(sb), pb ^ 1u, 50);
           if ((g.dbg_skip & 1) && ks >= 2) mbar_arrive(fullB(sb));
           else {
             mbar_arrive_expect_tx(fullB(sb), C::B_BYTES);
@@ -361,68 +465,157 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // on which A arrives after issuing round 0 of the tile's first block (the pipe executes in issue order).  Every
     // tcgen05.commit only tracks the MMAs of its own thread, so the release barriers count two arrivals.
     if (lane == 0) {
+      using G = OzGroups<S>;
       const int H = warp == 1 ? 0 : 1;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, pt = 0;
       long long t_full = 0, t_lvl = 0, t_q = 0, n_blk = 0;
-      const long long t_begin = clock64();
+      int tr_i = 0;
+      const long long t_begin = oz_clock();
+      // all MMAs of level group gq for one k block (this thread's K = 32 half); `zero`: first touch of the tile
+      auto issue_group = [&](auto gq_tag, uint32_t aD0, uint32_t bD0, bool zero, bool last) {
+        constexpr int gq = decltype(gq_tag)::value;
+        constexpr int la = G::lo(gq), lb = G::hi(gq);
+        static_assert(G::NG == 1 || lb - la + 1 <= C::MAX_STACK, "a level group must fit one stacked MMA");
+#pragma unroll
+        for (int i = 0; i <= lb; i++) {
+          const int jlo = la - i > 0 ? la - i : 0;
+          const int jhi = lb - i < S - 1 - i ? lb - i : S - 1 - i;
+#pragma unroll
+          for (int j0 = jlo; j0 <= jhi; j0 += C::MAX_STACK) {
+            const int cnt = (jhi - j0 + 1) < C::MAX_STACK ? (jhi - j0 + 1) : C::MAX_STACK;
+            umma_i8_lo(tmem + (uint32_t)((i + j0) * NT), aD0 + (uint32_t)((i * C::PLANE_BYTES) >> 4),
+                       bD0 + (uint32_t)((j0 * (NT * kOzKB)) >> 4), umma_idesc_i8(kOzM, cnt * NT), (zero && i == 0) ? 0u : 1u);
+          }
+          if (zero && i == 0) mbar_arrive(touched(gq));       // the accumulate = 0 MMAs of this group are in the pipe: B may follow
+          if (G::NG == 1 && last) umma_commit(lvl_full(i));   // one group: round i completes level i
+          if (zero && (i == 0 || i == S - 1)) oz_trace(g, tr_i, 60 + i);
+        }
+      };
+      auto commit_levels = [&](auto gq_tag) {
+        constexpr int gq = decltype(gq_tag)::value;
+        if constexpr (G::NG > 1)
+#pragma unroll
+          for (int l = G::hi(gq); l >= G::lo(gq); l--) umma_commit(lvl_full(l));
+      };
+      auto for_groups = [&](auto&& f) {
+        f(std::integral_constant<int, 0>{});
+        if constexpr (G::NG > 1) f(std::integral_constant<int, 1>{});
+        if constexpr (G::NG > 2) f(std::integral_constant<int, 2>{});
+      };
       for (;;) {
-        long long tq0 = clock64();
+        long long tq0 = oz_clock();
         oz_wait(qfull(qslot), qphase);
-        t_q += clock64() - tq0;
+        t_q += oz_clock() - tq0;
         int item;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(q_items + 4u * qslot) : "memory");
         mbar_arrive(qempty(qslot));
         if (++qslot == kOzQueue) { qslot = 0; qphase ^= 1u; }
         if (item < 0) break;
-        int jt, rb;
-        oz_decode_item(g, item, jt, rb);
+        const int jt = item >> 24, rb = item & 0xffffff;
         const int c0 = g.N - NT * (g.T - jt);
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;
-        for (int ks = 0; ks < nk; ks++) {
-          long long tf0 = clock64();
+        // ---- head: the first HB blocks, group-major.  Group gq only needs ITS levels back from the epilogue (which drains
+        // the previous tile from the top level down), so the MMAs of the upper groups run under the rest of the drain.
+        oz_trace(g, tr_i, 1000 * H + 1);   // tile start (item known)
+        const int HB = G::NG == 1 ? 0 : (nk < kOzHead ? nk : kOzHead);   // one group: no head, one copy of the issue code (hot in the instruction cache)
+        uint32_t aD[kOzHead], bD[kOzHead];
+        int hsa[kOzHead], hsb[kOzHead];
+        {
+          int xa = sa, xb = sb;
+          uint32_t ya = pa, yb = pb;
+#pragma unroll
+          for (int k = 0; k < kOzHead; k++) {
+            hsa[k] = xa; hsb[k] = xb;
+            aD[k] = umma_desc_lo(sA + xa * C::A_UNIT_BYTES + 32 * H);
+            bD[k] = umma_desc_lo(sB + xb * C::B_BYTES + 32 * H);
+            if (k < HB) {
+              if (++xa == C::A_UNITS) { xa = 0; ya ^= 1u; }
+              if (++xb == kOzBStages) { xb = 0; yb ^= 1u; }
+            }
+          }
+          // the parities of the head's slots are consumed below through (pa, pb) advanced in step
+          (void)ya; (void)yb;
+        }
+        if constexpr (G::NG > 1) for_groups([&](auto gq_tag) {
+          constexpr int gq = decltype(gq_tag)::value;
+          long long tl0 = oz_clock();
+          if (H == 0) {
+            {
+              // the epilogue warps hand the levels back in a fixed order, so the barrier of the level they read LAST implies
+              // the others (a poll of a completed mbarrier still costs ~300 cycles while other warps are polling)
+              constexpr int l_last = G::NG > 1 ? G::lo(gq) : S - 1;
+              oz_spin(lvl_empty(l_last), pt ^ 1u);
+            }   // previous tile's values are in registers
+          } else {
+            oz_spin(touched(gq), pt);   // A has issued the accumulate = 0 MMA of this group
+          }
+          t_lvl += oz_clock() - tl0;
+          oz_trace(g, tr_i, 1000 * H + 10 + gq);   // group gq released to this issuer
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          int wa = sa, wb = sb;
+          uint32_t qa = pa, qb = pb;
+#pragma unroll
+          for (int k = 0; k < kOzHead; k++) {
+            if (k < HB) {
+              if (gq == 0) {
+                long long tf0 = oz_clock();
+                oz_wait(fullA(wa), qa);
+                oz_wait(fullB(wb), qb);
+                t_full += oz_clock() - tf0; n_blk++;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (++wa == C::A_UNITS) { wa = 0; qa ^= 1u; }
+                if (++wb == kOzBStages) { wb = 0; qb ^= 1u; }
+              }
+              issue_group(gq_tag, aD[k], bD[k], k == 0 && H == 0, k == nk - 1);
+              oz_trace(g, tr_i, 1000 * H + 20 + 4 * k + gq);   // head: group gq of block k issued
+              if (k == nk - 1) commit_levels(gq_tag);
+              if (gq == G::NG - 1) {
+                umma_commit(emptyA(hsa[k]));
+                umma_commit(emptyB(hsb[k]));
+              }
+            }
+          }
+        });
+        for (int k = 0; k < HB; k++) {
+          if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
+          if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
+        }
+        // ---- body: one block at a time (same group order: the instruction count and the pipe time are those of the
+        // plain A-plane order); the last block hands every group to the epilogue as soon as it has been issued
+        for (int ks = HB; ks < nk; ks++) {
+          long long tf0 = oz_clock();
           oz_wait(fullA(sa), pa);
           oz_wait(fullB(sb), pb);
-          t_full += clock64() - tf0; n_blk++;
+          t_full += oz_clock() - tf0; n_blk++;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const bool first_blk = ks == 0, last_blk = ks == nk - 1;
-          // descriptor low words of this block's ring slots, at this thread's K = 32 half
           const uint32_t aD0 = umma_desc_lo(sA + sa * C::A_UNIT_BYTES + 32 * H), bD0 = umma_desc_lo(sB + sb * C::B_BYTES + 32 * H);
-          if (first_blk && H == 1) {
-            oz_wait(touched, pt);   // A has issued the accumulate = 0 MMAs of this tile
+          const bool last_blk = ks == nk - 1;
+          if (last_blk) oz_trace(g, tr_i, 1000 * H + 40);   // last block: operands resident
+          if (G::NG == 1 && ks == 0) {
+            // first touch of the tile: the epilogue must have read the previous tile's levels (A), and A's accumulate = 0 MMAs
+            // must be in the pipe before B's first MMAs (B)
+            long long tl0 = oz_clock();
+            if (H == 0) { if (!(g.dbg_skip & 16)) oz_spin(lvl_empty(S - 1), pt ^ 1u); } else oz_spin(touched(0), pt);   // dbg_skip bit 4: timing experiment, results invalid
+            t_lvl += oz_clock() - tl0;
+            oz_trace(g, tr_i, 1000 * H + 10);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-#pragma unroll
-          for (int i = 0; i < S; i++) {
-#pragma unroll
-            for (int j0 = 0; j0 < S - i; j0 += C::MAX_STACK) {
-              const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
-              if (first_blk && i == 0 && H == 0) {
-                // first touch of levels j0 .. j0 + cnt - 1 in this tile: the epilogue must have read the previous tile's
-                // values of exactly these levels (it drains them lowest first, so the first stack rarely waits)
-                long long tl0 = clock64();
-#pragma unroll
-                for (int l = j0; l < j0 + cnt; l++) oz_wait(lvl_empty(l), pt ^ 1u);
-                t_lvl += clock64() - tl0;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              }
-              umma_i8_lo(tmem + (uint32_t)((i + j0) * NT), aD0 + (uint32_t)((i * C::PLANE_BYTES) >> 4),
-                         bD0 + (uint32_t)((j0 * (NT * kOzKB)) >> 4), umma_idesc_i8(kOzM, cnt * NT),
-                         (first_blk && H == 0 && i == 0) ? 0u : 1u);
-            }
-            if (first_blk && i == 0 && H == 0) mbar_arrive(touched);
-            if (last_blk) umma_commit(lvl_full(i));
-          }
+          for_groups([&](auto gq_tag) {
+            issue_group(gq_tag, aD0, bD0, G::NG == 1 && ks == 0 && H == 0, last_blk);
+            if (last_blk) commit_levels(gq_tag);
+          });
           umma_commit(emptyA(sa));
           umma_commit(emptyB(sb));
           if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
           if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
         }
+        oz_trace(g, tr_i, 1000 * H + 41);   // tile issued
         pt ^= 1u;
       }
-      if (g.prof && H == 0) {
+      if (OZ_PROF && g.prof && H == 0) {
         long long* p = g.prof + 8 * blockIdx.x;
-        p[0] = clock64() - t_begin; p[1] = t_full; p[2] = t_lvl; p[3] = t_q; p[4] = n_blk;
+        p[0] = oz_clock() - t_begin; p[1] = t_full; p[2] = t_lvl; p[3] = t_q; p[4] = n_blk;
       }
     }
   } else {
@@ -435,22 +628,23 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     const int etid = tid - 64;               // 0..255
     uint32_t pt = 0;
     long long t_wait = 0, t_tiles = 0, t_ld = 0, t_pre = 0;
+    int tr_i = 0;
     for (;;) {
-      oz_wait(qfull(qslot), qphase);
+      if (lane == 0) oz_wait_relaxed(qfull(qslot), qphase, 100);
+      __syncwarp();
       int item;
       asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(q_items + 4u * qslot) : "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(qempty(qslot));
       if (++qslot == kOzQueue) { qslot = 0; qphase ^= 1u; }
       if (item < 0) {
-        if (g.prof && tid == 64) { g.prof[8 * blockIdx.x + 5] = t_wait; g.prof[8 * blockIdx.x + 6] = t_tiles; g.prof[8 * blockIdx.x + 7] = t_ld; g.prof[8 * blockIdx.x + 4] += t_pre << 32; }
+        if (OZ_PROF && g.prof && tid == 64) { g.prof[8 * blockIdx.x + 5] = t_wait; g.prof[8 * blockIdx.x + 6] = t_tiles; g.prof[8 * blockIdx.x + 7] = t_ld; g.prof[8 * blockIdx.x + 4] += t_pre << 32; }
         break;
       }
       t_tiles++;
-      int jt, rb;
-      oz_decode_item(g, item, jt, rb);
+      const int jt = item >> 24, rb = item & 0xffffff;
       const int c0 = g.N - NT * (g.T - jt);
-      long long tp0 = clock64();
+      long long tp0 = oz_clock();
       // column scales of this tile (the previous tile's readers are past them: both barriers below order the rewrite after their last read)
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (etid < NT) {
@@ -459,38 +653,93 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         if (g.part_u) s_u[etid] = col >= 0 ? g.u[col] : 0.0;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      t_pre += clock64() - tp0;
-      // h_n = sum_l 2^-8l acc_l[n], lowest level first (the order in which the levels complete); a level's TMEM columns
-      // are handed back to the MMA issuer as soon as this warp has read them.  int32 -> double through the 2^52 + 2^31
+      t_pre += oz_clock() - tp0;
+      // h_n = sum_l 2^-8l acc_l[n] in Horner form from the TOP level down (the order in which the level groups complete,
+      // and the order in which the next tile's MMAs need them back); a level's TMEM columns are handed back to the MMA
+      // issuer as soon as this warp has read them.  int32 -> double through the 2^52 + 2^31
       // bias (one logic op + one DADD; I2F.F64 runs at a fraction of the FP64 rate).
+      // h_n = sum_l 2^-8l acc_l[n].  int32 -> double through the 2^52 + 2^31 bias (one logic op + one DADD; I2F.F64 runs at
+      // a fraction of the FP64 rate).  The loads are software-pipelined at HALF-level granularity: while one half (NQ
+      // columns) is folded on the FP64 pipe, the tcgen05.ld of the next half (and the poll for the next level) are in flight.
+      // The level loop is ROLLED (one trip = one level = two half steps, one per register buffer): seven unrolled copies of the
+      // fold are ~20 KB of code that every warp walks once per tile, and the instruction fetch stalls of that walk were 18 %
+      // of the epilogue's time.
+      constexpr int NQ = NH / 2;
+      static_assert(NH % 2 == 0 && NQ % 4 == 0, "half levels are loaded with x16 / x8 / x4 tcgen05.ld");
       double h[NH];
+      int32_t va[NQ], vb[NQ];
       const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NH);
-#pragma unroll
-      for (int l = 0; l < S; l++) {
-        long long tw0 = clock64();
-        oz_wait(lvl_full(l), pt);
-        t_wait += clock64() - tw0;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const double wl = __longlong_as_double((long long)(1023 - 8 * l) << 52);   // 2^-8l
-        int32_t v[NH];
-        long long tl0 = clock64();
-#pragma unroll
-        for (int c = 0; c + 16 <= NH; c += 16) tmem_ld16(trow + (uint32_t)(l * NT + c), v + c);   // the whole level in flight
-        if (NH % 16) tmem_ld8(trow + (uint32_t)(l * NT + (NH & ~15)), v + (NH & ~15));
-        tmem_ld_wait();
-        t_ld += clock64() - tl0;
-#pragma unroll
-        for (int c = 0; c + 16 <= NH; c += 16) tmem_ld_fence(v + c);
-        if (NH % 16) tmem_ld_fence8(v + (NH & ~15));
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      constexpr bool kDescending = OzGroups<S>::NG > 1;
+      auto level_of = [&](int t) { return kDescending ? S - 1 - t : t; };
+      auto poll_level = [&](int t) {
+        const int l = level_of(t);
+        long long tw0 = oz_clock();
+#if OZ_EPI_POLL == 0
+        if (lane == 0) { if (t == 0) oz_wait_relaxed(lvl_full(l), pt, 100); else oz_spin(lvl_full(l), pt); }   // one lane polls
+#elif OZ_EPI_POLL == 1
+        // experiment: one wait per tile (for the LAST level to complete), no polls afterwards
+        if (t == 0) { if (lane == 0) oz_wait_relaxed(lvl_full(kDescending ? 0 : S - 1), pt, 100); }
+#else
+        // experiment: wait for level 0, then for the last level, nothing afterwards
+        if (t == 0) { if (lane == 0) oz_wait_relaxed(lvl_full(l), pt, 100); }
+        else if (t == 1) { if (lane == 0) oz_spin(lvl_full(kDescending ? 0 : S - 1), pt); }
+#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive(lvl_empty(l));   // the level is in registers: its TMEM columns may be overwritten
+        t_wait += oz_clock() - tw0;
+        if (lane == 0 && t == 0) oz_trace(g, tr_i, 2000 + l + 100 * (warp - 2));   // first level complete (seen by this warp)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      };
+      auto start_half = [&](int t, int q, int32_t* dst) {
+        const uint32_t a = trow + (uint32_t)(level_of(t) * NT + q * NQ);
+        if (g.dbg_skip & 8) return;   // timing experiment: no TMEM loads (results invalid)
+        if (NQ >= 16) tmem_ld16(a, dst);
+        if (NQ % 16 >= 8) tmem_ld8(a + (NQ & ~15), dst + (NQ & ~15));
+        if (NQ % 8 >= 4) tmem_ld4(a + (NQ & ~7), dst + (NQ & ~7));
+      };
+      auto land_half = [&](int32_t* cur) {
+        long long tl0 = oz_clock();
+        tmem_ld_wait();
+        t_ld += oz_clock() - tl0;
+        if (NQ >= 16) tmem_ld_fence(cur);
+        if (NQ % 16 >= 8) tmem_ld_fence8(cur + (NQ & ~15));
+        if (NQ % 8 >= 4) tmem_ld_fence4(cur + (NQ & ~7));
+      };
+      auto fold_half = [&](int t, const int32_t* cur, double* hq) {
+        const double wl = kDescending ? 0.00390625 : __longlong_as_double((long long)(1023 - 8 * level_of(t)) << 52);   // 2^-8 | 2^-8l
+        if ((g.dbg_skip & 4) && t > 0) return;   // timing experiment: no FP64 work for the upper levels (results invalid)
 #pragma unroll
-        for (int n = 0; n < NH; n++) {
-          const double d = __hiloint2double(0x43300000, v[n] ^ (int)0x80000000) - 4503601774854144.0;
-          h[n] = (l == 0) ? d : fma(d, wl, h[n]);
+        for (int n = 0; n < NQ; n++) {
+          const double d = __hiloint2double(0x43300000, cur[n] ^ (int)0x80000000) - 4503601774854144.0;
+          hq[n] = kDescending ? fma(hq[n], wl, d) : fma(d, wl, hq[n]);   // Horner from the top | h += 2^-8l acc_l
         }
+      };
+#pragma unroll
+      for (int n = 0; n < NH; n++) h[n] = 0.0;
+      poll_level(0);
+      start_half(0, 0, va);
+#pragma unroll 1
+      for (int t = 0; t < S; t++) {
+        const int l = level_of(t);
+        land_half(va);
+        start_half(t, 1, vb);
+        fold_half(t, va, h);
+        land_half(vb);
+        // hand-over: only the level the issuer polls for (the last one read of a group); the others are implied
+        bool handover = !kDescending && l == S - 1;
+        if (kDescending) {
+#pragma unroll
+          for (int q = 0; q < OzGroups<S>::NG; q++) handover = handover || l == OzGroups<S>::lo(q);
+        }
+        if (handover) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(lvl_empty(l));   // the group is in registers: its TMEM columns may be overwritten
+        }
+        if (lane == 0 && t == S - 1) oz_trace(g, tr_i, 2010 + l + 100 * (warp - 2));   // last level in registers
+        if (t + 1 < S) { poll_level(t + 1); start_half(t + 1, 0, va); }
+        fold_half(t, vb, h + NQ);
       }
+      if (lane == 0) oz_trace(g, tr_i, 2020 + 100 * (warp - 2));   // all levels recombined
       pt ^= 1u;
       double acc = 0.0;
 #pragma unroll

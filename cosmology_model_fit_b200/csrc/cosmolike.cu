@@ -663,19 +663,21 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   g.B = rows; g.N = n; g.T = c->oz_T; g.n_rb = (int)((rows + kOzM - 1) / kOzM);
   g.part = c->d_part; g.rowscale = c->d_rscale; g.colscale = c->d_wscale; g.counter = c->d_counter;
   g.part_u = moments ? c->d_part_u : nullptr; g.u = c->d_u;
-  g.dbg_skip = (c->opt_dbg >> 4) & 3;   // dbg bits 4, 5: skip the W / R plane loads (timing experiments, results invalid)
-  g.prof = nullptr;
+  g.dbg_skip = (c->opt_dbg >> 4) & 31;   // dbg bits 4, 5: skip the W / R plane loads (timing experiments, results invalid)
+  g.prof = nullptr; g.trace = nullptr;
   if (c->opt_dbg & 4) {   // cycle counters of the contraction kernel, printed after the launch (profiling only)
-    rc = ensure_scratch(c, 8 * 8 * 1024);
+    rc = ensure_scratch(c, 8 * 8 * 1024 + 8 * 16384);
     if (rc != CL_OK) return rc;
     g.prof = reinterpret_cast<long long*>(c->d_scratch);
-    CUDA_TRY(c, cudaMemsetAsync(g.prof, 0, 8 * 8 * 1024, st));
+    CUDA_TRY(c, cudaMemsetAsync(g.prof, 0, 8 * 8 * 1024 + 8 * 16384, st));
+    if (c->opt_dbg & 8) g.trace = g.prof + 8 * 1024;   // event trace of CTA 0, written to $COSMOLIKE_TRACE (default oz_trace.txt)
   }
   // row blocks per L2 group: the S digit planes of a group's rows (+ the W planes) stay L2-resident across its column tiles
   int grp = c->opt_group_rb > 0 ? c->opt_group_rb : (int)std::max<int64_t>(8, ((28LL << 20) / ((int64_t)kOzM * c->oz_ld * S)) & ~7LL);
   g.group_rb = std::min(grp, g.n_rb);
   CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
   const int64_t items = (int64_t)g.n_rb * g.T;
+  if (items >= (1LL << 30) || g.n_rb >= (1 << 24)) return fail(c, CL_E_INVALID, "tcgen05 engine: too many tiles in one pass (lower max_rows_per_pass)");
   const int grid = (int)std::min<int64_t>(items, c->opt_gemm_ctas > 0 ? c->opt_gemm_ctas : c->sm_count);
   if (S == 5) oz_launch<5>(grid, st, tmRs, c->tmWs, g);
   else if (S == 6) oz_launch<6>(grid, st, tmRs, c->tmWs, g);
@@ -693,6 +695,15 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
     fprintf(stderr, "[oz prof] epilogue warp: tcgen05.ld+wait %.0f cyc, column-scale prologue %.0f cyc\n", s[7], pre);
     fprintf(stderr, "[oz prof] per CTA: total %.0f cyc, wait smem-full %.0f (%.1f%%), wait level-empty %.0f (%.1f%%), wait queue %.0f, k-blocks %.0f | epilogue warp: wait level-full %.0f (%.1f%%), tiles %.0f\n",
             s[0], s[1], 100 * s[1] / s[0], s[2], 100 * s[2] / s[0], s[3], s[4], s[5], 100 * s[5] / s[0], s[6]);
+    if (g.trace) {
+      std::vector<long long> t(1 + 11 * kOzTraceCap);
+      CUDA_TRY(c, cudaMemcpy(t.data(), g.trace, t.size() * 8, cudaMemcpyDeviceToHost));
+      const char* path = getenv("COSMOLIKE_TRACE");
+      if (FILE* f = fopen(path ? path : "oz_trace.txt", "w")) {
+        for (size_t i = 1; i < t.size(); i++) if (t[i]) fprintf(f, "%lld %lld\n", t[i] >> 44, t[i] & ((1LL << 44) - 1));
+        fclose(f);
+      }
+    }
   }
   return CL_OK;
 }

@@ -346,6 +346,25 @@ __global__ void __launch_bounds__(128, 1) k_sched(int iters, long long* cycles) 
     uint32_t ph = 0;
     for (int it = 0; it < iters; it++) {
       int slot = 0;
+      if constexpr (VARIANT == 7 || VARIANT == 8) {
+        // level-group-major order (groups from the top level down): 7 = two groups, 8 = three groups
+        constexpr int NG = VARIANT == 7 ? 2 : 3;
+#pragma unroll
+        for (int gq = 0; gq < NG; gq++) {
+          const int la = NG == 2 ? (gq == 0 ? (S + 1) / 2 : 0) : (S == 7 ? (gq == 0 ? 5 : gq == 1 ? 3 : 0) : (gq == 0 ? 4 : gq == 1 ? 2 : 0));
+          const int lb = gq == 0 ? S - 1 : (NG == 2 ? (S + 1) / 2 - 1 : (S == 7 ? (gq == 1 ? 4 : 2) : (gq == 1 ? 3 : 1)));
+#pragma unroll
+          for (int i = 0; i <= lb; i++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int jlo = la - i > 0 ? la - i : 0;
+              const int jhi = lb - i < S - 1 - i ? lb - i : S - 1 - i;
+              if (jhi >= jlo)
+                umma_i8(tmem + (uint32_t)((i + jlo) * NT), umma_desc(sA + i * 128 * KB + 32 * h, KB), umma_desc(sB + jlo * NT * KB + 32 * h, KB),
+                        umma_idesc_i8(128, (jhi - jlo + 1) * NT), 1u);
+            }
+        }
+      } else
 #pragma unroll
       for (int i = 0; i < S; i++)
 #pragma unroll
@@ -406,7 +425,12 @@ int main(int argc, char** argv) {
   ok &= run_check<128, 80, 2>(256);
   ok &= run_check<32, 256, 1>(128);
   if (!ok) { printf("descriptor check FAILED; skipping rates\n"); return 3; }
-  if (argc > 2) { int v = atoi(argv[2]); if (v == 6) run_sched<64, 7, 6>(nsm); fflush(stdout); return 0; }
+  if (argc > 2) {
+    int v = atoi(argv[2]);
+    if (v == 6) run_sched<64, 7, 6>(nsm);
+    if (v == 7) { run_sched<64, 7, 0>(nsm); run_sched<64, 7, 7>(nsm); run_sched<64, 7, 8>(nsm); run_sched<80, 6, 0>(nsm); run_sched<80, 6, 7>(nsm); run_sched<80, 6, 8>(nsm); }
+    fflush(stdout); return 0;
+  }
   run_sched<64, 7, 0>(nsm); run_sched<64, 7, 1>(nsm); run_sched<64, 7, 2>(nsm); run_sched<64, 7, 3>(nsm); run_sched<64, 7, 4>(nsm); run_sched<64, 7, 5>(nsm);
   run_sched<80, 6, 0>(nsm); run_sched<80, 6, 1>(nsm); run_sched<80, 6, 2>(nsm);
   fflush(stdout);
