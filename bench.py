@@ -36,7 +36,7 @@ UNIT = "evals/s"
 #: tcgen05.mma kind::i8 issue rate measured on this pool's B200 (profiles/r02_ubench_umma_i8.log), int8 TOP/s
 I8_PEAK_TOPS = 4485.0
 #: DRAM bytes per launch of k_chi2_ozaki<S> from ncu --set full (profiles/), keyed by (planes, N, B)
-OZ_DRAM_BYTES = {(7, 1701, 65536): 0.925e9}   # profiles/r02g_ncu_full_summary.txt: 0.893e9 read + 0.032e9 written
+OZ_DRAM_BYTES = {(7, 1701, 65536): 0.910e9}   # profiles/r02m_ncu_full_summary.txt: 0.879e9 read + 0.031e9 written
 
 
 def build_spec(n_sn):

@@ -9,10 +9,15 @@
 // recombined in FP64 by the epilogue: y_bn = 2^(eR_b + eW_n - 12) sum_l 2^-8l acc_l.  With S = 6 (46 bits, 21 slice
 // products) the result agrees with the FP64 contraction to ~3e-13 relative (|d chi2| ~ 3e-9 at chi2 ~ 4e4).
 //
-// Kernel: persistent CTAs, 10 warps.  warp 0 = scheduler + TMA producer (3-D boxes {64 B of k, rows, S planes}, 64-byte
-// swizzle, separate shared-memory rings for the R planes (A, 128 rows) and the W planes (B, NT rows)); warp 1 = TMEM
-// allocator + single-thread MMA issuer (one MMA covers up to 256 / NT stacked planes of W); warps 2-9 = epilogue
-// (tcgen05.ld one level at a time, FP64 recombination, row sum of squares, per-level hand-over to the MMA issuer).
+// Kernel: persistent CTAs, 11 warps.  warp 0 = scheduler + TMA producer (3-D boxes {64 B of k, rows, S planes}, 64-byte
+// swizzle, separate shared-memory rings for the R planes (A, 128 rows) and the W planes (B, NT rows); the item counter is
+// read one tile ahead and the decoded item goes through the queue); warps 1 and 10 = MMA issuers (one thread each, one
+// K = 32 half of every block each; one MMA covers up to 256 / NT stacked planes of W); warps 2-9 = epilogue (tcgen05.ld
+// in half-level steps, FP64 recombination, row sum of squares; two barrier waits per tile and ONE hand-over arrival).
+// Hand-over facts measured with the in-kernel event trace (OZ_PROF=1, `dbg` bit 3, tools/oz_trace_view.py) and
+// tools/ubench_mbar.cu: an mbarrier poll costs 13 cycles even with ten other warps polling; a tcgen05.fence costs an
+// epilogue warp ~300 cycles, so fences only follow actual waits; the levels of a tile complete in order, so the epilogue
+// waits for level 0 and then for the last level, and the issuer polls one barrier (the level read last), not S.
 // Triangular structure as in chi2_gemm.cuh: column tiles aligned to the end of the matrix, k stops at the diagonal
 // block (the zeros of W above the diagonal inside that block are simply multiplied: ~4 % of the executed products).
 #pragma once
@@ -46,29 +51,6 @@ template <int S> struct OzCfg {
   static constexpr int SMEM = 1024 + A_RING + B_RING + 2 * NT * 8 + 384;
   static constexpr int FRAC_BITS = 6 + 8 * (S - 1);
   static constexpr int MAX_STACK = 256 / NT;   // digit planes of W one MMA may cover (N <= 256)
-};
-
-// Level groups of the phased MMA order (see the issuer): groups are listed from the TOP level down, every group holds at
-// most MAX_STACK levels so that the A_0 stack of a group touches all of its levels with one instruction.
-#ifndef OZ_PHASES
-#define OZ_PHASES 1
-#endif
-#ifndef OZ_HEAD
-#define OZ_HEAD 2
-#endif
-constexpr int kOzHead = OZ_HEAD;   // k blocks of a new tile issued group-major while the epilogue still drains the previous tile
-template <int S> struct OzGroups {
-#if OZ_PHASES == 3
-  static constexpr int NG = 3;
-  __host__ __device__ static constexpr int lo(int g) { return S == 7 ? (g == 0 ? 5 : g == 1 ? 3 : 0) : S == 6 ? (g == 0 ? 4 : g == 1 ? 2 : 0) : (g == 0 ? 3 : g == 1 ? 1 : 0); }
-#elif OZ_PHASES == 2
-  static constexpr int NG = 2;
-  __host__ __device__ static constexpr int lo(int g) { return S == 7 ? (g == 0 ? 4 : 0) : S == 6 ? (g == 0 ? 3 : 0) : (g == 0 ? 3 : 1); }
-#else
-  static constexpr int NG = 1;
-  __host__ __device__ static constexpr int lo(int) { return 0; }
-#endif
-  __host__ __device__ static constexpr int hi(int g) { return g == 0 ? S - 1 : lo(g - 1) - 1; }
 };
 
 struct OzArgs {
@@ -190,12 +172,6 @@ __device__ __forceinline__ void oz_wait_relaxed(uint32_t bar, uint32_t parity, u
   }
   __trap();
 }
-#ifndef OZ_EPI_POLL
-#define OZ_EPI_POLL 2
-#endif
-#ifndef OZ_MERGE_TOP
-#define OZ_MERGE_TOP 0
-#endif
 #ifndef OZ_SPIN_NS
 #define OZ_SPIN_NS 40
 #endif
@@ -357,13 +333,13 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   auto lvl_empty = [&](int l) { return bars + 8u * (31 + l); };   // level l has been read by the eight epilogue warps
   const uint32_t q_items = bars + 8u * 38;   // int[kOzQueue]
   const uint32_t tslot = bars + 8u * 40;
-  auto touched = [&](int gq) { return bars + 8u * (41 + gq); };   // issuer A has issued the first-touch MMAs of level group gq
+  const uint32_t touched = bars + 8u * 41;   // issuer A has issued the first-touch MMAs of the tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::A_UNITS; s++) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 2); }   // released by both issuers' commits
     for (int s = 0; s < kOzBStages; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 2); }
-    for (int q = 0; q < OzGroups<S>::NG; q++) mbar_init(touched(q), 1);
+    mbar_init(touched, 1);
     for (int s = 0; s < kOzQueue; s++) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 10); }   // 2 MMA threads + 8 epilogue warps
     for (int l = 0; l < S; l++) { mbar_init(lvl_full(l), 2); mbar_init(lvl_empty(l), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -458,51 +434,24 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
     // from shared memory once each (shared-memory bandwidth, not the tensor pipe, bounds the narrow form).  Round i completes
     // level i: in the last k block each level is committed on its own barrier as soon as its round has been issued, so the
     // epilogue overlaps the rest of the block.
-    // A tcgen05.mma costs its issuing thread ~100 cycles of dependent uniform-datapath work while the pipe needs ~90 per
-    // instruction of this schedule, so the issue is split: thread A (warp 1) issues the first K = 32 half of every block,
-    // thread B (warp kOzIssuerB) the second.  Integer accumulation commutes; the only order that matters is that A's
+    // The MMA queue is shallow: an issuing thread is held back until the pipe has taken its previous MMAs, and between two
+    // MMAs it spends ~100 cycles of dependent uniform-datapath work while the pipe needs ~90 per instruction of this schedule.
+    // The issue is therefore split: thread A (warp 1) issues the first K = 32 half of every block, thread B (warp kOzIssuerB)
+    // the second (tensor pipe active 67.8 % -> 70.6 % of the kernel).  Integer accumulation commutes; the only order that matters is that A's
     // first-touch MMAs of a tile (accumulate = 0) enter the pipe before B's first MMAs of that tile: B waits for `touched`,
     // on which A arrives after issuing round 0 of the tile's first block (the pipe executes in issue order).  Every
     // tcgen05.commit only tracks the MMAs of its own thread, so the release barriers count two arrivals.
+    // ONE copy of the issue code serves every block, both issuers and every ring position (run-time descriptors): a variant
+    // with compile-time ring slots (12 instantiations, plain R2UR instead of the ELECT / R2UR.BROADCAST loop around every
+    // tcgen05.mma) has half the instructions per MMA and is 3-4 % SLOWER - the issue rate is set by the pipe's back-pressure
+    // (the MMA queue is shallow), not by the instruction count, and the larger code costs instruction-cache misses.
     if (lane == 0) {
-      using G = OzGroups<S>;
       const int H = warp == 1 ? 0 : 1;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0, pt = 0;
       long long t_full = 0, t_lvl = 0, t_q = 0, n_blk = 0;
       int tr_i = 0;
       const long long t_begin = oz_clock();
-      // all MMAs of level group gq for one k block (this thread's K = 32 half); `zero`: first touch of the tile
-      auto issue_group = [&](auto gq_tag, uint32_t aD0, uint32_t bD0, bool zero, bool last) {
-        constexpr int gq = decltype(gq_tag)::value;
-        constexpr int la = G::lo(gq), lb = G::hi(gq);
-        static_assert(G::NG == 1 || lb - la + 1 <= C::MAX_STACK, "a level group must fit one stacked MMA");
-#pragma unroll
-        for (int i = 0; i <= lb; i++) {
-          const int jlo = la - i > 0 ? la - i : 0;
-          const int jhi = lb - i < S - 1 - i ? lb - i : S - 1 - i;
-#pragma unroll
-          for (int j0 = jlo; j0 <= jhi; j0 += C::MAX_STACK) {
-            const int cnt = (jhi - j0 + 1) < C::MAX_STACK ? (jhi - j0 + 1) : C::MAX_STACK;
-            umma_i8_lo(tmem + (uint32_t)((i + j0) * NT), aD0 + (uint32_t)((i * C::PLANE_BYTES) >> 4),
-                       bD0 + (uint32_t)((j0 * (NT * kOzKB)) >> 4), umma_idesc_i8(kOzM, cnt * NT), (zero && i == 0) ? 0u : 1u);
-          }
-          if (zero && i == 0) mbar_arrive(touched(gq));       // the accumulate = 0 MMAs of this group are in the pipe: B may follow
-          if (G::NG == 1 && last) umma_commit(lvl_full(i));   // one group: round i completes level i
-          if (zero && (i == 0 || i == S - 1)) oz_trace(g, tr_i, 60 + i);
-        }
-      };
-      auto commit_levels = [&](auto gq_tag) {
-        constexpr int gq = decltype(gq_tag)::value;
-        if constexpr (G::NG > 1)
-#pragma unroll
-          for (int l = G::hi(gq); l >= G::lo(gq); l--) umma_commit(lvl_full(l));
-      };
-      auto for_groups = [&](auto&& f) {
-        f(std::integral_constant<int, 0>{});
-        if constexpr (G::NG > 1) f(std::integral_constant<int, 1>{});
-        if constexpr (G::NG > 2) f(std::integral_constant<int, 2>{});
-      };
       for (;;) {
         long long tq0 = oz_clock();
         oz_wait(qfull(qslot), qphase);
@@ -512,101 +461,43 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         mbar_arrive(qempty(qslot));
         if (++qslot == kOzQueue) { qslot = 0; qphase ^= 1u; }
         if (item < 0) break;
-        const int jt = item >> 24, rb = item & 0xffffff;
+        const int jt = item >> 24;
         const int c0 = g.N - NT * (g.T - jt);
         const int nk = (c0 + NT + kOzKB - 1) / kOzKB;
-        // ---- head: the first HB blocks, group-major.  Group gq only needs ITS levels back from the epilogue (which drains
-        // the previous tile from the top level down), so the MMAs of the upper groups run under the rest of the drain.
         oz_trace(g, tr_i, 1000 * H + 1);   // tile start (item known)
-        const int HB = G::NG == 1 ? 0 : (nk < kOzHead ? nk : kOzHead);   // one group: no head, one copy of the issue code (hot in the instruction cache)
-        uint32_t aD[kOzHead], bD[kOzHead];
-        int hsa[kOzHead], hsb[kOzHead];
-        {
-          int xa = sa, xb = sb;
-          uint32_t ya = pa, yb = pb;
-#pragma unroll
-          for (int k = 0; k < kOzHead; k++) {
-            hsa[k] = xa; hsb[k] = xb;
-            aD[k] = umma_desc_lo(sA + xa * C::A_UNIT_BYTES + 32 * H);
-            bD[k] = umma_desc_lo(sB + xb * C::B_BYTES + 32 * H);
-            if (k < HB) {
-              if (++xa == C::A_UNITS) { xa = 0; ya ^= 1u; }
-              if (++xb == kOzBStages) { xb = 0; yb ^= 1u; }
-            }
-          }
-          // the parities of the head's slots are consumed below through (pa, pb) advanced in step
-          (void)ya; (void)yb;
-        }
-        if constexpr (G::NG > 1) for_groups([&](auto gq_tag) {
-          constexpr int gq = decltype(gq_tag)::value;
-          long long tl0 = oz_clock();
-          if (H == 0) {
-            {
-              // the epilogue warps hand the levels back in a fixed order, so the barrier of the level they read LAST implies
-              // the others (a poll of a completed mbarrier still costs ~300 cycles while other warps are polling)
-              constexpr int l_last = G::NG > 1 ? G::lo(gq) : S - 1;
-              oz_spin(lvl_empty(l_last), pt ^ 1u);
-            }   // previous tile's values are in registers
-          } else {
-            oz_spin(touched(gq), pt);   // A has issued the accumulate = 0 MMA of this group
-          }
-          t_lvl += oz_clock() - tl0;
-          oz_trace(g, tr_i, 1000 * H + 10 + gq);   // group gq released to this issuer
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          int wa = sa, wb = sb;
-          uint32_t qa = pa, qb = pb;
-#pragma unroll
-          for (int k = 0; k < kOzHead; k++) {
-            if (k < HB) {
-              if (gq == 0) {
-                long long tf0 = oz_clock();
-                oz_wait(fullA(wa), qa);
-                oz_wait(fullB(wb), qb);
-                t_full += oz_clock() - tf0; n_blk++;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (++wa == C::A_UNITS) { wa = 0; qa ^= 1u; }
-                if (++wb == kOzBStages) { wb = 0; qb ^= 1u; }
-              }
-              issue_group(gq_tag, aD[k], bD[k], k == 0 && H == 0, k == nk - 1);
-              oz_trace(g, tr_i, 1000 * H + 20 + 4 * k + gq);   // head: group gq of block k issued
-              if (k == nk - 1) commit_levels(gq_tag);
-              if (gq == G::NG - 1) {
-                umma_commit(emptyA(hsa[k]));
-                umma_commit(emptyB(hsb[k]));
-              }
-            }
-          }
-        });
-        for (int k = 0; k < HB; k++) {
-          if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
-          if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
-        }
-        // ---- body: one block at a time (same group order: the instruction count and the pipe time are those of the
-        // plain A-plane order); the last block hands every group to the epilogue as soon as it has been issued
-        for (int ks = HB; ks < nk; ks++) {
+        for (int ks = 0; ks < nk; ks++) {
           long long tf0 = oz_clock();
           oz_wait(fullA(sa), pa);
           oz_wait(fullB(sb), pb);
           t_full += oz_clock() - tf0; n_blk++;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t aD0 = umma_desc_lo(sA + sa * C::A_UNIT_BYTES + 32 * H), bD0 = umma_desc_lo(sB + sb * C::B_BYTES + 32 * H);
-          const bool last_blk = ks == nk - 1;
+          const bool first_blk = ks == 0, last_blk = ks == nk - 1;
           if (last_blk) oz_trace(g, tr_i, 1000 * H + 40);   // last block: operands resident
-          if (G::NG == 1 && ks == 0) {
-            // first touch of the tile: the epilogue must have read the previous tile's levels (A), and A's accumulate = 0 MMAs
-            // must be in the pipe before B's first MMAs (B)
+          if (first_blk) {
+            // first touch of the tile: the epilogue must have read the previous tile's levels (A polls the barrier of the
+            // level that is read last), and A's accumulate = 0 MMAs must be in the pipe before B's first MMAs (B polls `touched`)
             long long tl0 = oz_clock();
-            if (H == 0) { if (!(g.dbg_skip & 16)) oz_spin(lvl_empty(S - 1), pt ^ 1u); } else oz_spin(touched(0), pt);   // dbg_skip bit 4: timing experiment, results invalid
+            if (H == 0) oz_spin(lvl_empty(S - 1), pt ^ 1u); else oz_spin(touched, pt);
             t_lvl += oz_clock() - tl0;
             oz_trace(g, tr_i, 1000 * H + 10);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          for_groups([&](auto gq_tag) {
-            issue_group(gq_tag, aD0, bD0, G::NG == 1 && ks == 0 && H == 0, last_blk);
-            if (last_blk) commit_levels(gq_tag);
-          });
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // descriptor low words of this block's ring slots, at this thread's K = 32 half
+          const uint32_t aD0 = umma_desc_lo(sA + sa * C::A_UNIT_BYTES + 32 * H), bD0 = umma_desc_lo(sB + sb * C::B_BYTES + 32 * H);
+          const bool zero = H == 0 && first_blk;
+#pragma unroll
+          for (int i = 0; i < S; i++) {
+#pragma unroll
+            for (int j0 = 0; j0 < S - i; j0 += C::MAX_STACK) {
+              const int cnt = (S - i - j0) < C::MAX_STACK ? (S - i - j0) : C::MAX_STACK;
+              umma_i8_lo(tmem + (uint32_t)((i + j0) * NT), aD0 + (uint32_t)((i * C::PLANE_BYTES) >> 4),
+                         bD0 + (uint32_t)((j0 * (NT * kOzKB)) >> 4), umma_idesc_i8(kOzM, cnt * NT), (zero && i == 0) ? 0u : 1u);
+            }
+            if (zero && i == 0) mbar_arrive(touched);   // the accumulate = 0 MMAs are in the pipe: B may follow
+            if (last_blk) umma_commit(lvl_full(i));     // round i completes level i
+          }
           umma_commit(emptyA(sa));
           umma_commit(emptyB(sb));
+          if (first_blk) oz_trace(g, tr_i, 1000 * H + 20);   // first block issued
           if (++sa == C::A_UNITS) { sa = 0; pa ^= 1u; }
           if (++sb == kOzBStages) { sb = 0; pb ^= 1u; }
         }
@@ -669,24 +560,17 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       double h[NH];
       int32_t va[NQ], vb[NQ];
       const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NH);
-      constexpr bool kDescending = OzGroups<S>::NG > 1;
-      auto level_of = [&](int t) { return kDescending ? S - 1 - t : t; };
+      auto level_of = [&](int t) { return t; };   // levels are read in the order in which they complete
+      // Two waits per tile: level 0 (the epilogue starts under the MMAs of the tile's last block) and, before level 1 is
+      // read, the LAST level (levels complete in order, so nothing needs polling afterwards).  __syncwarp and the tcgen05
+      // fence only follow an actual wait.
       auto poll_level = [&](int t) {
-        const int l = level_of(t);
+        if (t > 1) return;
         long long tw0 = oz_clock();
-#if OZ_EPI_POLL == 0
-        if (lane == 0) { if (t == 0) oz_wait_relaxed(lvl_full(l), pt, 100); else oz_spin(lvl_full(l), pt); }   // one lane polls
-#elif OZ_EPI_POLL == 1
-        // experiment: one wait per tile (for the LAST level to complete), no polls afterwards
-        if (t == 0) { if (lane == 0) oz_wait_relaxed(lvl_full(kDescending ? 0 : S - 1), pt, 100); }
-#else
-        // experiment: wait for level 0, then for the last level, nothing afterwards
-        if (t == 0) { if (lane == 0) oz_wait_relaxed(lvl_full(l), pt, 100); }
-        else if (t == 1) { if (lane == 0) oz_spin(lvl_full(kDescending ? 0 : S - 1), pt); }
-#endif
+        if (lane == 0) { if (t == 0) oz_wait_relaxed(lvl_full(0), pt, 100); else oz_spin(lvl_full(S - 1), pt); }   // one lane polls
         __syncwarp();
         t_wait += oz_clock() - tw0;
-        if (lane == 0 && t == 0) oz_trace(g, tr_i, 2000 + l + 100 * (warp - 2));   // first level complete (seen by this warp)
+        if (lane == 0 && t == 0) oz_trace(g, tr_i, 2000 + 100 * (warp - 2));   // first level complete (seen by this warp)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       };
       auto start_half = [&](int t, int q, int32_t* dst) {
@@ -705,12 +589,12 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         if (NQ % 8 >= 4) tmem_ld_fence4(cur + (NQ & ~7));
       };
       auto fold_half = [&](int t, const int32_t* cur, double* hq) {
-        const double wl = kDescending ? 0.00390625 : __longlong_as_double((long long)(1023 - 8 * level_of(t)) << 52);   // 2^-8 | 2^-8l
+        const double wl = __longlong_as_double((long long)(1023 - 8 * level_of(t)) << 52);   // 2^-8l
         if ((g.dbg_skip & 4) && t > 0) return;   // timing experiment: no FP64 work for the upper levels (results invalid)
 #pragma unroll
         for (int n = 0; n < NQ; n++) {
           const double d = __hiloint2double(0x43300000, cur[n] ^ (int)0x80000000) - 4503601774854144.0;
-          hq[n] = kDescending ? fma(hq[n], wl, d) : fma(d, wl, hq[n]);   // Horner from the top | h += 2^-8l acc_l
+          hq[n] = fma(d, wl, hq[n]);   // h += 2^-8l acc_l
         }
       };
 #pragma unroll
@@ -724,16 +608,11 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
         start_half(t, 1, vb);
         fold_half(t, va, h);
         land_half(vb);
-        // hand-over: only the level the issuer polls for (the last one read of a group); the others are implied
-        bool handover = !kDescending && l == S - 1;
-        if (kDescending) {
-#pragma unroll
-          for (int q = 0; q < OzGroups<S>::NG; q++) handover = handover || l == OzGroups<S>::lo(q);
-        }
-        if (handover) {
+        // hand-over: the issuer polls the barrier of the level that is read last; the other levels are implied
+        if (l == S - 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(lvl_empty(l));   // the group is in registers: its TMEM columns may be overwritten
+          if (lane == 0) mbar_arrive(lvl_empty(l));   // the tile is in registers: its TMEM columns may be overwritten
         }
         if (lane == 0 && t == S - 1) oz_trace(g, tr_i, 2010 + l + 100 * (warp - 2));   // last level in registers
         if (t + 1 < S) { poll_level(t + 1); start_half(t + 1, 0, va); }

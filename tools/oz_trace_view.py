@@ -4,7 +4,7 @@ import sys
 ev = [tuple(map(int, l.split())) for l in open(sys.argv[1])]
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-names = {70: "** last level complete (MMAs of the tile done)", 1: "A tile", 40: "A last-blk", 41: "A issued", 1001: "B tile", 1040: "B last-blk", 1041: "B issued", }
+names = {10: "A handover seen", 1010: "B touched seen", 20: "A first block issued", 1020: "B first block issued", 70: "** last level complete (MMAs of the tile done)", 1: "A tile", 40: "A last-blk", 41: "A issued", 1001: "B tile", 1040: "B last-blk", 1041: "B issued", }
 for g in range(3):
     names[10 + g] = f"A grp{g} free"; names[1010 + g] = f"B grp{g} go"
     for k in range(2):
