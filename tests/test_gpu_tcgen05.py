@@ -172,3 +172,23 @@ def test_stage3_split_timing(engines):
         assert (planes > 0.005) == bool(slices)
     hist = engines("sn_pantheon", 7).stage3_split(3)
     assert hist.shape[1] == 2 and len(hist) >= 1
+
+
+@pytest.mark.parametrize("n", [65, 100, 129, 191, 640, 1000])
+def test_ragged_sn_counts_vs_oracle(n):
+    """SN blocks whose size is no multiple of anything in the kernel (column tile NT = 64 / 80, k block 64, TMA box 128
+    rows): the first column tile starts at a negative column (TMA zero fill), the plane pitch is padded, the last k block is
+    partial.  Pantheon+ rows 0..n-1 with the matching corner of the covariance, all three engines against the CPU oracle."""
+    import oracle.oracle as O
+    from cosmology_model_fit_b200 import Engine, datasets, fits
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    z, zh, mb, cov = datasets.pantheon_plus(cut=False)
+    sub = fits.sn_pantheon((z[:n].copy(), zh[:n].copy(), mb[:n].copy(), np.ascontiguousarray(cov[:n, :n])))
+    theta = uniform_theta(sub.bounds, 257, seed=n)
+    want = O.Oracle(sub).chi_squared(theta, nthreads=0)
+    with Engine(sub) as e:
+        for slices in (0, 6, 7):
+            e.set_option("chi2_engine", 1 if slices else 0)
+            if slices:
+                e.set_option("chi2_slices", slices)
+            close(e.chi_squared(theta), want, slices or 7)
