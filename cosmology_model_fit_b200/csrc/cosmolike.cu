@@ -806,7 +806,8 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
     rc = ensure_pinned(c, rows * nd, rows * 4);
     if (rc != CL_OK) return rc;
     if (r0 > 0) CUDA_TRY(c, cudaStreamSynchronize(st));  // staging buffers are reused
-    for (int64_t i = 0; i < rows; i++) memcpy(c->h_theta + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
+    if (ld == nd) memcpy(c->h_theta, theta + r0 * ld, (size_t)rows * nd * sizeof(double));   // contiguous rows: one copy
+    else for (int64_t i = 0; i < rows; i++) memcpy(c->h_theta + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_theta, c->h_theta, rows * nd * sizeof(double), cudaMemcpyHostToDevice, st));
     double* d_res = c->d_out;
     if (width == 1) rc = run_pass(c, c->d_theta, rows, nd, what, d_res, nullptr, false, st, r0 == 0);
