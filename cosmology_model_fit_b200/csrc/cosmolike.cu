@@ -52,7 +52,7 @@ struct cl_ctx {
   double *h_theta = nullptr, *h_out = nullptr;  // pinned
   int64_t h_theta_cap = 0, h_out_cap = 0;
   int64_t launches = 0;
-  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0;
+  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0, opt_s12_lean = 1;
   int* d_counter = nullptr;
   // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
   int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_slice_tpb = 128;
@@ -221,12 +221,19 @@ static bool lower_factor_from_invcov(const double* Cinv, int n, std::vector<doub
 
 // ---- kernel dispatch over the (family, dark-energy) instantiations ----
 typedef void (*S12Kernel)(const DevSpec, const Stage12Args);
-static S12Kernel pick_s12(int fam, int de) {
-#define CASE(F, D) if (fam == F && de == D) return k_friedmann_residuals<F, D>;
+static S12Kernel pick_s12(int fam, int de, bool lean = false) {
+#define CASE(F, D) if (fam == F && de == D) return k_friedmann_residuals<F, D, 0>;
+#define LEAN_CASE(D) if (lean && fam == CL_FAMILY_LATE && de == D) return k_friedmann_residuals<CL_FAMILY_LATE, D, 1>;
+  LEAN_CASE(CL_DE_LCDM) LEAN_CASE(CL_DE_WCDM) LEAN_CASE(CL_DE_CPL) LEAN_CASE(CL_DE_THAWING)
   CASE(CL_FAMILY_LATE, CL_DE_LCDM) CASE(CL_FAMILY_LATE, CL_DE_WCDM) CASE(CL_FAMILY_LATE, CL_DE_CPL) CASE(CL_FAMILY_LATE, CL_DE_THAWING)
   CASE(CL_FAMILY_FULL, CL_DE_LCDM) CASE(CL_FAMILY_FULL, CL_DE_WCDM) CASE(CL_FAMILY_FULL, CL_DE_CPL) CASE(CL_FAMILY_FULL, CL_DE_THAWING)
 #undef CASE
+#undef LEAN_CASE
   return nullptr;
+}
+// the lean instantiation serves plain evaluations of a large SN block alone (see friedmann.cuh)
+static bool s12_lean(const DevSpec& d, int mode) {
+  return mode == MODE_EVAL && d.family == CL_FAMILY_LATE && d.n_sn > 0 && !d.sn_small && d.n_bao == 0 && d.n_cc == 0 && d.cmb_mode == CL_CMB_NONE;
 }
 
 static int validate(const cl_spec* s) {
@@ -493,6 +500,7 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
   // kernel attributes
   S12Kernel k12 = pick_s12(d.family, d.de_model);
   CTRY(cudaFuncSetAttribute(k12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
+  if (s12_lean(d, MODE_EVAL)) CTRY(cudaFuncSetAttribute(pick_s12(d.family, d.de_model, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
   CTRY(cudaFuncSetAttribute(k_chi2_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CTRY(cudaFuncSetAttribute(k_chi2_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CTRY(cudaFuncSetAttribute(k_chi2_ozaki<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<5>::SMEM));
@@ -516,6 +524,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "gemm_ctas") { c->opt_gemm_ctas = (int)value; return CL_OK; }
   if (n == "stage12_ctas") { c->opt_s12_ctas = (int)value; return CL_OK; }
   if (n == "dbg") { c->opt_dbg = (int)value; return CL_OK; }
+  if (n == "stage12_lean") { c->opt_s12_lean = value != 0; return CL_OK; }
   if (n == "gemm_dynamic") { c->opt_gemm_dynamic = value ? 1 : 0; return CL_OK; }
   if (n == "gemm_group_rb") { c->opt_group_rb = (int)value; return CL_OK; }
   if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }   // DMMA engine only
@@ -578,7 +587,7 @@ static int ensure_scratch(cl_ctx* c, int64_t bytes) {
 }
 
 static int launch_s12(cl_ctx* c, const Stage12Args& a, cudaStream_t st) {
-  S12Kernel k = pick_s12(c->ds.family, c->ds.de_model);
+  S12Kernel k = pick_s12(c->ds.family, c->ds.de_model, c->opt_s12_lean && s12_lean(c->ds, a.mode));
   // at most ~8 CTAs per resident slot, and the same number of rows for every CTA (no ragged tail at small batches)
   int64_t want = c->opt_s12_ctas > 0 ? c->opt_s12_ctas : (int64_t)c->sm_count * 3 * 8;
   int64_t rows_per_cta = (a.B + want - 1) / want;

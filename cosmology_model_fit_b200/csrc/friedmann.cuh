@@ -342,10 +342,16 @@ struct S12Smem {
   double theta[2][CL_MAX_DIM];  // this row's and the next row's parameter vector
 };
 
-template <int FAM, int DE>
+template <int FAM, int DE, int LEAN>
 __global__ void __launch_bounds__(kS12Threads, CL_S12_MINBLOCKS)
 k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__ Stage12Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // LEAN = 1: the instantiation for plain evaluations of a large SN block alone (no BAO / CMB / CC terms, no helper modes):
+  // the probe switches below become compile-time constants and the dead phases drop out of the code (the full kernel is
+  // ~140 KB of SASS, and instruction-fetch stalls showed in its profile)
+  const int mode = LEAN ? (int)MODE_EVAL : a.mode;
+  const int n_bao = LEAN ? 0 : s.n_bao, n_cc = LEAN ? 0 : s.n_cc, cmb_mode = LEAN ? (int)CL_CMB_NONE : s.cmb_mode;
+  const bool sn_small = LEAN ? false : (bool)s.sn_small;
   S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = s.G;
@@ -369,7 +375,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     // ---- prior box / guard: rows that the reference never evaluates (sn/pantheon.py:80-92) ----
     double lp = 0.0;
     int flags = 0;
-    if (a.mode == MODE_EVAL) {
+    if (mode == MODE_EVAL) {
       if (a.what == CL_OUT_LOGPROB) {
         if (s.has_bounds)
           for (int j = 0; j < s.ndim; j++)
@@ -393,10 +399,10 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       }
     }
 
-    const bool need_grid = (a.mode == MODE_EVAL && (s.n_sn > 0 || s.n_bao > 0)) || a.mode == MODE_DIST ||
-                           a.mode == MODE_BAO || a.mode == MODE_RESID;
-    const bool need_cmb = (a.mode == MODE_EVAL && s.cmb_mode != CL_CMB_NONE) || a.mode == MODE_CMB;
-    const bool need_rd = s.rd_mode == CL_RD_FIT && ((a.mode == MODE_EVAL && s.n_bao > 0) || a.mode == MODE_BAO || a.mode == MODE_CMB);
+    const bool need_grid = (mode == MODE_EVAL && (s.n_sn > 0 || n_bao > 0)) || mode == MODE_DIST ||
+                           mode == MODE_BAO || mode == MODE_RESID;
+    const bool need_cmb = (mode == MODE_EVAL && cmb_mode != CL_CMB_NONE) || mode == MODE_CMB;
+    const bool need_rd = s.rd_mode == CL_RD_FIT && ((mode == MODE_EVAL && n_bao > 0) || mode == MODE_BAO || mode == MODE_CMB);
 
     // ================= stage 1: dh = c/H on the grid, cumulative trapezoid =================
     // thread t owns nodes [16t, 16t+16) and the 16 intervals that start at them.  It stores {D_M relative to its first
@@ -504,7 +510,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     }
 
     // ================= helper outputs =================
-    if (a.mode == MODE_DIST) {
+    if (mode == MODE_DIST) {
       for (int q = tid; q < a.nq; q += kS12Threads) {
         double z = a.zq[q];
         if (a.outDM) a.outDM[b * a.nq + q] = hermite_dm(s, sm.gd, sm.off, z);
@@ -517,11 +523,11 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 
     // ================= stage 2: residuals =================
     const int n_sn = s.n_sn;
-    if ((a.mode == MODE_EVAL || a.mode == MODE_RESID) && n_sn > 0 && !(a.dbg & 2)) {
+    if ((mode == MODE_EVAL || mode == MODE_RESID) && n_sn > 0 && !(a.dbg & 2)) {
       const double offset = (s.col_offset >= 0 && !a.zero_offset) ? th[s.col_offset] : 0.0;
-      const int64_t ld = a.mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
+      const int64_t ld = mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
-      const bool to_smem = s.sn_small && a.mode == MODE_EVAL;
+      const bool to_smem = sn_small && mode == MODE_EVAL;
       if (s.grid_uniform && (s.n_vel == 0 || s.vel_pm1) && s.sn_mu_fixed == nullptr && s.n_lin == 0) {
         // fast path.  Static per-SN operands: zs = {1 + z_cmb, w} (or {z_cmb, 0} without a velocity template) and
         // obsp = obs - 25 - 5 log10(1 + z_hel), so that delta = obsp - offset - 5 log10 D_M(z_cosmo):
@@ -634,15 +640,15 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         }
       }
     }
-    if (a.mode == MODE_RESID) {
+    if (mode == MODE_RESID) {
       if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
       __syncthreads();
       continue;
     }
 
     // BAO theory (bao_theory, bao/desi_cmb_union3.py:76-94 / bao/desi_cmb_pantheon.py:85-99)
-    const bool do_bao = (a.mode == MODE_EVAL || a.mode == MODE_BAO) && s.n_bao > 0;
-    if (do_bao && tid < s.n_bao) {
+    const bool do_bao = (mode == MODE_EVAL || mode == MODE_BAO) && n_bao > 0;
+    if (do_bao && tid < n_bao) {
       double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : sm.scal[1]);
       double z = __ldg(s.bao_z + tid);
       double DM = hermite_dm(s, sm.gd, sm.off, z);
@@ -653,17 +659,17 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       else if (q == CL_BAO_DM_OVER_RS) v = DM / rd;
       else if (q == CL_BAO_DH_OVER_RS) v = DH / rd;
       else v = DM / DH;
-      if (a.mode == MODE_BAO) a.out[b * s.n_bao + tid] = v;
+      if (mode == MODE_BAO) a.out[b * n_bao + tid] = v;
       else sm.vec[tid] = __ldg(s.bao_val + tid) - v;
     }
-    if (a.mode == MODE_BAO) {
+    if (mode == MODE_BAO) {
       if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
       __syncthreads();
       continue;
     }
 
     // cosmic chronometers (ohd/cc.py:22-26)
-    if (a.mode == MODE_EVAL && tid < s.n_cc)
+    if (mode == MODE_EVAL && tid < n_cc)
       sm.vec[CL_MAX_BAO + tid] = __ldg(s.cc_H + tid) - H_of_z<FAM, DE>(s, c, __ldg(s.cc_z + tid));
 
     // Gauss-Legendre integrands (cmb/data_planck_act_compression.py:160-197): thread q < n_gl -> D_M node,
@@ -686,22 +692,22 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         v[1] = __ldg(s.gl_w + q) * (DH_of_z<FAM, DE>(s, c, z) / (av * av * sqrt(3.0 * (1.0 + Rb))));
       }
     }
-    const bool need_red = need_cmb || s.n_bao > 0 || s.n_cc > 0 || s.sn_small;  // uniform
+    const bool need_red = need_cmb || n_bao > 0 || n_cc > 0 || sn_small;  // uniform
     if (need_red) __syncthreads();  // sm.vec complete
 
-    if (a.mode == MODE_EVAL) {
-      if (tid < s.n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
+    if (mode == MODE_EVAL) {
+      if (tid < n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
         double t = 0.0;
-        for (int i = 0; i < s.n_bao; i++) t += sm.vec[i] * __ldg(s.bao_W + i * s.n_bao + tid);
+        for (int i = 0; i < n_bao; i++) t += sm.vec[i] * __ldg(s.bao_W + i * n_bao + tid);
         v[2] = t * sm.vec[tid];
       }
-      if (tid < s.n_cc) {
+      if (tid < n_cc) {
         const double* d = sm.vec + CL_MAX_BAO;
         double t = 0.0;
-        for (int i = 0; i < s.n_cc; i++) t += d[i] * __ldg(s.cc_W + i * s.n_cc + tid);
+        for (int i = 0; i < n_cc; i++) t += d[i] * __ldg(s.cc_W + i * n_cc + tid);
         v[3] = t * d[tid];
       }
-      if (s.sn_small && tid < n_sn) {
+      if (sn_small && tid < n_sn) {
         const double* d = sm.vec + CL_MAX_BAO + CL_MAX_CC;
         double t = 0.0;
         if (s.sn_form == CL_SN_INVCOV) {  // delta @ inv_cov @ delta (sn/union3_1.py:57)
@@ -727,16 +733,16 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         dm = (zstar / 2.0) * v[0];
         rs = ((1.0 / (1.0 + zstar)) / 2.0) * v[1];
         double Om_h2 = c.och2 + c.obh2 + s.k.Omnu_h2;
-        if (s.cmb_mode == CL_CMB_THETA_WB_WM) { cmbv[0] = rs / dm; cmbv[1] = c.obh2; cmbv[2] = Om_h2; }
+        if (cmb_mode == CL_CMB_THETA_WB_WM) { cmbv[0] = rs / dm; cmbv[1] = c.obh2; cmbv[2] = Om_h2; }
         else { cmbv[0] = 100 * sqrt(Om_h2) * dm / kC_KMS; cmbv[1] = M_PI * dm / rs; cmbv[2] = c.obh2; }
       }
-      if (a.mode == MODE_CMB) {
+      if (mode == MODE_CMB) {
         double* r = a.out + b * 8;
         r[0] = cmbv[0]; r[1] = cmbv[1]; r[2] = cmbv[2]; r[3] = zstar; r[4] = rs; r[5] = dm;
         r[6] = rd_out; r[7] = 100 * (rs / dm);
       } else {
         double chi2_cmb = 0.0;
-        if (s.cmb_mode != CL_CMB_NONE) {
+        if (cmb_mode != CL_CMB_NONE) {
           double d[3] = {s.cmb_prior[0] - cmbv[0], s.cmb_prior[1] - cmbv[1], s.cmb_prior[2] - cmbv[2]};
           for (int j = 0; j < 3; j++) {
             double t = 0.0;
@@ -745,10 +751,10 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           }
         }
         double extra = 0.0, ccnorm = 0.0;
-        if (s.n_cc > 0) {
+        if (n_cc > 0) {
           double f = s.col_fcc >= 0 ? th[s.col_fcc] : 1.0;
           extra += (s.cc_norm_sign < 0.0 ? 1.0 / (f * f) : f * f) * v[3];   // error-inflation form: chi2 * f ** -2 (ohd/cc_pantheon.py:63)
-          if (s.cc_norm_sign != 0.0) ccnorm = s.n_cc * log(2 * M_PI) + s.cc_logdet - s.cc_norm_sign * 2 * s.n_cc * log(f);
+          if (s.cc_norm_sign != 0.0) ccnorm = n_cc * log(2 * M_PI) + s.cc_logdet - s.cc_norm_sign * 2 * n_cc * log(f);
         }
         for (int g = 0; g < s.n_gc; g++) {
           double r = (th[s.gc_col[g]] - s.gc_mean[g]) / s.gc_sigma[g];
