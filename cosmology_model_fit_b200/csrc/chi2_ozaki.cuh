@@ -163,10 +163,10 @@ __device__ __forceinline__ void oz_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
-// long waits (the epilogue's first level of a tile, the producer's ring slots): poll with a pause in between, so that the
-// barrier unit stays free for the threads on the critical path
+// long waits (the epilogue's first level of a tile, the producer's ring slots): poll with a pause in between - the waiting
+// warps share their SM sub-partitions with the two MMA issuers
 __device__ __forceinline__ void oz_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
-  for (long long i = 0; i < (1LL << 26); i++) {
+  for (long long i = 0; i < (1LL << 28); i++) {
     if (mbar_try_wait(bar, parity)) return;
     __nanosleep(ns);
   }
