@@ -292,8 +292,15 @@ def main():
         e2e_api = "ShardedEngine.log_likelihood(global batch): pinned H2D of the row shard, cl_eval_device, NCCL all-gather, D2H"
         h2d, d2h = B * nd * 8, B * world * 8
     else:
-        e2e_call = lambda i: eng.log_likelihood(host_batches[i % n_rot])
-        e2e_api = "Engine.log_likelihood(batch) -> cl_eval (host buffers, pinned staging)"
+        # theta batches and the result buffer live in page-locked arrays (Engine.pinned_empty): cl_eval moves them by DMA
+        pinned_batches = []
+        for hb in host_batches:
+            pb = eng.pinned_empty(hb.shape)
+            pb[...] = hb
+            pinned_batches.append(pb)
+        pinned_out = eng.pinned_empty((B,))
+        e2e_call = lambda i: eng.log_likelihood(pinned_batches[i % n_rot], out=pinned_out)
+        e2e_api = "Engine.log_likelihood(batch, out=) on Engine.pinned_empty() host arrays -> cl_eval (DMA from / to the caller's page-locked buffers)"
         h2d, d2h = B * nd * 8, B * 8
     for i in range(2):
         e2e_call(i)

@@ -798,6 +798,29 @@ extern "C" int cl_eval_device(cl_ctx* c, const double* d_theta, int64_t B, int64
   return CL_OK;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister / cl_host_alloc) can be the source or target of a DMA as it is
+static bool is_page_locked(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int cl_host_alloc(cl_ctx* c, size_t bytes, void** ptr) {
+  if (!ptr) return fail(c, CL_E_INVALID, "ptr is NULL");
+  *ptr = nullptr;
+  if (c) CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(c, CL_E_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+  return CL_OK;
+}
+
+extern "C" int cl_host_free(cl_ctx* c, void* ptr) {
+  if (!ptr) return CL_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(c, CL_E_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e)); }
+  return CL_OK;
+}
+
 // host-memory evaluation with `width` outputs per row (1: out, 4: components, 3: moments)
 static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int what, double* out, int width, bool moments) {
   int rc = check_eval_args(c, theta, B, ld, out);
@@ -807,17 +830,23 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
   const int nd = c->ds.ndim;
   cudaStream_t st = c->stream;
   c->ev = c->evring[c->n_timed % cl_ctx::kRing];
+  const bool theta_pinned = is_page_locked(theta), out_pinned = is_page_locked(out);
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
   for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
     int64_t rows = std::min(c->max_rows, B - r0);
     rc = ensure_rows(c, rows);
     if (rc != CL_OK) return rc;
-    rc = ensure_pinned(c, rows * nd, rows * 4);
+    rc = ensure_pinned(c, theta_pinned ? 0 : rows * nd, out_pinned ? 0 : rows * 4);
     if (rc != CL_OK) return rc;
     if (r0 > 0) CUDA_TRY(c, cudaStreamSynchronize(st));  // staging buffers are reused
-    if (ld == nd) memcpy(c->h_theta, theta + r0 * ld, (size_t)rows * nd * sizeof(double));   // contiguous rows: one copy
-    else for (int64_t i = 0; i < rows; i++) memcpy(c->h_theta + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_theta, c->h_theta, rows * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (theta_pinned) {   // DMA straight from the caller's page-locked rows
+      CUDA_TRY(c, cudaMemcpy2DAsync(c->d_theta, nd * sizeof(double), theta + r0 * ld, ld * sizeof(double), nd * sizeof(double),
+                                    (size_t)rows, cudaMemcpyHostToDevice, st));
+    } else {
+      if (ld == nd) memcpy(c->h_theta, theta + r0 * ld, (size_t)rows * nd * sizeof(double));   // contiguous rows: one copy
+      else for (int64_t i = 0; i < rows; i++) memcpy(c->h_theta + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
+      CUDA_TRY(c, cudaMemcpyAsync(c->d_theta, c->h_theta, rows * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     double* d_res = c->d_out;
     if (width == 1) rc = run_pass(c, c->d_theta, rows, nd, what, d_res, nullptr, false, st, r0 == 0);
     else if (width == 4) rc = run_pass(c, c->d_theta, rows, nd, CL_OUT_CHI2, nullptr, d_res, false, st, r0 == 0);
@@ -831,10 +860,10 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
       c->launches++;
       CUDA_TRY(c, cudaGetLastError());
     }
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_out, d_res, rows * width * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(out_pinned ? out + r0 * width : c->h_out, d_res, rows * width * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
-    memcpy(out + r0 * width, c->h_out, rows * width * sizeof(double));
+    if (!out_pinned) memcpy(out + r0 * width, c->h_out, rows * width * sizeof(double));
   }
   c->n_timed++;
   return CL_OK;

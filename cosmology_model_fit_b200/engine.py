@@ -25,7 +25,7 @@ _LIB_NAME = "libcosmolike_b200.so"
 ABI_SYMBOLS = (
     "cl_create", "cl_destroy", "cl_last_error", "cl_eval", "cl_eval_device", "cl_eval_components",
     "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
-    "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split",
+    "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split", "cl_host_alloc", "cl_host_free",
 )
 
 #: chi-squared engines for large SN blocks (include/cosmolike.h CL_CHI2_ENGINE_*)
@@ -74,6 +74,8 @@ def load_library():
     lib.cl_launch_count.argtypes = [ctxp]
     lib.cl_launch_count.restype = i64
     lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
+    lib.cl_host_alloc.argtypes = [ctxp, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.cl_host_free.argtypes = [ctxp, C.c_void_p]
     _lib = lib
     return lib
 
@@ -136,23 +138,39 @@ class Engine:
             raise ValueError(f"theta must have shape ({self.ndim},) or (B, {self.ndim})")
         return t, scalar
 
-    def _eval(self, theta, what):
+    def pinned_empty(self, shape, dtype=np.float64):
+        """Uninitialised array in page-locked host memory (cl_host_alloc).  theta batches and `out=` buffers that live in such
+        arrays are moved by DMA directly; ordinary numpy arrays go through the library's staging copy.  The memory is
+        released when the array (and every view of it) is garbage-collected."""
+        import weakref
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        self._check(self.lib.cl_host_alloc(self._ctx, max(n, 1), C.byref(ptr)))
+        buf = (C.c_char * max(n, 1)).from_address(ptr.value)
+        weakref.finalize(buf, self.lib.cl_host_free, None, C.c_void_p(ptr.value))
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def _eval(self, theta, what, out=None):
         t, scalar = self._theta(theta)
-        out = np.empty(t.shape[0], dtype=np.float64)
+        if out is None:
+            out = np.empty(t.shape[0], dtype=np.float64)
+        elif out.dtype != np.float64 or out.shape != (t.shape[0],) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array with one element per row of theta")
         self._check(self.lib.cl_eval(self._ctx, _p(t), t.shape[0], t.shape[1], what, _p(out)))
         return float(out[0]) if scalar else out
 
-    def chi_squared(self, theta):
+    def chi_squared(self, theta, out=None):
         """chi_squared(params) (sn/pantheon.py:57-61)"""
-        return self._eval(theta, OUT_CHI2)
+        return self._eval(theta, OUT_CHI2, out)
 
-    def log_likelihood(self, theta):
+    def log_likelihood(self, theta, out=None):
         """log_likelihood(params) (sn/pantheon.py:64-65; guard of bao/desi_fs_lya_cmb.py:117-121)"""
-        return self._eval(theta, OUT_LOGLIKE)
+        return self._eval(theta, OUT_LOGLIKE, out)
 
-    def log_probability(self, theta):
+    def log_probability(self, theta, out=None):
         """log_probability(params): -inf outside the prior box (sn/pantheon.py:88-97)"""
-        return self._eval(theta, OUT_LOGPROB)
+        return self._eval(theta, OUT_LOGPROB, out)
 
     def log_probs_vectorized(self, batch, dtype=np.float32):
         """Batch log-probability for emcee(vectorize=True); float32 like bao/desi.py:100-106 unless dtype says

@@ -13,6 +13,7 @@
 #ifndef COSMOLIKE_H
 #define COSMOLIKE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -256,6 +257,12 @@ int cl_stage3_split(cl_ctx* ctx, int n, double* ms);
 /* Same for the most recent n evaluations (the library keeps the last 64), oldest first: ms[i][4].
  * Returns the number of entries written (<= n) or a negative error. */
 int cl_timing_history(cl_ctx* ctx, int n, double* ms);
+/* Page-locked host memory for theta / result buffers.  cl_eval(), cl_eval_components() and cl_eval_sn_moments() recognise
+ * page-locked pointers (from here, cudaHostAlloc, cudaHostRegister or torch pin_memory) and move them by DMA directly;
+ * pageable buffers go through the library's own pinned staging area (one extra host copy each way).  ctx may be NULL. */
+int cl_host_alloc(cl_ctx* ctx, size_t bytes, void** ptr);
+int cl_host_free(cl_ctx* ctx, void* ptr);
+
 /* Number of kernels this library launched on the context since creation. */
 int64_t cl_launch_count(const cl_ctx* ctx);
 

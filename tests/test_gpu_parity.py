@@ -269,6 +269,44 @@ def test_strided_theta_rows(engines):
     assert e.lib.cl_eval(e._ctx, wide.ctypes.data_as(dp), len(wide), 3, 0, out.ctypes.data_as(dp)) == -1  # ld < ndim
 
 
+def test_page_locked_buffers_take_the_dma_path(engines):
+    """Engine.pinned_empty (cl_host_alloc): theta and out= in page-locked memory are moved without the staging copy; the
+    values are the same bits as through pageable arrays, also for strided rows, several passes and the other outputs."""
+    import ctypes as C
+    import gc
+    from cosmology_model_fit_b200 import Engine
+    g = golden("sn_pantheon")
+    e = engines("sn_pantheon")
+    th = g["theta"]
+    want = e.chi_squared(th)
+    pt = e.pinned_empty(th.shape)
+    pt[...] = th
+    po = e.pinned_empty((len(th),))
+    got = e.chi_squared(pt, out=po)
+    assert got is po and np.array_equal(po, want)
+    assert np.array_equal(e.log_probability(pt, out=po), e.log_probability(g["theta"]))
+    assert np.array_equal(e.chi_squared(pt), want) and np.array_equal(e.chi_squared(th, out=po), want)   # mixed
+    wide = e.pinned_empty((len(th), 7))
+    wide[...] = 0.0
+    wide[:, :4] = th
+    dp = C.POINTER(C.c_double)
+    assert e.lib.cl_eval(e._ctx, wide.ctypes.data_as(dp), len(wide), 7, 0, po.ctypes.data_as(dp)) == 0
+    assert np.array_equal(po, want)
+    assert np.array_equal(e.components(pt), e.components(th))
+    with pytest.raises(ValueError):
+        e.chi_squared(pt, out=np.empty(len(th) + 1))
+    with Engine(spec("sn_pantheon")) as e2:   # several passes over one pinned batch
+        e2.set_option("max_rows_per_pass", 128)
+        big = e2.pinned_empty((1000, 4))
+        big[...] = np.resize(th, (1000, 4))
+        out = e2.pinned_empty((1000,))
+        e2.chi_squared(big, out=out)
+        assert np.array_equal(out, e.chi_squared(np.resize(th, (1000, 4))))
+        del big, out
+    del pt, po, wide
+    gc.collect()
+
+
 def test_ragged_batches_and_row_order(engines, oracles):
     """B = 1, 127, 128, 129, 1000 (row-block edges of the 128-row GEMM tile) give the same per-row values."""
     from cosmology_model_fit_b200.synthetic import uniform_theta
