@@ -288,8 +288,14 @@ def main():
         from cosmology_model_fit_b200.parallel import ShardedEngine
         sh = ShardedEngine(spec, device=local_rank, engine=eng)
         global_batches = [np.concatenate([theta_batch(spec, B, seed=1000 + r * 16 + i) for r in range(world)]) for i in range(2)]
-        e2e_call = lambda i: sh.log_likelihood(global_batches[i % 2])
-        e2e_api = "ShardedEngine.log_likelihood(global batch): pinned H2D of the row shard, cl_eval_device, NCCL all-gather, D2H"
+        pinned_global = []
+        for gb in global_batches:   # page-locked global batches and result vector (Engine.pinned_empty): DMA without staging copies
+            pb = eng.pinned_empty(gb.shape)
+            pb[...] = gb
+            pinned_global.append(pb)
+        pinned_all = eng.pinned_empty((B * world,))
+        e2e_call = lambda i: sh.log_likelihood(pinned_global[i % 2], out=pinned_all)
+        e2e_api = "ShardedEngine.log_likelihood(global batch, out=) on page-locked host arrays: H2D of the row shard, cl_eval_device, NCCL all-gather, D2H of the full vector on every rank"
         h2d, d2h = B * nd * 8, B * world * 8
     else:
         # theta batches and the result buffer live in page-locked arrays (Engine.pinned_empty): cl_eval moves them by DMA

@@ -56,30 +56,50 @@ class ShardedEngine:
             self.d_all = t.empty(total, dtype=t.float64, device=self.device)
             self.h_all = t.empty(total, dtype=t.float64).pin_memory()
 
-    def evaluate(self, theta, what=OUT_LOGLIKE):
-        """theta: the GLOBAL batch [B, d] (identical on every rank).  Returns ndarray[B] on every rank."""
+    def evaluate(self, theta, what=OUT_LOGLIKE, out=None):
+        """theta: the GLOBAL batch [B, d] (identical on every rank).  Returns ndarray[B] on every rank (`out` if given).
+        Page-locked arrays (`self.engine.pinned_empty`) for theta and `out` are moved by DMA directly: no staging copy of the
+        row shard, and - when the shards are equal - the gathered vector lands in `out` without a second host copy."""
         theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
         B = theta.shape[0]
+        if out is not None and (out.dtype != np.float64 or out.shape != (B,) or not out.flags.c_contiguous):
+            raise ValueError("out must be a contiguous float64 array with one element per row of theta")
         lo, hi = shard_bounds(B, self.rank, self.world)
         rows_max = -(-B // self.world)
         if self.evaluator is not None:
-            return self._evaluate_host(theta, lo, hi, rows_max, what)
+            res = self._evaluate_host(theta, lo, hi, rows_max, what)
+            if out is None:
+                return res
+            out[...] = res
+            return out
         t, dist = self.torch, self.dist
         self._buffers(rows_max, rows_max * self.world)
         n = hi - lo
+        equal = rows_max * self.world == B
+        h_out = t.from_numpy(out) if out is not None and equal else None
+        direct_out = h_out is not None and h_out.is_pinned()
         with t.cuda.stream(self.stream):
             if n:
-                self.h_theta[:n].copy_(t.from_numpy(theta[lo:hi]))
-                self.d_theta[:n].copy_(self.h_theta[:n], non_blocking=True)
+                src = t.from_numpy(theta[lo:hi])
+                if not src.is_pinned():   # ordinary host memory: stage the row shard in the page-locked buffer
+                    self.h_theta[:n].copy_(src)
+                    src = self.h_theta[:n]
+                self.d_theta[:n].copy_(src, non_blocking=True)
                 self.engine.eval_device(self.d_theta.data_ptr(), n, self.spec.ndim, what, self.d_out.data_ptr(),
                                         self.stream.cuda_stream)
             if self.world > 1:
                 dist.all_gather_into_tensor(self.d_all[: rows_max * self.world], self.d_out[:rows_max], group=self.group)
-                self.h_all[: rows_max * self.world].copy_(self.d_all[: rows_max * self.world], non_blocking=True)
+                (h_out if direct_out else self.h_all[: rows_max * self.world]).copy_(self.d_all[: rows_max * self.world], non_blocking=True)
             else:
-                self.h_all[:n].copy_(self.d_out[:n], non_blocking=True)
+                (h_out if direct_out else self.h_all[:n]).copy_(self.d_out[:n], non_blocking=True)
         self.stream.synchronize()
-        return self._unpad(self.h_all.numpy(), B, rows_max)
+        if direct_out:
+            return out
+        res = self._unpad(self.h_all.numpy(), B, rows_max)
+        if out is None:
+            return res
+        out[...] = res
+        return out
 
     def _evaluate_host(self, theta, lo, hi, rows_max, what):
         t, dist = self.torch, self.dist
@@ -103,14 +123,14 @@ class ShardedEngine:
             out[lo:hi] = flat[r * rows_max: r * rows_max + (hi - lo)]
         return out
 
-    def chi_squared(self, theta):
-        return self.evaluate(theta, OUT_CHI2)
+    def chi_squared(self, theta, out=None):
+        return self.evaluate(theta, OUT_CHI2, out)
 
-    def log_likelihood(self, theta):
-        return self.evaluate(theta, OUT_LOGLIKE)
+    def log_likelihood(self, theta, out=None):
+        return self.evaluate(theta, OUT_LOGLIKE, out)
 
-    def log_probability(self, theta):
-        return self.evaluate(theta, OUT_LOGPROB)
+    def log_probability(self, theta, out=None):
+        return self.evaluate(theta, OUT_LOGPROB, out)
 
     def close(self):
         if self.engine is not None and getattr(self, "_own_engine", True):

@@ -307,6 +307,22 @@ def test_page_locked_buffers_take_the_dma_path(engines):
     gc.collect()
 
 
+def test_sharded_engine_single_rank_with_page_locked_buffers(engines):
+    """ShardedEngine on one rank (no process group): ordinary and page-locked theta / out= give the Engine's bits."""
+    from cosmology_model_fit_b200.parallel import ShardedEngine
+    g = golden("sn_pantheon")
+    e = engines("sn_pantheon")
+    want = e.log_likelihood(g["theta"])
+    sh = ShardedEngine(spec("sn_pantheon"), device=0, engine=e)
+    assert np.array_equal(sh.log_likelihood(g["theta"]), want)
+    pt = e.pinned_empty(g["theta"].shape)
+    pt[...] = g["theta"]
+    po = e.pinned_empty((len(want),))
+    assert sh.log_likelihood(pt, out=po) is po and np.array_equal(po, want)
+    plain = np.empty(len(want))
+    assert sh.log_likelihood(pt, out=plain) is plain and np.array_equal(plain, want)
+
+
 def test_ragged_batches_and_row_order(engines, oracles):
     """B = 1, 127, 128, 129, 1000 (row-block edges of the 128-row GEMM tile) give the same per-row values."""
     from cosmology_model_fit_b200.synthetic import uniform_theta

@@ -42,6 +42,8 @@ WORKER = textwrap.dedent("""
         got = eng.chi_squared(theta)
         assert got.shape == (B,)
         assert np.max(np.abs(got - g["chi2"][:B])) < 1e-7, (dist.get_rank(), B)
+        buf = np.empty(B)
+        assert eng.chi_squared(theta, out=buf) is buf and np.array_equal(buf, got)
     dist.barrier()
     dist.destroy_process_group()
     print("rank" + os.environ["RANK"] + "ok", flush=True)
