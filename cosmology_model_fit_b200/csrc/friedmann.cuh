@@ -349,9 +349,12 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   // LEAN = 1: the instantiation for plain evaluations of a large SN block alone (no BAO / CMB / CC terms, no helper modes):
   // the probe switches below become compile-time constants and the dead phases drop out of the code (the full kernel is
   // ~140 KB of SASS, and instruction-fetch stalls showed in its profile)
-  const int mode = LEAN ? (int)MODE_EVAL : a.mode;
-  const int n_bao = LEAN ? 0 : s.n_bao, n_cc = LEAN ? 0 : s.n_cc, cmb_mode = LEAN ? (int)CL_CMB_NONE : s.cmb_mode;
-  const bool sn_small = LEAN ? false : (bool)s.sn_small;
+  // (macros, not locals: a local copy of a kernel parameter occupies a register in the full kernel, which is at its 80-register cap)
+#define mode (LEAN ? (int)MODE_EVAL : a.mode)
+#define n_bao (LEAN ? 0 : s.n_bao)
+#define n_cc (LEAN ? 0 : s.n_cc)
+#define cmb_mode (LEAN ? (int)CL_CMB_NONE : s.cmb_mode)
+#define sn_small (LEAN ? false : (bool)s.sn_small)
   S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = s.G;
@@ -772,6 +775,11 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     // (the two barriers inside block_sum order this iteration's shared-memory reads before the next writes)
   }
 }
+#undef mode
+#undef n_bao
+#undef n_cc
+#undef cmb_mode
+#undef sn_small
 
 // ---- finalize: combine the SN chi2 partials of stage 3 with the scalar terms ----
 struct FinalizeArgs {
