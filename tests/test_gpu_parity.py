@@ -430,3 +430,20 @@ def test_generic_log_probability(engines, name):
     assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"])) and not np.isnan(lp).any()
     fin = np.isfinite(g["logp"])
     chi2_close(-2 * lp[fin], -2 * g["logp"][fin])
+
+
+@pytest.mark.parametrize("name", ["sn_pantheon", "sn_des5y", "sn_pantheon_dipole_xyz", "sn_pantheon_and_sh0es", "sn_pantheon_dipole"])
+def test_lean_stage12_kernel_gives_the_full_kernels_bits(name):
+    """Large-SN-only configurations run the lean instantiation of stage 1+2 (probe switches compile-time); the full kernel
+    (`stage12_lean = 0`) must give the same bits for chi2, log-probability (prior rows included) and the SN moments."""
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    g = golden(name)
+    theta = np.concatenate([g["theta"], uniform_theta(g["bounds"], 300, seed=11)])
+    res = []
+    for lean in (1, 0):
+        with Engine(spec(name)) as e:
+            e.set_option("stage12_lean", lean)
+            res.append((e.chi_squared(theta), e.log_probability(theta * 1.02), e.sn_residuals(theta[:3])))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b, equal_nan=True)
