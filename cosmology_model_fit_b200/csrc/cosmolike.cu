@@ -52,7 +52,7 @@ struct cl_ctx {
   double *h_theta = nullptr, *h_out = nullptr;  // pinned
   int64_t h_theta_cap = 0, h_out_cap = 0;
   int64_t launches = 0;
-  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0, opt_s12_lean = 1;
+  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0, opt_s12_lean = 1, opt_fuse_planes = 0;   // fused planes: measured slower, opt-in
   int* d_counter = nullptr;
   // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
   int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_slice_tpb = 128;
@@ -525,6 +525,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "stage12_ctas") { c->opt_s12_ctas = (int)value; return CL_OK; }
   if (n == "dbg") { c->opt_dbg = (int)value; return CL_OK; }
   if (n == "stage12_lean") { c->opt_s12_lean = value != 0; return CL_OK; }
+  if (n == "fuse_planes") { c->opt_fuse_planes = value != 0; return CL_OK; }
   if (n == "gemm_dynamic") { c->opt_gemm_dynamic = value ? 1 : 0; return CL_OK; }
   if (n == "gemm_group_rb") { c->opt_group_rb = (int)value; return CL_OK; }
   if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }   // DMMA engine only
@@ -658,12 +659,14 @@ static void oz_launch(int grid, cudaStream_t st, const CUtensorMap& tmR, const C
 }
 
 // stage 3 with the tcgen05 engine: slice the residual rows, then the int8 contraction
-static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool record, bool moments) {
+static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool record, bool moments, bool planes_ready) {
   int rc = ensure_planes(c, rows, st);
   if (rc != CL_OK) return rc;
   const int S = c->opt_slices, n = c->ds.n_sn;
-  rc = oz_slice(c, S, c->d_R, c->ldR, rows, n, c->d_Rs, c->d_rscale, st);
-  if (rc != CL_OK) return rc;
+  if (!planes_ready) {   // stage 2 has not written the planes itself
+    rc = oz_slice(c, S, c->d_R, c->ldR, rows, n, c->d_Rs, c->d_rscale, st);
+    if (rc != CL_OK) return rc;
+  }
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
   CUtensorMap tmRs;
   rc = make_tmap_planes(c, &tmRs, c->d_Rs, n, rows, S, c->oz_ld, kOzM, S);   // OzCfg<S>::SLO planes per box
@@ -726,14 +729,23 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   Stage12Args a{};
   a.theta = d_theta; a.B = rows; a.ld = ld; a.mode = MODE_EVAL; a.what = moments ? CL_OUT_CHI2 : what;
   a.R = c->d_R; a.ldR = c->ldR; a.aux = c->d_aux; a.zero_offset = moments ? 1 : 0; a.dbg = c->opt_dbg;
+  // int32 level accumulators hold S products of |d_i d_j| <= 2^14 over n_sn terms: exact up to n_sn = 2^31 / (7 * 2^14) = 18724
+  const bool planes = large && c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384;
+  // stage 2 writes the digit planes itself when the lean kernel runs its fast SN path and a thread can hold its share of the row
+  const DevSpec& d = c->ds;
+  const bool fused = planes && c->opt_fuse_planes && c->opt_s12_lean && s12_lean(d, MODE_EVAL) && d.n_sn <= 8 * kS12Threads &&
+                     d.grid_uniform && (d.n_vel == 0 || d.vel_pm1) && d.sn_mu_fixed == nullptr && d.n_lin == 0 && !(c->opt_dbg & 2);
+  if (fused) {
+    rc = ensure_planes(c, rows, st);
+    if (rc != CL_OK) return rc;
+    a.planes = reinterpret_cast<signed char*>(c->d_Rs); a.planes_ld = c->oz_ld; a.rowscale = c->d_rscale; a.planes_S = c->opt_slices;
+  }
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
   rc = launch_s12(c, a, st);
   if (rc != CL_OK) return rc;
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
-  // int32 level accumulators hold S products of |d_i d_j| <= 2^14 over n_sn terms: exact up to n_sn = 2^31 / (7 * 2^14) = 18724
-  const bool planes = large && c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384;
   if (planes) {
-    rc = run_stage3_planes(c, rows, st, record, moments);
+    rc = run_stage3_planes(c, rows, st, record, moments, fused);
     if (rc != CL_OK) return rc;
   } else if (large) {
     if (record) CUDA_TRY(c, cudaEventRecord(c->ev[6], st));

@@ -77,6 +77,12 @@ struct Stage12Args {
   int nq;
   double *outDM, *outDH;  // MODE_DIST
   double* out;            // MODE_BAO [B][n_bao], MODE_CMB [B][8]
+  // fused digit planes (lean kernel, fast SN path, n_sn <= 8 threads-per-CTA): the residual row goes straight to the int8
+  // planes of the tcgen05 contraction ([planes_S][B][planes_ld], the layout of k_oz_slice_rows) and R is not written
+  signed char* planes;
+  int64_t planes_ld;
+  double* rowscale;       // [B] 2^e of the row
+  int planes_S;
 };
 
 }  // namespace cosmolike

@@ -566,6 +566,80 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           }
           return (ob + obs_off) - 5.0 * log10(hermite_dm(s, sm.gd, sm.off, zq));  // outside the grid / non-positive distance
         };
+        if (LEAN && a.planes != nullptr) {
+          // Fused digit planes: the thread keeps its residuals (columns tid + 256 k) in registers, the CTA agrees on the row's
+          // power-of-two scale, and the balanced base-256 digits go straight to the int8 planes - the same arithmetic as
+          // k_oz_slice_rows (chi2_ozaki.cuh), so the planes are the same bits; the FP64 row never goes through HBM.
+          double dv[8];
+          double mx = 0.0;
+          {
+            // two SNe per trip, operands prefetched one trip ahead (the static arrays live in L2), as in the plain loop below
+            double2 zs0 = make_double2(1.0, 0.0), zs1 = zs0;
+            double ob0 = 0.0, ob1 = 0.0;
+            if (tid < n_sn) { zs0 = __ldg(s.sn_zs + tid); ob0 = __ldg(s.sn_obsp + tid); }
+            if (tid + kS12Threads < n_sn) { zs1 = __ldg(s.sn_zs + tid + kS12Threads); ob1 = __ldg(s.sn_obsp + tid + kS12Threads); }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              const double2 c0 = zs0, c1 = zs1;
+              const double o0 = ob0, o1 = ob1;
+              const int i0 = tid + 2 * t * kS12Threads, i1 = i0 + kS12Threads;
+              if (t < 3) {
+                if (i0 + 2 * kS12Threads < n_sn) { zs0 = __ldg(s.sn_zs + i0 + 2 * kS12Threads); ob0 = __ldg(s.sn_obsp + i0 + 2 * kS12Threads); }
+                if (i1 + 2 * kS12Threads < n_sn) { zs1 = __ldg(s.sn_zs + i1 + 2 * kS12Threads); ob1 = __ldg(s.sn_obsp + i1 + 2 * kS12Threads); }
+              }
+              dv[2 * t] = i0 < n_sn ? resid(c0, o0) : 0.0;
+              dv[2 * t + 1] = i1 < n_sn ? resid(c1, o1) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const double av = fabs(dv[k]);
+              mx = (av <= 1.7e308) ? fmax(mx, av) : __longlong_as_double(0x7ff0000000000000LL);   // NaN / Inf: the row is bad
+            }
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0) sm.wsum[warp] = mx;   // free since the prefix offsets were formed
+          __syncthreads();
+#pragma unroll
+          for (int w = 0; w < kS12Threads / 32; w++) mx = fmax(mx, sm.wsum[w]);
+          const bool bad = !(mx <= 1.7e308);
+          const int S = a.planes_S, frac_bits = 6 + 8 * (S - 1);
+          int e = 0;
+          if (mx > 0.0 && !bad) e = ilogb(mx) + 1;
+          e = max(e, -900);
+          const double up = __longlong_as_double((long long)(1023 + frac_bits - e) << 52);   // 2^(frac_bits - e)
+          const double lim = 1.01 * __longlong_as_double((long long)(1023 + frac_bits) << 52);
+          if (tid == 0) a.rowscale[b] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)(1023 + e) << 52);
+          const unsigned long long bias = 0x0080808080808080ULL >> (8 * (8 - S));   // 0x80 at every digit position below the top one
+          // The digits are staged in shared memory - the grid nodes are dead once every thread has its residuals, which the
+          // barrier above guarantees - and leave the CTA as 16-byte stores (49 one-byte global stores per thread cost
+          // more than the slicing kernel they replace).
+          signed char* stage = reinterpret_cast<signed char*>(sm.gd);
+          const int pld = (int)a.planes_ld;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int i = tid + k * kS12Threads;
+            if (i < pld) {   // the padding columns n_sn .. planes_ld - 1 are zero digits
+              const long long v = i < n_sn ? __double2ll_rn(fmin(fmax(dv[k] * up, -lim), lim)) : 0LL;
+              const unsigned long long u = ((unsigned long long)v + bias) ^ bias;
+              const uint32_t ulo = (uint32_t)u, uhi = (uint32_t)(u >> 32);
+              signed char* q = stage + (S - 1) * pld + i;   // byte j of u is the digit of plane S - 1 - j
+#pragma unroll
+              for (int j = 0; j < 7; j++) {
+                if (j < S) *q = (signed char)((j < 4 ? ulo >> (8 * j) : uhi >> (8 * (j - 4))) & 0xffu);
+                q -= pld;
+              }
+            }
+          }
+          __syncthreads();
+          signed char* __restrict__ prow = a.planes + b * a.planes_ld;
+          const int64_t pstride = a.B * a.planes_ld;
+          const int ld16 = pld >> 4;   // planes_ld is a multiple of 128
+          for (int v = tid; v < S * ld16; v += kS12Threads) {
+            const int p = v / ld16, o = v - p * ld16;
+            *reinterpret_cast<uint4*>(prow + p * pstride + 16 * o) = *reinterpret_cast<const uint4*>(stage + p * pld + 16 * o);
+          }
+        } else {
         // two SNe per thread per trip (independent dependency chains); operands are prefetched one trip ahead
         // because all of L1 is carved out as shared memory and the static arrays live in L2
         const double2* __restrict__ zsp = s.sn_zs + tid;
@@ -589,6 +663,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           outp[0] = d0;
           if (v1) outp[kS12Threads] = d1;
           outp += 2 * kS12Threads; i += 2 * kS12Threads;
+        }
         }
       } else {
         const double2* __restrict__ pack = reinterpret_cast<const double2*>(s.sn_pack);

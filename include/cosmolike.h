@@ -267,7 +267,7 @@ int cl_host_free(cl_ctx* ctx, void* ptr);
 int64_t cl_launch_count(const cl_ctx* ctx);
 
 /* Options (integers): "chi2_engine" (CL_CHI2_ENGINE_*), "chi2_slices" (5..7), "max_rows_per_pass", "gemm_ctas",
- * "stage12_ctas", "stage12_lean" (0: always the full stage-1+2 kernel), "gemm_group_rb", "chi2_slice_tpb", and for the DMMA engine "gemm_dynamic", "gemm_diag_skip".  "dbg" is for
+ * "stage12_ctas", "stage12_lean" (0: always the full stage-1+2 kernel), "fuse_planes" (1: the lean stage-2 kernel writes the digit planes itself; same bits, measured slower), "gemm_group_rb", "chi2_slice_tpb", and for the DMMA engine "gemm_dynamic", "gemm_diag_skip".  "dbg" is for
  * profiling builds of the library (nvcc -DOZ_PROF=1; the production build compiles the counters out): bit 2 prints the cycle
  * counters of the tcgen05 contraction to stderr, bit 3 writes the event trace of CTA 0 to $COSMOLIKE_TRACE (default
  * oz_trace.txt); bits 4-7 are timing experiments that INVALIDATE the results (loads / folds switched off).

@@ -165,11 +165,15 @@ def test_stage3_split_timing(engines):
     theta = uniform_theta(golden("sn_pantheon")["bounds"], 4096, seed=1)
     for slices in (7, 0):
         e = engines("sn_pantheon", slices)
-        e.chi_squared(theta)
-        planes, contraction = e.stage3_split()
-        t = e.last_timing()
-        assert contraction > 0 and abs(planes + contraction - t["stage3_ms"]) < 1e-3
-        assert (planes > 0.005) == bool(slices)
+        for fuse in ((1, 0) if slices else (1,)):
+            e.set_option("fuse_planes", fuse)
+            e.chi_squared(theta)
+            planes, contraction = e.stage3_split()
+            t = e.last_timing()
+            assert contraction > 0 and abs(planes + contraction - t["stage3_ms"]) < 1e-3
+            # a separate slicing kernel only runs for the tcgen05 engine when stage 2 does not write the planes itself
+            assert (planes > 0.005) == (bool(slices) and not fuse)
+        e.set_option("fuse_planes", 0)
     hist = engines("sn_pantheon", 7).stage3_split(3)
     assert hist.shape[1] == 2 and len(hist) >= 1
 
@@ -192,3 +196,26 @@ def test_ragged_sn_counts_vs_oracle(n):
             if slices:
                 e.set_option("chi2_slices", slices)
             close(e.chi_squared(theta), want, slices or 7)
+
+
+@pytest.mark.parametrize("slices", [5, 6, 7])
+@pytest.mark.parametrize("name", ["sn_pantheon", "sn_des5y"])
+def test_fused_digit_planes_are_the_slicing_kernels_bits(name, slices):
+    """Stage 2 of the lean kernel can write the digit planes itself (`fuse_planes`, opt-in): same scale, same digits as the
+    separate slicing kernel, hence the same chi2 bits - random rows, prior rows, a NaN row, the SN moments, ragged batches."""
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    g = golden(name)
+    theta = np.concatenate([g["theta"], uniform_theta(g["bounds"], 517, seed=23)])
+    if name == "sn_pantheon":
+        theta[5, 3] = 60.0   # z_cosmo < 0 for the nearest SNe: NaN residuals (test_nan_residuals_propagate)
+    res = []
+    for fuse in (1, 0):
+        with Engine(spec(name)) as e:
+            e.set_option("chi2_slices", slices)
+            e.set_option("fuse_planes", fuse)
+            res.append((e.chi_squared(theta), e.log_probability(theta * 1.01), e.sn_moments(theta[:100]), e.chi_squared(theta[:129])))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b, equal_nan=True)
+    if name == "sn_pantheon":
+        assert np.isnan(res[0][0][5]) and np.isfinite(np.delete(res[0][0], 5)).all()
