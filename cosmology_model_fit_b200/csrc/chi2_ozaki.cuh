@@ -172,6 +172,9 @@ __device__ __forceinline__ void oz_wait_relaxed(uint32_t bar, uint32_t parity, u
   }
   __trap();
 }
+#ifndef OZ_EPI_NS
+#define OZ_EPI_NS 100   // pause between the epilogue's polls for the first level of a tile
+#endif
 #ifndef OZ_SPIN_NS
 #define OZ_SPIN_NS 40
 #endif
@@ -567,7 +570,7 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       auto poll_level = [&](int t) {
         if (t > 1) return;
         long long tw0 = oz_clock();
-        if (lane == 0) { if (t == 0) oz_wait_relaxed(lvl_full(0), pt, 100); else oz_spin(lvl_full(S - 1), pt); }   // one lane polls
+        if (lane == 0) { if (t == 0) oz_wait_relaxed(lvl_full(0), pt, OZ_EPI_NS); else oz_spin(lvl_full(S - 1), pt); }   // one lane polls
         __syncwarp();
         t_wait += oz_clock() - tw0;
         if (lane == 0 && t == 0) oz_trace(g, tr_i, 2000 + 100 * (warp - 2));   // first level complete (seen by this warp)
