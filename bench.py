@@ -330,6 +330,7 @@ def main():
         ref_out = d_out.clone()
         for name, e_id, sl in (("dmma_fp64", 0, 7), ("tcgen05_7planes", 1, 7), ("tcgen05_6planes", 1, 6)):
             eng.set_option("chi2_engine", e_id); eng.set_option("chi2_slices", sl)
+            eng.set_option("chi2_guard", 1 if sl >= 7 else 0)   # 6 planes: the accuracy guard would send every row to the FP64 engine at its default tolerance
             for i in range(3):
                 step(args.steps - 1)
             diff = float((d_out - ref_out).abs().max().item()) * 2.0      # |d chi2| against the headline engine, same batch
@@ -345,6 +346,7 @@ def main():
                              "planes_ms": float(np.mean(sp[:, 0])), "contraction_ms": float(np.mean(sp[:, 1])),
                              "max_abs_dchi2_vs_headline": diff}
         eng.set_option("chi2_engine", 1 if args.engine == "tcgen05" else 0); eng.set_option("chi2_slices", args.slices)
+        eng.set_option("chi2_guard", 1)
 
     if rank == 0:
         N = args.n_sn

@@ -44,6 +44,8 @@ struct GemmArgs {
   int diag_skip;   // 1: warps stop at their own last column inside the diagonal block
   int* counter;    // dynamic scheduling: global item counter (zeroed before the launch); nullptr = static snake order
   int group_rb;    // dynamic scheduling: row blocks per L2 group
+  const int* guard; // nullable; accuracy-guard fallback pass of the tcgen05 engine (dynamic scheduling only): guard[1] = rows
+                    // flagged (0: nothing to do), guard[2 + rb] != 0 marks the row blocks to compute; the others are skipped
 };
 
 constexpr int kQueueDepth = 4;  // items the producer may run ahead of the consumers
@@ -174,12 +176,19 @@ k_chi2_gemm(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUt
     if (warp == kConsumerWarps && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+      const bool nothing = g.guard != nullptr && g.guard[1] == 0;
       for (int64_t round = 0;; round++) {
         // next item: atomic counter (dynamic) or boustrophedon over the static order; published through the item queue
         int64_t item;
-        if (g.counter) item = atomicAdd(g.counter, 1);
+        if (nothing) item = total;
+        else if (g.counter) item = atomicAdd(g.counter, 1);
         else { item = snake_item(round, blockIdx.x, gridDim.x); if (item >= total && round * gridDim.x < total) continue; }
         const bool done = item >= total;
+        if (!done && g.guard != nullptr) {   // fallback pass: only the flagged row blocks
+          int jt_, rb_;
+          decode_item(g, item, jt_, rb_);
+          if (g.guard[2 + rb_] == 0) continue;
+        }
         mbar_wait(qempty_bar(qslot), qphase ^ 1u);
         asm volatile("st.shared.s32 [%0], %1;" ::"r"(q_items + 4u * qslot), "r"(done ? -1 : (int)item) : "memory");
         mbar_arrive(qfull_bar(qslot));

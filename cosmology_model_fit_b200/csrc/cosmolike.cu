@@ -63,6 +63,13 @@ struct cl_ctx {
   double *d_wscale = nullptr, *d_rscale = nullptr;
   int64_t oz_cap_rows = 0;
   CUtensorMap tmWs{};
+  // accuracy guard of the tcgen05 engine (friedmann.cuh: GuardArgs): static part of the a-priori bound and the fallback state
+  double oz_omega = 0.0;             // sqrt(sum_n (nnz_n 2^eW_n)^2) over the rows of W
+  int opt_guard = 1;
+  double guard_abs = 5e-7, guard_rel = 1e-12;
+  int* d_guard = nullptr;            // [0] rows flagged since creation, [1] in the current pass, [2 + rb] row-block marks
+  unsigned char* d_rowflag = nullptr;
+  double *d_part_fb = nullptr, *d_part_u_fb = nullptr;   // [T][cap] partials of the FP64 fallback pass
   std::string err, desc;
   std::mutex mu;
 };
@@ -304,6 +311,7 @@ extern "C" int cl_destroy(cl_ctx* c) {
   for (void* p : c->dev_allocs) cudaFree(p);
   for (double* p : {c->d_theta, c->d_out, c->d_R, c->d_aux, c->d_part, c->d_part_u, c->d_scratch, c->d_W, c->d_u}) if (p) cudaFree(p);
   if (c->d_counter) cudaFree(c->d_counter);
+  for (void* p : {(void*)c->d_guard, (void*)c->d_rowflag, (void*)c->d_part_fb, (void*)c->d_part_u_fb}) if (p) cudaFree(p);
   for (void* p : {(void*)c->d_Ws, (void*)c->d_Rs, (void*)c->d_wscale, (void*)c->d_rscale}) if (p) cudaFree(p);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
@@ -441,6 +449,18 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
         u[i] = (double)acc; uu += acc * acc;
       }
       c->uu = (double)uu;
+      {  // static part of the digit-plane error bound: every row of W with its power-of-two scale (as k_oz_slice_rows forms it)
+        long double om2 = 0.0L;
+        for (int i = 0; i < n; i++) {
+          double mx = 0.0;
+          int nnz = 0;
+          for (int j = 0; j <= i; j++) { const double a = fabs(W[(size_t)i * c->ldW + j]); mx = std::max(mx, a); nnz += a != 0.0; }
+          const int e = std::max(mx > 0.0 ? ilogb(mx) + 1 : 0, -900);
+          const long double t = (long double)nnz * ldexpl(1.0L, e);
+          om2 += t * t;
+        }
+        c->oz_omega = (double)sqrtl(om2);
+      }
       if (d.sn_small) {
         std::vector<double> Wc((size_t)n * n);
         for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Wc[(size_t)i * n + j] = W[(size_t)i * c->ldW + j];
@@ -526,6 +546,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "dbg") { c->opt_dbg = (int)value; return CL_OK; }
   if (n == "stage12_lean") { c->opt_s12_lean = value != 0; return CL_OK; }
   if (n == "fuse_planes") { c->opt_fuse_planes = value != 0; return CL_OK; }
+  if (n == "chi2_guard") { c->opt_guard = value != 0; return CL_OK; }
   if (n == "gemm_dynamic") { c->opt_gemm_dynamic = value ? 1 : 0; return CL_OK; }
   if (n == "gemm_group_rb") { c->opt_group_rb = (int)value; return CL_OK; }
   if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }   // DMMA engine only
@@ -541,12 +562,41 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   return fail(c, CL_E_INVALID, "unknown option %s", name);
 }
 
+extern "C" int cl_set_option_f64(cl_ctx* c, const char* name, double value) {
+  if (!c || !name) return CL_E_INVALID;
+  std::string n(name);
+  if (!(value >= 0.0)) return fail(c, CL_E_INVALID, "%s must be >= 0", name);
+  if (n == "chi2_guard_abs") { c->guard_abs = value; return CL_OK; }
+  if (n == "chi2_guard_rel") { c->guard_rel = value; return CL_OK; }
+  return fail(c, CL_E_INVALID, "unknown option %s", name);
+}
+
+// eps_S of the digit-plane error bound: 2^(2 - 8 S) (1 + (S - 1) 256 / 255)
+static double oz_eps(int S) { return ldexp(1.0 + (S - 1) * (256.0 / 255.0), 2 - 8 * S); }
+
+extern "C" int cl_guard_info(cl_ctx* c, double out[4]) {
+  if (!c || !out) return CL_E_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  out[0] = out[1] = 0.0; out[2] = c->oz_omega; out[3] = oz_eps(c->opt_slices) * c->oz_omega;
+  if (c->d_guard) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int h[2] = {0, 0};
+    CUDA_TRY(c, cudaDeviceSynchronize());   // the counters may be in flight on a caller-supplied stream
+    CUDA_TRY(c, cudaMemcpy(h, c->d_guard, sizeof h, cudaMemcpyDeviceToHost));
+    out[0] = h[0]; out[1] = h[1];
+  }
+  return CL_OK;
+}
+
 // ---- workspace ----
 static int ensure_rows(cl_ctx* c, int64_t rows) {
   if (rows <= c->cap_rows) return CL_OK;
   int64_t cap = std::max<int64_t>(rows, std::min<int64_t>(c->max_rows, std::max<int64_t>(1024, c->cap_rows * 2)));
   CUDA_TRY(c, cudaDeviceSynchronize());  // the workspace may be in use on a caller-supplied stream
-  for (double** p : {&c->d_theta, &c->d_out, &c->d_R, &c->d_aux, &c->d_part, &c->d_part_u}) { if (*p) cudaFree(*p); *p = nullptr; }
+  for (double** p : {&c->d_theta, &c->d_out, &c->d_R, &c->d_aux, &c->d_part, &c->d_part_u, &c->d_part_fb, &c->d_part_u_fb}) { if (*p) cudaFree(*p); *p = nullptr; }
+  int guard_total = 0;   // rows flagged since creation survive a regrowth of the workspace
+  if (c->d_guard) { cudaMemcpy(&guard_total, c->d_guard, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(c->d_guard); c->d_guard = nullptr; }
+  if (c->d_rowflag) { cudaFree(c->d_rowflag); c->d_rowflag = nullptr; }
   c->cap_rows = 0;
   CUDA_TRY(c, cudaMalloc(&c->d_theta, cap * CL_MAX_DIM * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_out, cap * 4 * sizeof(double)));
@@ -556,6 +606,13 @@ static int ensure_rows(cl_ctx* c, int64_t rows) {
     const int64_t t_max = std::max<int64_t>(c->T, 2 * ((c->ds.n_sn + OzCfg<7>::NT - 1) / OzCfg<7>::NT));  // either engine
     CUDA_TRY(c, cudaMalloc(&c->d_part, cap * t_max * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&c->d_part_u, cap * t_max * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_part_fb, cap * c->T * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_part_u_fb, cap * c->T * sizeof(double)));
+    const size_t gbytes = (2 + (size_t)(cap + 127) / 128) * sizeof(int);
+    CUDA_TRY(c, cudaMalloc(&c->d_guard, gbytes));
+    CUDA_TRY(c, cudaMemset(c->d_guard, 0, gbytes));
+    CUDA_TRY(c, cudaMemcpy(c->d_guard, &guard_total, sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMalloc(&c->d_rowflag, cap));
   }
   c->cap_rows = cap;
   return CL_OK;
@@ -721,6 +778,35 @@ static int run_stage3_planes(cl_ctx* c, int64_t rows, cudaStream_t st, bool reco
   return CL_OK;
 }
 
+// stage 3 on the FP64 tensor pipe (chi2_gemm.cuh).  `guard` != nullptr: the accuracy-guard fallback pass of the tcgen05 engine,
+// restricted to the flagged row blocks (returns at once on the device when nothing is flagged).
+static int run_stage3_dmma(cl_ctx* c, int64_t rows, cudaStream_t st, bool moments, double* part, double* part_u, const int* guard) {
+  CUtensorMap tmR;
+  int rc = make_tmap(c, &tmR, c->d_R, rows, c->ds.n_sn, c->ldR);
+  if (rc != CL_OK) return rc;
+  GemmArgs g{};
+  g.B = rows; g.N = c->ds.n_sn; g.T = c->T; g.n_rb = (int)((rows + kBM - 1) / kBM);
+  g.part = part; g.part_u = part_u; g.u = c->d_u; g.diag_skip = c->opt_diag_skip;
+  g.counter = nullptr; g.guard = guard;
+  if (c->opt_gemm_dynamic || guard) {
+    // row blocks per L2 group: <= ~58 MB of residual rows, a multiple of 8 (the R rows of a group + the 23 MB of W stay
+    // L2-resident across the group's column tiles; measured on B200: 32 row blocks at N=1701 -> 1.2 GB of DRAM reads per
+    // launch instead of 6.5 GB, and multiples of 8 schedule ~2 % better than odd group sizes)
+    int grp = c->opt_group_rb > 0 ? c->opt_group_rb
+                                  : (int)std::max<int64_t>(8, ((58LL << 20) / ((int64_t)kBM * c->ldR * 8)) & ~7LL);
+    g.group_rb = std::min(grp, g.n_rb);
+    g.counter = c->d_counter;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+  }
+  int64_t items = (int64_t)g.n_rb * g.T;
+  int grid = (int)std::min<int64_t>(items, c->opt_gemm_ctas > 0 ? c->opt_gemm_ctas : c->sm_count);
+  if (moments) k_chi2_gemm<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
+  else k_chi2_gemm<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  return CL_OK;
+}
+
 // one pass over `rows` device-resident parameter vectors: stage 1+2 -> stage 3 -> finalize
 static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, int what, double* d_out, double* d_comps,
                     bool moments, cudaStream_t st, bool record) {
@@ -750,37 +836,45 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
     if (rc != CL_OK) return rc;
   } else if (large) {
     if (record) CUDA_TRY(c, cudaEventRecord(c->ev[6], st));
-    CUtensorMap tmR;
-    rc = make_tmap(c, &tmR, c->d_R, rows, c->ds.n_sn, c->ldR);
+    rc = run_stage3_dmma(c, rows, st, moments, c->d_part, c->d_part_u, nullptr);
     if (rc != CL_OK) return rc;
-    GemmArgs g{};
-    g.B = rows; g.N = c->ds.n_sn; g.T = c->T; g.n_rb = (int)((rows + kBM - 1) / kBM);
-    g.part = c->d_part; g.part_u = c->d_part_u; g.u = c->d_u; g.diag_skip = c->opt_diag_skip;
-    g.counter = nullptr;
-    if (c->opt_gemm_dynamic) {
-      // row blocks per L2 group: <= ~58 MB of residual rows, a multiple of 8 (the R rows of a group + the 23 MB of W stay
-      // L2-resident across the group's column tiles; measured on B200: 32 row blocks at N=1701 -> 1.2 GB of DRAM reads per
-      // launch instead of 6.5 GB, and multiples of 8 schedule ~2 % better than odd group sizes)
-      int grp = c->opt_group_rb > 0 ? c->opt_group_rb
-                                    : (int)std::max<int64_t>(8, ((58LL << 20) / ((int64_t)kBM * c->ldR * 8)) & ~7LL);
-      g.group_rb = std::min(grp, g.n_rb);
-      g.counter = c->d_counter;
-      CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+  }
+  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
+  // accuracy guard (tcgen05 engine): rows whose a-priori error bound exceeds the tolerance are flagged by the finalize kernel
+  // and recomputed on the FP64 tensor pipe; the three fallback launches return at once when nothing is flagged
+  const bool guard = planes && c->opt_guard;
+  GuardArgs q{};
+  if (guard) {
+    q.rowscale = c->d_rscale; q.kappa = oz_eps(c->opt_slices) * c->oz_omega; q.tol_abs = c->guard_abs; q.tol_rel = c->guard_rel;
+    q.guard = c->d_guard; q.rowflag = c->d_rowflag; q.only_flagged = 0;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_guard + 1, 0, (1 + (size_t)(rows + 127) / 128) * sizeof(int), st));
+  }
+  const unsigned fgrid = (unsigned)((rows + 255) / 256);
+  FinalizeArgs f{};
+  f.B = rows; f.what = what; f.n_part = planes ? 2 * c->oz_T : c->T; f.sn_large = large ? 1 : 0;
+  f.part = c->d_part; f.aux = c->d_aux; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value; f.q = q;
+  if (moments) k_sum_parts<<<fgrid, 256, 0, st>>>(c->d_part, c->d_part_u, f.n_part, rows, c->uu, d_out, q);   // d_out[rows][3] = (yy, yu, uu)
+  else k_finalize<<<fgrid, 256, 0, st>>>(f);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  if (guard) {
+    if (fused) {   // the FP64 residual rows of the flagged blocks were never written: stage 1+2 again for those rows
+      Stage12Args a2 = a;
+      a2.planes = nullptr; a2.rowscale = nullptr; a2.guard = c->d_guard;
+      S12Kernel k = pick_s12(c->ds.family, c->ds.de_model, true);
+      k<<<c->sm_count * 3, kS12Threads, sizeof(S12Smem), st>>>(c->ds, a2);
+      c->launches++;
+      CUDA_TRY(c, cudaGetLastError());
     }
-    int64_t items = (int64_t)g.n_rb * g.T;
-    int grid = (int)std::min<int64_t>(items, c->opt_gemm_ctas > 0 ? c->opt_gemm_ctas : c->sm_count);
-    if (moments) k_chi2_gemm<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
-    else k_chi2_gemm<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmR, c->tmW, g);
+    rc = run_stage3_dmma(c, rows, st, moments, c->d_part_fb, c->d_part_u_fb, c->d_guard);
+    if (rc != CL_OK) return rc;
+    q.only_flagged = 1;
+    f.q = q; f.part = c->d_part_fb; f.n_part = c->T;
+    if (moments) k_sum_parts<<<fgrid, 256, 0, st>>>(c->d_part_fb, c->d_part_u_fb, c->T, rows, c->uu, d_out, q);
+    else k_finalize<<<fgrid, 256, 0, st>>>(f);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
   }
-  if (record) CUDA_TRY(c, cudaEventRecord(c->ev[3], st));
-  FinalizeArgs f{};
-  f.B = rows; f.what = what; f.n_part = planes ? 2 * c->oz_T : c->T; f.sn_large = large ? 1 : 0;
-  f.part = c->d_part; f.aux = c->d_aux; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value;
-  k_finalize<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(f);
-  c->launches++;
-  CUDA_TRY(c, cudaGetLastError());
   if (record) CUDA_TRY(c, cudaEventRecord(c->ev[4], st));
   return CL_OK;
 }
@@ -863,16 +957,8 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
     double* d_res = c->d_out;
     if (width == 1) rc = run_pass(c, c->d_theta, rows, nd, what, d_res, nullptr, false, st, r0 == 0);
     else if (width == 4) rc = run_pass(c, c->d_theta, rows, nd, CL_OUT_CHI2, nullptr, d_res, false, st, r0 == 0);
-    else rc = run_pass(c, c->d_theta, rows, nd, CL_OUT_CHI2, nullptr, nullptr, true, st, r0 == 0);
+    else rc = run_pass(c, c->d_theta, rows, nd, CL_OUT_CHI2, d_res, nullptr, true, st, r0 == 0);   // d_res[rows][3] = (yy, yu, uu)
     if (rc != CL_OK) return rc;
-    if (moments) {
-      // out[b] = (yy, yu, uu): reduce the partial planes on the host side of the ABI is avoided: reuse finalize
-      // (yy, yu, uu) from the SN partial planes alone
-      const int n_part = (c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384) ? 2 * c->oz_T : c->T;
-      k_sum_parts<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(c->d_part, c->d_part_u, n_part, rows, c->uu, d_res);
-      c->launches++;
-      CUDA_TRY(c, cudaGetLastError());
-    }
     CUDA_TRY(c, cudaMemcpyAsync(out_pinned ? out + r0 * width : c->h_out, d_res, rows * width * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -970,8 +1056,8 @@ static int timing_of(cl_ctx* c, int64_t idx, double ms[4]) {
 
 extern "C" int cl_last_timing(cl_ctx* c, double ms[4]) {
   if (!c || !ms) return CL_E_INVALID;
-  if (c->n_timed == 0) return fail(c, CL_E_INVALID, "no evaluation has been timed yet");
   std::lock_guard<std::mutex> lk(c->mu);
+  if (c->n_timed == 0) return fail(c, CL_E_INVALID, "no evaluation has been timed yet");
   return timing_of(c, c->n_timed - 1, ms);
 }
 

@@ -83,6 +83,9 @@ struct Stage12Args {
   int64_t planes_ld;
   double* rowscale;       // [B] 2^e of the row
   int planes_S;
+  // accuracy-guard fallback pass: only the rows of flagged 128-row blocks are evaluated (guard[1] = rows flagged in this
+  // pass: the kernel returns at once when it is 0; guard[2 + rb] != 0 marks row block rb)
+  const int* guard;
 };
 
 }  // namespace cosmolike

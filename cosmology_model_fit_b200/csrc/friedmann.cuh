@@ -22,6 +22,11 @@
 
 namespace cosmolike {
 
+// CL_S12_DBG=1 (profiling builds only) compiles the timing switches `dbg` bit 0 (skip the grid pass) and bit 1 (skip the SN pass) in;
+// both invalidate the results, so the production build does not carry them
+#ifndef CL_S12_DBG
+#define CL_S12_DBG 0
+#endif
 #ifndef CL_S12_MINBLOCKS
 #define CL_S12_MINBLOCKS 3
 #endif
@@ -361,6 +366,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   if (tid < 128) sm.logtab[tid] = s.logtab[tid];  // visible after the first __syncthreads of the loop body
   const uint32_t gd_addr = s12_smem_u32(sm.gd), tab_addr = s12_smem_u32(sm.logtab);
 
+  if (a.guard != nullptr && a.guard[1] == 0) return;   // fallback pass with nothing flagged
   if (tid < s.ndim && (int64_t)blockIdx.x < a.B) sm.theta[0][tid] = a.theta[(int64_t)blockIdx.x * a.ld + tid];
   __syncthreads();
   int tb = 0;
@@ -372,6 +378,12 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const bool stage_next = tid < s.ndim && b + gridDim.x < a.B;
     double th_next = 0.0;
     if (stage_next) th_next = a.theta[(b + gridDim.x) * a.ld + tid];  // consumed only at the end of the iteration
+    if (a.guard != nullptr && a.guard[2 + (b >> 7)] == 0) {   // fallback pass: this row's block is not flagged (uniform across the CTA)
+      __syncthreads();
+      if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
+      __syncthreads();
+      continue;
+    }
     Cosmo c;
     unpack(s, th, c);
 
@@ -415,7 +427,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const int i0 = tid * kPPT;
     if (need_grid) {
       const uint32_t dst = gd_addr + (uint32_t)pad_idx(i0) * 16u;
-      if (a.dbg & 1) {
+      if (CL_S12_DBG && (a.dbg & 1)) {   // timing experiment (profiling build): no grid pass, results invalid
         run = 1.0;
       } else if (s.grid_uniform) {
         // Static node tables (ln(1+z_i), Omnu_z(z_i)).  A thread owns 16 CONSECUTIVE nodes, so reading the tables from global
@@ -526,7 +538,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 
     // ================= stage 2: residuals =================
     const int n_sn = s.n_sn;
-    if ((mode == MODE_EVAL || mode == MODE_RESID) && n_sn > 0 && !(a.dbg & 2)) {
+    if ((mode == MODE_EVAL || mode == MODE_RESID) && n_sn > 0 && !(CL_S12_DBG && (a.dbg & 2))) {
       const double offset = (s.col_offset >= 0 && !a.zero_offset) ? th[s.col_offset] : 0.0;
       const int64_t ld = mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
@@ -562,7 +574,10 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
             // (interpolator.py:96-108) collapses to the quadratic y_i + t hd_i + t^2 (hd_{i+1} - hd_i)/2; the dropped
             // cubic coefficient is pure rounding of the cumulative sum (~1e-16 D_M).
             const double dm = fma(t, fma(0.5 * t, n1.y - n0.y, n0.y), n0.x + base);
-            return (ob + obs_off) - fast_5log10(dm, tab_addr);
+            // the table log10 decodes the bits of a NORMAL POSITIVE number; a NaN / Inf / non-positive distance (NaN or Inf
+            // parameters, E^2 < 0) takes the libm call below, which gives the reference's NaN (np.log10)
+            if (dm > 1e-300 && dm < 1e300) return (ob + obs_off) - fast_5log10(dm, tab_addr);
+            return (ob + obs_off) - 5.0 * log10(dm);
           }
           return (ob + obs_off) - 5.0 * log10(hermite_dm(s, sm.gd, sm.off, zq));  // outside the grid / non-positive distance
         };
@@ -857,6 +872,28 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #undef sn_small
 
 // ---- finalize: combine the SN chi2 partials of stage 3 with the scalar terms ----
+// Accuracy guard of the int8 digit-plane engine ("error bound"): with S planes every residual row and
+// every row of W carries FRAC = 8 S - 2 fractional bits below its power-of-two scale, and the products with i + j >= S are
+// dropped, so per component  |dy_n| <= 2^eR_b 2^eW_n nnz_n eps_S,  eps_S = 2^(2 - 8 S) (1 + (S - 1) 256 / 255),  hence
+//   |d chi2_b| <= 2 sqrt(chi2_b) rho_b + rho_b^2,   rho_b = 2^eR_b kappa,   kappa = eps_S sqrt(sum_n (nnz_n 2^eW_n)^2)
+// (kappa is static: formed by cl_create).  Rows whose bound exceeds max(tol_abs, tol_rel chi2) are flagged and recomputed
+// on the FP64 tensor pipe by the fallback pass (k_chi2_gemm restricted to the flagged 128-row blocks).
+struct GuardArgs {
+  const double* rowscale;   // nullptr = guard off
+  double kappa, tol_abs, tol_rel;
+  int* guard;               // [0] rows flagged since cl_create, [1] rows flagged in this pass, [2 + rb] row-block marks
+  unsigned char* rowflag;   // [B] 1 = this row is recomputed by the fallback pass
+  int only_flagged;         // fallback pass: rewrite the flagged rows only (and do not flag again)
+};
+__device__ __forceinline__ bool guard_row(const GuardArgs& q, int64_t b, double chi2_sn) {
+  const double rho = q.rowscale[b] * q.kappa;
+  const double bound = fma(2.0 * sqrt(fmax(chi2_sn, 0.0)), rho, rho * rho);
+  const bool flag = bound > fmax(q.tol_abs, q.tol_rel * chi2_sn);   // NaN rows (bad residuals) compare false: chi2 stays NaN
+  q.rowflag[b] = flag ? 1 : 0;
+  if (flag) { q.guard[2 + (b >> 7)] = 1; atomicAdd(q.guard + 1, 1); atomicAdd(q.guard, 1); }
+  return flag;
+}
+
 struct FinalizeArgs {
   int64_t B;
   int what, n_part, sn_large;
@@ -865,22 +902,26 @@ struct FinalizeArgs {
   double* out;         // [B]
   double* comps;       // nullable [B][4]
   double guard_value;
+  GuardArgs q;
 };
 
 __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FinalizeArgs f) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= f.B) return;
+  if (f.q.only_flagged && (f.q.guard[1] == 0 || !f.q.rowflag[b])) return;
   int flags = (int)f.aux[AUX_FLAGS * f.B + b];
   double lp = f.aux[AUX_LOGPRIOR * f.B + b];
   if (flags) {
     double r = (flags & FLAG_OUTSIDE) ? -INFINITY : (f.what == CL_OUT_LOGPROB ? lp + f.guard_value : f.guard_value);
     if (f.out) f.out[b] = r;
     if (f.comps) for (int j = 0; j < 4; j++) f.comps[b * 4 + j] = NAN;
+    if (f.q.rowscale && !f.q.only_flagged) f.q.rowflag[b] = 0;
     return;
   }
   double sn = 0.0;
   if (f.sn_large) for (int t = 0; t < f.n_part; t++) sn += f.part[(int64_t)t * f.B + b];
   else sn = f.aux[AUX_SN_SMALL * f.B + b];
+  if (f.q.rowscale && !f.q.only_flagged) guard_row(f.q, b, sn);
   double bao = f.aux[AUX_BAO * f.B + b], cmb = f.aux[AUX_CMB * f.B + b], extra = f.aux[AUX_EXTRA * f.B + b];
   if (f.comps) { f.comps[b * 4] = sn; f.comps[b * 4 + 1] = bao; f.comps[b * 4 + 2] = cmb; f.comps[b * 4 + 3] = extra; }
   if (!f.out) return;
@@ -894,11 +935,13 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ Finali
 
 // moments mode: out[b] = (y.y, y.u, u.u)
 __global__ void __launch_bounds__(256) k_sum_parts(const double* __restrict__ part, const double* __restrict__ part_u, int T,
-                                                   int64_t B, double uu, double* __restrict__ out) {
+                                                   int64_t B, double uu, double* __restrict__ out, const GuardArgs q) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (q.only_flagged && (q.guard[1] == 0 || !q.rowflag[b])) return;
   double yy = 0.0, yu = 0.0;
   for (int t = 0; t < T; t++) { yy += part[(int64_t)t * B + b]; yu += part_u[(int64_t)t * B + b]; }
+  if (q.rowscale && !q.only_flagged) guard_row(q, b, yy);
   out[b * 3] = yy; out[b * 3 + 1] = yu; out[b * 3 + 2] = uu;
 }
 

@@ -1,8 +1,8 @@
 """Observational inputs for the engine.
 
 The reference's loaders (`y20xx*/data.py: get_data()`) are reused as-is when a reference checkout is on
-sys.path; this module only (a) reads the compact column fixtures committed under tests/golden/ (the GPU box
-has no reference tree) and (b) applies the same row selection / ordering as the loaders, with the seeded
+sys.path; this module only (a) reads the compact column files shipped inside the package (cosmology_model_fit_b200/data/, or
+$COSMOLIKE_DATA; the GPU box has no reference tree) and (b) applies the same row selection / ordering as the loaders, with the seeded
 synthetic covariance standing in for the blobs missing from the reference checkout.
 """
 from __future__ import annotations
@@ -13,11 +13,11 @@ import numpy as np
 
 from .synthetic import synthetic_sn_covariance
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_DATA = os.environ.get("COSMOLIKE_DATA") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 def _load(name, root=None):
-    return np.load(os.path.join(root or _GOLDEN, name))
+    return np.load(os.path.join(root or _DATA, name))
 
 
 def pantheon_plus(cut=True, root=None):

@@ -26,6 +26,7 @@ ABI_SYMBOLS = (
     "cl_create", "cl_destroy", "cl_last_error", "cl_eval", "cl_eval_device", "cl_eval_components",
     "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
     "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split", "cl_host_alloc", "cl_host_free",
+    "cl_set_option_f64", "cl_guard_info",
 )
 
 #: chi-squared engines for large SN blocks (include/cosmolike.h CL_CHI2_ENGINE_*)
@@ -74,6 +75,8 @@ def load_library():
     lib.cl_launch_count.argtypes = [ctxp]
     lib.cl_launch_count.restype = i64
     lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
+    lib.cl_set_option_f64.argtypes = [ctxp, C.c_char_p, C.c_double]
+    lib.cl_guard_info.argtypes = [ctxp, C.c_double * 4]
     lib.cl_host_alloc.argtypes = [ctxp, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.cl_host_free.argtypes = [ctxp, C.c_void_p]
     _lib = lib
@@ -127,7 +130,17 @@ class Engine:
         return self.lib.cl_describe(self._ctx).decode()
 
     def set_option(self, name, value):
-        self._check(self.lib.cl_set_option(self._ctx, name.encode(), int(value)))
+        if isinstance(value, float) and name in ("chi2_guard_abs", "chi2_guard_rel"):
+            self._check(self.lib.cl_set_option_f64(self._ctx, name.encode(), float(value)))
+        else:
+            self._check(self.lib.cl_set_option(self._ctx, name.encode(), int(value)))
+
+    def guard_info(self):
+        """Accuracy guard of the tcgen05 chi-squared engine (cl_guard_info): rows recomputed on the FP64 engine since
+        creation / by the last pass, and the static factors of the a-priori bound."""
+        v = (C.c_double * 4)()
+        self._check(self.lib.cl_guard_info(self._ctx, v))
+        return {"rows_total": int(v[0]), "rows_last_pass": int(v[1]), "omega": v[2], "kappa": v[3]}
 
     # -- evaluation -------------------------------------------------------------------------------------------
     def _theta(self, theta):

@@ -45,6 +45,9 @@ def sn_profile_grid(engine, axes, mode="profile", chunk=65536, h0_axis=None, h0_
             raise ValueError("h0_axis needs a free H0 column that is not among `axes`")
         if sp.bao_z is not None or sp.cmb_mode != 0 or sp.cc_z is not None or sp.family != 0:
             raise ValueError("the H0 axis is analytic only for SN-only late-time models")
+        if sp.sn_mu_fixed is not None:
+            # SH0ES calibrator rows carry a fixed distance modulus (sn/pantheon_and_sh0es.py:63-69) and do not move with H0
+            raise ValueError("the H0 axis is not a pure offset when the spec has fixed-distance (calibrator) rows")
         fixed[sp.col_H0] = h0_ref
     if sorted(list(axes) + list(fixed)) != list(range(sp.ndim)):
         raise ValueError("axes must cover every theta column except the offset (and H0 with h0_axis)")

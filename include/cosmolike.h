@@ -267,12 +267,27 @@ int cl_host_free(cl_ctx* ctx, void* ptr);
 int64_t cl_launch_count(const cl_ctx* ctx);
 
 /* Options (integers): "chi2_engine" (CL_CHI2_ENGINE_*), "chi2_slices" (5..7), "max_rows_per_pass", "gemm_ctas",
- * "stage12_ctas", "stage12_lean" (0: always the full stage-1+2 kernel), "fuse_planes" (1: the lean stage-2 kernel writes the digit planes itself; same bits, measured slower), "gemm_group_rb", "chi2_slice_tpb", and for the DMMA engine "gemm_dynamic", "gemm_diag_skip".  "dbg" is for
+ * "stage12_ctas", "stage12_lean" (0: always the full stage-1+2 kernel), "fuse_planes" (1: the lean stage-2 kernel writes the digit planes itself; same bits, measured slower), "chi2_guard" (0 switches the accuracy guard of the tcgen05 engine off), "gemm_group_rb", "chi2_slice_tpb", and for the DMMA engine "gemm_dynamic", "gemm_diag_skip".  "dbg" is for
  * profiling builds of the library (nvcc -DOZ_PROF=1; the production build compiles the counters out): bit 2 prints the cycle
  * counters of the tcgen05 contraction to stderr, bit 3 writes the event trace of CTA 0 to $COSMOLIKE_TRACE (default
  * oz_trace.txt); bits 4-7 are timing experiments that INVALIDATE the results (loads / folds switched off).
  * Returns CL_E_INVALID for unknown names. */
 int cl_set_option(cl_ctx* ctx, const char* name, int64_t value);
+
+/* Floating-point options: "chi2_guard_abs" (default 5e-7), "chi2_guard_rel" (default 1e-12) - see cl_guard_info. */
+int cl_set_option_f64(cl_ctx* ctx, const char* name, double value);
+
+/* Accuracy guard of the tcgen05 (int8 digit plane) chi-squared engine.  The engine replaces the reference's FP64 forward
+ * substitution (solve_triangular.py:5-14) by an exact integer contraction of S digit planes per operand row; its only
+ * errors are the fixed-point rounding of the operands (one power-of-two scale per row) and the dropped products below the
+ * last kept digit, so an a-priori bound exists per row b:
+ *     |d chi2_b| <= 2 sqrt(chi2_b) rho_b + rho_b^2,  rho_b = 2^eR_b * eps_S * Omega,
+ *     eps_S = 2^(2-8S) (1 + (S-1) 256/255),  Omega = sqrt(sum_n (nnz_n 2^eW_n)^2)   (static, from W = L^-1).
+ * With option "chi2_guard" = 1 (default) every row whose bound exceeds max(chi2_guard_abs, chi2_guard_rel * chi2_b) is
+ * recomputed on the FP64 tensor pipe (DMMA engine) inside the same call; the values the caller sees therefore always meet
+ * the tolerance or are FP64 results.  out[0] = rows recomputed since cl_create, out[1] = rows recomputed by the most recent
+ * pass, out[2] = Omega, out[3] = eps_S * Omega for the current plane count.  Synchronises the device. */
+int cl_guard_info(cl_ctx* ctx, double out[4]);
 
 /* Library / device description string, e.g. "cosmolike_b200 abi 3, sm_100a, NVIDIA B200 (148 SMs)". */
 const char* cl_describe(const cl_ctx* ctx);

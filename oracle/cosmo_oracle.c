@@ -201,6 +201,28 @@ double oracle_solve_triangular(const double* L, const double* b, int n, double* 
   for (int i = 0; i < n; i++) y[i] = (b[i] - dot4(L + (size_t)i * n, y, i)) / L[(size_t)i * n + i];
   return dot4(y, y, n);
 }
+/* The same forward substitution (solve_triangular.py:10-14) carried in 80-bit extended precision: the arithmetic yardstick of
+ * the conditioning tests (tests/test_gpu_conditioning.py).  It is NOT the reference's arithmetic (that is the FP64 version
+ * above); it measures how far the FP64 result of anybody - the reference included - is from the exact value for the given
+ * (L, delta).  out[b] = |L^-1 R[b]|^2. */
+int oracle_solve_triangular_ld(const double* L, const double* R, int64_t B, int n, double* out) {
+  long double* y = malloc(sizeof(long double) * (size_t)n);
+  if (!y) return -1;
+  for (int64_t b = 0; b < B; b++) {
+    const double* r = R + (size_t)b * n;
+    long double chi2 = 0.0L;
+    for (int i = 0; i < n; i++) {
+      const double* Li = L + (size_t)i * n;
+      long double acc = r[i];
+      for (int k = 0; k < i; k++) acc -= (long double)Li[k] * y[k];
+      y[i] = acc / (long double)Li[i];
+      chi2 += y[i] * y[i];
+    }
+    out[b] = (double)chi2;
+  }
+  free(y);
+  return 0;
+}
 /* delta @ M @ delta: (delta @ M) is a vector-matrix product, then a dot (sn/union3_1.py:57) */
 static double quad_form(const double* M, const double* d, int n) {
   double acc = 0.0;

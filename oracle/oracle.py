@@ -46,6 +46,7 @@ def _load():
         lib.oracle_pchip_slopes.argtypes = [_dp, _dp, C.c_int, _dp]
         lib.oracle_solve_triangular.argtypes = [_dp, _dp, C.c_int, _dp]
         lib.oracle_solve_triangular.restype = C.c_double
+        lib.oracle_solve_triangular_ld.argtypes = [_dp, _dp, i64, C.c_int, _dp]
         lib.oracle_max_threads.restype = C.c_int
         for f in (lib.oracle_interp_hermite, lib.oracle_interp_pchip, lib.oracle_pchip_slopes):
             f.restype = None
@@ -150,3 +151,18 @@ def solve_triangular(L, b):
     L, b = np.ascontiguousarray(L, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
     y = np.empty_like(b)
     return float(_load().oracle_solve_triangular(_p(L), _p(b), b.size, _p(y)))
+
+
+def solve_triangular_ld(L, R):
+    """|L^-1 R[b]|^2 per row by forward substitution in 80-bit extended precision (the yardstick of the conditioning tests)."""
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    R = np.ascontiguousarray(np.atleast_2d(R), dtype=np.float64)
+    out = np.empty(R.shape[0])
+    if _load().oracle_solve_triangular_ld(_p(L), _p(R), R.shape[0], L.shape[0], _p(out)) != 0:
+        raise MemoryError
+    return out
+
+
+def solve_triangular_batch(L, R):
+    """The reference's FP64 forward substitution (solve_triangular.py:5-14) for every row of R."""
+    return np.array([solve_triangular(L, r) for r in np.atleast_2d(R)])

@@ -26,6 +26,7 @@ import types
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+DATA = os.path.join(os.path.dirname(os.path.dirname(HERE)), "cosmology_model_fit_b200", "data")   # observational columns (inputs, not goldens)
 REPO = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("COSMO_REFERENCE", "/root/reference")
 sys.path.insert(0, REPO)
@@ -41,7 +42,7 @@ def dump_data_columns():
 
     df = pd.read_csv(f"{REF}/y2022pantheonSHOES/raw-data/distances.txt", sep=" ")
     np.savez_compressed(
-        f"{HERE}/data_pantheon_plus.npz",
+        f"{DATA}/data_pantheon_plus.npz",
         zHD=df["zHD"].to_numpy(np.float64),
         zHEL=df["zHEL"].to_numpy(np.float64),
         m_b_corr=df["m_b_corr"].to_numpy(np.float64),
@@ -54,7 +55,7 @@ def dump_data_columns():
     )
     df = pd.read_csv(f"{REF}/y2025DESdovekie/raw-data/distances.csv", sep=r"\s+")
     np.savez_compressed(
-        f"{HERE}/data_des_dovekie.npz",
+        f"{DATA}/data_des_dovekie.npz",
         zHD=df["zHD"].to_numpy(np.float64),
         zHEL=df["zHEL"].to_numpy(np.float64),
         MU=df["MU"].to_numpy(np.float64),
@@ -64,7 +65,7 @@ def dump_data_columns():
     cov = np.genfromtxt(f"{REF}/y2026union3_1/raw-data/covariance.txt", dtype=np.float64)
     n = df["zcmb"].size
     np.savez_compressed(
-        f"{HERE}/data_union3_1.npz",
+        f"{DATA}/data_union3_1.npz",
         zcmb=df["zcmb"].to_numpy(np.float64),
         zhel=df["zhel"].to_numpy(np.float64),
         mb=df["mb"].to_numpy(np.float64),
@@ -82,7 +83,7 @@ def dump_data_columns():
         out[f"{tag}_value"] = d["value"]
         out[f"{tag}_quantity"] = d["quantity"]
         out[f"{tag}_cov"] = np.loadtxt(f"{REF}/y2025BAO/raw-data/{cfile}", delimiter=" ", dtype=np.float64)
-    np.savez_compressed(f"{HERE}/data_desi_bao.npz", **out)
+    np.savez_compressed(f"{DATA}/data_desi_bao.npz", **out)
     # cosmic chronometers: the loader builds the covariance with the reference's own pchip (y2005cc/data.py:5-40)
     cwd = os.getcwd()
     os.chdir(REF)
@@ -93,14 +94,14 @@ def dump_data_columns():
     finally:
         os.chdir(cwd)
         sys.path.remove(REF)
-    np.savez_compressed(f"{HERE}/data_cc.npz", z=np.asarray(zc, dtype=np.float64), H=np.asarray(Hc, dtype=np.float64), cov=np.asarray(covc, dtype=np.float64))
+    np.savez_compressed(f"{DATA}/data_cc.npz", z=np.asarray(zc, dtype=np.float64), H=np.asarray(Hc, dtype=np.float64), cov=np.asarray(covc, dtype=np.float64))
 
 
 # ------------------------------------------------------------------------------------------------
 # loader stubs for the missing blobs
 # ------------------------------------------------------------------------------------------------
 def _stub_pantheon():
-    d = np.load(f"{HERE}/data_pantheon_plus.npz")
+    d = np.load(f"{DATA}/data_pantheon_plus.npz")
     cov_full = synthetic_sn_covariance(d["m_b_corr_err_DIAG"])
     keep = np.where(d["zHD"] > 0.01)[0]  # y2022pantheonSHOES/data.py:25
 
@@ -133,7 +134,7 @@ def _stub_pantheon():
 
 
 def _stub_des():
-    d = np.load(f"{HERE}/data_des_dovekie.npz")
+    d = np.load(f"{DATA}/data_des_dovekie.npz")
     cov_full = synthetic_sn_covariance(d["MUERR"])
     order = np.argsort(d["zHD"])  # y2025DESdovekie/data.py:25
 
@@ -727,7 +728,7 @@ def main(argv):
         np.savez_compressed(f"{HERE}/golden_{name}.npz", **{k: np.asarray(v) for k, v in res.items()})
         return 0
     names = argv or list(CASES)
-    if not os.path.exists(f"{HERE}/data_pantheon_plus.npz") or not argv:
+    if not os.path.exists(f"{DATA}/data_pantheon_plus.npz") or not argv:
         dump_data_columns()
     for name in names:
         print(f"[golden] {name} ...", flush=True)

@@ -447,3 +447,53 @@ def test_lean_stage12_kernel_gives_the_full_kernels_bits(name):
             res.append((e.chi_squared(theta), e.log_probability(theta * 1.02), e.sn_residuals(theta[:3])))
     for a, b in zip(*res):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_nan_parameters_give_nan_like_numpy(engines):
+    """NaN / Inf parameters and E^2 < 0 (Omega_m < 0) make D_M NaN; np.log10 in the reference then returns NaN and so must
+    chi_squared / log_likelihood here (the table log10 of the fast SN path decodes bits and would otherwise return a finite
+    number).  chi_squared ignores the prior box, so these rows reach the model like in the reference's nautilus scripts."""
+    import oracle.oracle as O
+    g = golden("sn_pantheon")
+    good = np.array(g["theta"][0], dtype=np.float64)
+    rows = np.tile(good, (6, 1))
+    rows[1, 1] = np.nan          # H0
+    rows[2, 2] = np.nan          # Omega_m
+    rows[3, 2] = -0.5            # E^2 < 0 beyond z = 0.44
+    rows[4, 1] = np.inf
+    rows[5, 3] = np.nan          # v
+    want = O.Oracle(spec("sn_pantheon")).chi_squared(rows)
+    assert np.isfinite(want[0]) and np.isnan(want[1:4]).all()
+    for opt in ({}, {"chi2_engine": 0}, {"stage12_lean": 0}, {"fuse_planes": 1}):
+        from cosmology_model_fit_b200 import Engine
+        with Engine(spec("sn_pantheon")) as e:
+            for k, v in opt.items():
+                e.set_option(k, v)
+            got = e.chi_squared(rows)
+            ll = e.log_likelihood(rows)
+        assert abs(got[0] - want[0]) < 1e-6, opt
+        assert np.isnan(got[1:]).all() and np.isnan(ll[1:]).all(), (opt, got)
+
+
+def test_offset_marginal_vs_bruteforce_integral_of_the_oracle(engines):
+    """SURVEY.md N3 (not in the reference, parity otherwise unpinned): -2 ln int dM exp(-chi2(M)/2) from the two-dot epilogue
+    against brute-force quadrature over M of the CPU ORACLE's chi_squared (the reference's arithmetic, sn/pantheon.py:57-61)."""
+    import oracle.oracle as O
+    from cosmology_model_fit_b200.profile import offset_profile
+    e = engines("sn_pantheon")   # theta = (M, H0, Om, v)
+    orc = O.Oracle(spec("sn_pantheon"))
+    base = np.array([[0.0, 70.0, 0.30, 0.0], [0.0, 64.0, 0.45, -2.0], [0.0, 81.0, 0.12, 1.5]])
+    mom = e.sn_moments(base)
+    marg, mstar = offset_profile(mom, "marginal")
+    prof, _ = offset_profile(mom, "profile")
+    sig = 1.0 / np.sqrt(mom[:, 2])
+    for i in range(base.shape[0]):
+        M = mstar[i] + sig[i] * np.linspace(-12.0, 12.0, 1201)
+        rows = np.tile(base[i], (M.size, 1))
+        rows[:, 0] = M
+        c = orc.chi_squared(rows, nthreads=0)
+        assert abs(c.min() - prof[i]) < 1e-6 * max(1.0, prof[i])
+        w = np.exp(-0.5 * (c - c.min()))
+        integral = np.sum(0.5 * (w[1:] + w[:-1]) * np.diff(M))     # trapezoid: spectrally accurate for a Gaussian on +-12 sigma
+        brute = c.min() - 2.0 * np.log(integral)
+        assert abs(brute - marg[i]) < 1e-6 * max(1.0, abs(marg[i])), (brute, marg[i])

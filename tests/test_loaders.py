@@ -88,13 +88,13 @@ def test_des_union3_bao_files(tmp_path):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
 def test_reference_files_match_the_committed_fixtures():
-    """The reference's own raw files through loaders.py against tests/golden/data_*.npz (the covariance blobs of
+    """The reference's own raw files through loaders.py against cosmology_model_fit_b200/data/data_*.npz (the covariance blobs of
     Pantheon+ and DES are missing from the checkout: columns only)."""
     t = loaders._read_table(f"{REF}/y2022pantheonSHOES/raw-data/distances.txt")
-    d = np.load(os.path.join(datasets._GOLDEN, "data_pantheon_plus.npz"))
+    d = np.load(os.path.join(datasets._DATA, "data_pantheon_plus.npz"))
     assert np.array_equal(t["zHD"], d["zHD"]) and np.array_equal(t["m_b_corr"], d["m_b_corr"]) and t["zHD"].size == 1701
     t = loaders._read_table(f"{REF}/y2025DESdovekie/raw-data/distances.csv")
-    d = np.load(os.path.join(datasets._GOLDEN, "data_des_dovekie.npz"))
+    d = np.load(os.path.join(datasets._DATA, "data_des_dovekie.npz"))
     assert np.array_equal(t["MU"], d["MU"]) and t["MU"].size == 1820
     u = loaders.union3_1_files(f"{REF}/y2026union3_1/raw-data/bins_union_3_1.csv", f"{REF}/y2026union3_1/raw-data/covariance.txt")
     for a, b in zip(u, datasets.union3_1()):
