@@ -4,6 +4,7 @@ import os
 import numpy as np
 
 from cosmology_model_fit_b200 import datasets, fits
+from cosmology_model_fit_b200 import spec as S
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -44,6 +45,9 @@ SPECS = {
     "bao_desi_cmb_union3": lambda: fits.bao_desi_cmb_union3(union3(), desi_fs()),
     "bao_desi_fs_lya_cmb": lambda: fits.bao_desi_fs_lya_cmb(desi_fs()),
     "cmb_cmb": lambda: fits.cmb_cmb(),
+    "cmb_cmb_act": lambda: fits.cmb_cmb(S.cmb_act()),
+    "cmb_cmb_planck_lens": lambda: fits.cmb_cmb(S.cmb_planck_lens()),
+    "cmb_cmb_planck": lambda: fits.cmb_cmb(S.cmb_planck()),
     "bao_desi_des5y_bbn_theta_star": lambda: fits.bao_desi_des5y_bbn_theta_star(des(), desi()),
     "bao_desi_cmb_pantheon": lambda: fits.bao_desi_cmb_pantheon(pantheon(), desi()),
     "bao_desi_cmb_des5y": lambda: fits.bao_desi_cmb_des5y(des(), desi_fs()),

@@ -283,6 +283,41 @@ def case_cmb_cmb():
     return dict(theta=theta, loglike=ll, blobs=blobs, theta_logp=tp, logp=logp, bounds=ref.bounds)
 
 
+def _cmb_cmb_with_module(modname):
+    """cmb/cmb.py with `import cmb.<modname> as cmb` in place of its checked-in `cmb.data_planck_act_compression`: the
+    constants module is pre-seeded under the name cmb/cmb.py imports (the reference's author swaps that import line by hand)."""
+    _enter_reference()
+    import importlib
+    mod = importlib.import_module(f"cmb.{modname}")
+    sys.modules["cmb.data_planck_act_compression"] = mod
+    import cmb as cmb_pkg
+    cmb_pkg.data_planck_act_compression = mod
+    import cmb.cmb as ref
+    assert ref.cmb is mod
+
+    theta = uniform_theta(ref.bounds, 24)
+    theta = np.vstack([theta, [[67.61, 0.0225, 0.1193]]])
+    ll = np.empty(len(theta)); blobs = np.empty((len(theta), 4))
+    for i, t in enumerate(theta):
+        ll[i], blobs[i] = ref.log_likelihood(t)
+    return dict(theta=theta, loglike=ll, blobs=blobs, priors=np.asarray(mod.DISTANCE_PRIORS), bounds=ref.bounds)
+
+
+def case_cmb_cmb_act():
+    """cmb/data_act_compression.py (ACT DR6 alone) behind cmb/cmb.py."""
+    return _cmb_cmb_with_module("data_act_compression")
+
+
+def case_cmb_cmb_planck_lens():
+    """cmb/data_planck_lens_compression.py (Planck PR3 + lensing) behind cmb/cmb.py."""
+    return _cmb_cmb_with_module("data_planck_lens_compression")
+
+
+def case_cmb_cmb_planck():
+    """cmb/data_planck_compression.py (Planck PR3) behind cmb/cmb.py."""
+    return _cmb_cmb_with_module("data_planck_compression")
+
+
 def case_bao_desi_des5y_bbn_theta_star():
     """Config 1 (as checked in): thawing w0, l_A-only CMB term, BBN prior, theta = (dM, H0, obh2, och2, w0)."""
     _stub_des()

@@ -133,6 +133,17 @@ def test_cmb_only_and_blobs(engines):
     assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"]))
 
 
+@pytest.mark.parametrize("name", ["cmb_cmb_act", "cmb_cmb_planck_lens", "cmb_cmb_planck"])
+def test_cmb_constant_sets_behind_cmb_cmb(engines, name):
+    """spec.cmb_act / cmb_planck_lens / cmb_planck against cmb/cmb.py run on the swapped constants module."""
+    g = golden(name)
+    e = engines(name)
+    chi2_close(-2 * e.log_likelihood(g["theta"]), -2 * g["loglike"])
+    cm = e.cmb(g["theta"])
+    blobs = np.c_[cm[:, 7], cm[:, 4], cm[:, 5] / 1000, cm[:, 3]]
+    assert rel_err(blobs, g["blobs"]) < DIST_RTOL
+
+
 def test_config1_log_probability(engines):
     g = golden("bao_desi_des5y_bbn_theta_star")
     e = engines("bao_desi_des5y_bbn_theta_star")

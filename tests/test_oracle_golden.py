@@ -104,6 +104,20 @@ def test_cmb_only_blobs():
     assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"]))
 
 
+@pytest.mark.parametrize("name", ["cmb_cmb_act", "cmb_cmb_planck_lens", "cmb_cmb_planck"])
+def test_cmb_constant_sets_behind_cmb_cmb(name):
+    """cmb/data_act_compression.py, data_planck_lens_compression.py, data_planck_compression.py swapped into cmb/cmb.py's import
+    (tests/golden/make_golden.py::_cmb_cmb_with_module): pins spec.cmb_act / cmb_planck_lens / cmb_planck."""
+    g = golden(name)
+    sp = spec(name)
+    assert np.array_equal(np.asarray(sp.cmb_consts.priors), g["priors"])
+    o = O.Oracle(sp)
+    assert np.max(np.abs(o.log_likelihood(g["theta"]) - g["loglike"])) < CHI2_ATOL
+    cm = o.cmb(g["theta"])
+    blobs = np.c_[cm[:, 7], cm[:, 4], cm[:, 5] / 1000, cm[:, 3]]
+    assert rel_err(blobs, g["blobs"]) < DIST_RTOL
+
+
 def test_config1_logprob_with_bbn_prior():
     g = golden("bao_desi_des5y_bbn_theta_star")
     o = O.Oracle(spec("bao_desi_des5y_bbn_theta_star"))
