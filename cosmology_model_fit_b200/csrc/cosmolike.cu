@@ -52,7 +52,7 @@ struct cl_ctx {
   double *h_theta = nullptr, *h_out = nullptr;  // pinned
   int64_t h_theta_cap = 0, h_out_cap = 0;
   int64_t launches = 0;
-  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0, opt_s12_lean = 1, opt_fuse_planes = 0;   // fused planes: measured slower, opt-in
+  int opt_gemm_ctas = 0, opt_s12_ctas = 0, opt_diag_skip = 1, opt_dbg = 0, opt_gemm_dynamic = 1, opt_group_rb = 0, opt_s12_lean = 1, opt_fuse_planes = 1;   // stage 2 writes the digit planes itself where it can
   int* d_counter = nullptr;
   // stage 3 on tcgen05 (chi2_ozaki.cuh): int8 digit planes of W (static) and of the residual rows (per pass)
   int opt_engine = CL_CHI2_ENGINE_TCGEN05, opt_slices = 7, opt_slice_tpb = 128;
@@ -422,6 +422,22 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
       TRY(upload(c, zs.data(), zs.size(), &dz));
       d.sn_zs = reinterpret_cast<const double2*>(dz);
       TRY(upload(c, obsp.data(), obsp.size(), &d.sn_obsp));
+      // quad-interleaved copies for the fused digit-plane path (friedmann.cuh): [q][m] = supernova 4 m + q, padded with the last one
+      const int q4 = 2 * kS12Threads;
+      if (n <= 4 * q4) {
+        std::vector<double> zs4((size_t)4 * q4 * 2), ob4((size_t)4 * q4);
+        for (int q = 0; q < 4; q++)
+          for (int m = 0; m < q4; m++) {
+            const int i = std::min(4 * m + q, n - 1);
+            zs4[2 * ((size_t)q * q4 + m)] = zs[2 * i]; zs4[2 * ((size_t)q * q4 + m) + 1] = zs[2 * i + 1];
+            ob4[(size_t)q * q4 + m] = obsp[i];
+          }
+        const double* dz4 = nullptr;
+        TRY(upload(c, zs4.data(), zs4.size(), &dz4));
+        d.sn_zs4 = reinterpret_cast<const double2*>(dz4);
+        TRY(upload(c, ob4.data(), ob4.size(), &d.sn_obsp4));
+        d.sn_q4 = q4;
+      }
     }
     if (s.n_vel > 0) TRY(upload(c, s.sn_vel_weight, (size_t)n * s.n_vel, &d.sn_vel_w));
     if (s.sn_mu_fixed) TRY(upload(c, s.sn_mu_fixed, (size_t)n, &d.sn_mu_fixed));
@@ -820,7 +836,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   const bool planes = large && c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384;
   // stage 2 writes the digit planes itself when the lean kernel runs its fast SN path and a thread can hold its share of the row
   const DevSpec& d = c->ds;
-  const bool fused = planes && c->opt_fuse_planes && c->opt_s12_lean && s12_lean(d, MODE_EVAL) && d.n_sn <= 8 * kS12Threads &&
+  const bool fused = planes && c->opt_fuse_planes && c->opt_s12_lean && s12_lean(d, MODE_EVAL) && d.sn_zs4 != nullptr && ((d.n_sn + 127) & ~127) <= 8 * kS12Threads &&
                      d.grid_uniform && (d.n_vel == 0 || d.vel_pm1) && d.sn_mu_fixed == nullptr && d.n_lin == 0 && !(c->opt_dbg & 2);
   if (fused) {
     rc = ensure_planes(c, rows, st);

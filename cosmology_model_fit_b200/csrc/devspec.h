@@ -36,6 +36,9 @@ struct DevSpec {
   const double* sn_pack;   // [n_sn][4] = {z_cmb, first velocity-template weight, 1 + z_hel, obs} (general path)
   const double2* sn_zs;    // [n_sn] {1 + z_cmb, w} with a +-1 step template, {z_cmb, 0} without one (fast path)
   const double* sn_obsp;   // [n_sn] obs - 25 - 5 log10(1 + z_hel)
+  const double2* sn_zs4;   // [4][sn_q4] quad-interleaved copy of sn_zs: entry [q][m] = supernova 4 m + q (fused digit planes)
+  const double* sn_obsp4;  // [4][sn_q4] the same for sn_obsp; both padded with copies of the last supernova
+  int sn_q4;
   const double *sn_vel_w, *sn_mat_small;
   const double* sn_mu_fixed;  // nullable [n_sn], NaN = model
   const double* sn_lin_t;     // [n_lin][n_sn]
@@ -77,7 +80,7 @@ struct Stage12Args {
   int nq;
   double *outDM, *outDH;  // MODE_DIST
   double* out;            // MODE_BAO [B][n_bao], MODE_CMB [B][8]
-  // fused digit planes (lean kernel, fast SN path, n_sn <= 8 threads-per-CTA): the residual row goes straight to the int8
+  // fused digit planes (lean kernel, fast SN path, planes_ld <= 8 threads-per-CTA): the residual row goes straight to the int8
   // planes of the tcgen05 contraction ([planes_S][B][planes_ld], the layout of k_oz_slice_rows) and R is not written
   signed char* planes;
   int64_t planes_ld;

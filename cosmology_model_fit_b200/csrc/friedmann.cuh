@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "devspec.h"
+#include "digits.cuh"
 
 namespace cosmolike {
 
@@ -179,13 +180,21 @@ __device__ __forceinline__ double fast_5log10(double x, uint32_t tab) {
   const double ed = (double)((hi >> 20) - 1023);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
   const double2 tc = lds_d2(tab + (((uint32_t)hi >> 9) & 0x7f0u));  // 16 bytes per entry, index = (hi >> 13) & 127
-  const double r = fma(m, tc.x, -1.0);
-  double p = kLog5Poly[7];
-#pragma unroll
-  for (int k = 6; k >= 1; k--) p = fma(p, r, kLog5Poly[k]);
+  const double r = fma(m, tc.x, -1.0);   // |r| < 2^-8
+  // degree 6 (the r^7 term is < 5e-18); the coefficients of r^4 .. r^6 are rounded to their high words (|effect| < 1e-17),
+  // which makes them instruction immediates instead of constant-bank loads
+  double p = fma(-0.3619120121002197, r, 0.4342944622039795);
+  p = fma(p, r, -0.5428681373596191);
+  p = fma(p, r, kLog5Poly[3]);
+  p = fma(p, r, kLog5Poly[2]);
+  p = fma(p, r, kLog5Poly[1]);
   double res = fma(ed, kLog5Two[0], tc.y);
   res = fma(ed, kLog5Two[1], res);
   return fma(r, p, res);
+}
+// true for a normal positive finite double (the domain of fast_5log10): one integer add and one unsigned compare on the high word
+__device__ __forceinline__ bool normal_positive(double x) {
+  return (uint32_t)(__double2hiint(x) - 0x00100000) < 0x7fe00000u;
 }
 
 // cubic Hermite segment in Horner form: y(t) on [node i, node i+1], t in [0,1], hd = h * slope
@@ -472,6 +481,9 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
             run = fma(prev + nxt, 0.5, run);
             prev = nxt;
           }
+          // the pad slot behind the chunk gets hd of the NEXT chunk's first node, so that the SN pass finds hd_{j+1} at a
+          // fixed 24 bytes behind node j's pair, also across a chunk boundary
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + 16u * kPPT + 8u), "d"(prev) : "memory");
         } else if (i0 < G) {
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
@@ -538,6 +550,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 
     // ================= stage 2: residuals =================
     const int n_sn = s.n_sn;
+    bool row_synced = false;   // the fused digit-plane path ends the row's shared-memory traffic with its own barrier
     if ((mode == MODE_EVAL || mode == MODE_RESID) && n_sn > 0 && !(CL_S12_DBG && (a.dbg & 2))) {
       const double offset = (s.col_offset >= 0 && !a.zero_offset) ? th[s.col_offset] : 0.0;
       const int64_t ld = mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
@@ -555,104 +568,108 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           ravg = rcp_pos(fma(-z_pec, z_pec, 1.0));
           rdif = -z_pec * ravg;
         }
-        const double inv_step = s.inv_step, z_last = s.z_last, obs_off = -offset;
-        const int imax = G - 2;
-        const uint32_t off_addr = s12_smem_u32(sm.off);
+        const double inv_step = s.inv_step, obs_off = -offset;
+        const uint32_t imax = (uint32_t)(G - 2);
+        // the shared-memory window base is laundered through an empty asm: the compiler otherwise rebuilds it (S2R + MOV + LEA)
+        // for every supernova instead of keeping one register
+        uint32_t gd_base = gd_addr;
+        asm volatile("" : "+r"(gd_base));
+        const uint32_t off_base = gd_base + (s12_smem_u32(sm.off) - gd_addr), tab_base = gd_base + (tab_addr - gd_addr);
         // floor(z/step) without conversion instructions: adding 1.5 * 2^52 leaves round(x) in the low word
         const double kMagic = 6755399441055744.0;
         auto resid = [&](double2 zs, double ob) -> double {
           const double zq = shift ? fma(zs.x, fma(zs.y, rdif, ravg), -1.0) : zs.x;  // (1+z_cmb)/(1+z_pec) - 1
-          if (zq > 1e-9 && zq < z_last) {
-            const double w = fma(zq, inv_step, -0.5) + kMagic;  // round(z/step - 1/2): the interval index (ties: either side)
-            const int j = min(__double2loint(w), imax);
+          const double w = fma(zq, inv_step, -0.5) + kMagic;  // round(z/step - 1/2): the interval index (ties: either side)
+          const uint32_t j = (uint32_t)__double2loint(w);
+          // inside the grid <=> 0 <= round(z/step - 1/2) <= G - 2: the high word of w is then the magic constant's and the low
+          // word the index (two integer compares; NaN, negative and huge redshifts fail the first)
+          if (__double2hiint(w) == 0x43380000 && j <= imax) {
             const double t = fma(zq, inv_step, -(w - kMagic));  // in [0, 1] up to rounding
-            const double2 n0 = lds_d2(gd_addr + ((uint32_t)(j + (j >> 4)) << 4));
-            const double2 n1 = lds_d2(gd_addr + ((uint32_t)(j + 1 + ((j + 1) >> 4)) << 4));
-            double base;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(base) : "r"(off_addr + ((uint32_t)(j >> 4) << 3)));
+            const uint32_t a0 = gd_base + ((j + (j >> 4)) << 4);
+            const double2 n0 = lds_d2(a0);
+            double hd1, base;   // hd of node j + 1: 24 bytes on (the pad slot behind a chunk carries the next chunk's first hd)
+            asm volatile("ld.shared.f64 %0, [%1+24];" : "=d"(hd1) : "r"(a0));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(base) : "r"(off_base + ((j >> 4) << 3)));
             // On the trapezoid-built grid D_M(i+1) - D_M(i) = (hd_i + hd_{i+1})/2, so the cubic Hermite segment
             // (interpolator.py:96-108) collapses to the quadratic y_i + t hd_i + t^2 (hd_{i+1} - hd_i)/2; the dropped
             // cubic coefficient is pure rounding of the cumulative sum (~1e-16 D_M).
-            const double dm = fma(t, fma(0.5 * t, n1.y - n0.y, n0.y), n0.x + base);
+            const double dm = fma(t, fma(0.5 * t, hd1 - n0.y, n0.y), n0.x + base);
             // the table log10 decodes the bits of a NORMAL POSITIVE number; a NaN / Inf / non-positive distance (NaN or Inf
             // parameters, E^2 < 0) takes the libm call below, which gives the reference's NaN (np.log10)
-            if (dm > 1e-300 && dm < 1e300) return (ob + obs_off) - fast_5log10(dm, tab_addr);
+            if (normal_positive(dm)) return (ob + obs_off) - fast_5log10(dm, tab_base);
             return (ob + obs_off) - 5.0 * log10(dm);
           }
           return (ob + obs_off) - 5.0 * log10(hermite_dm(s, sm.gd, sm.off, zq));  // outside the grid / non-positive distance
         };
         if (LEAN && a.planes != nullptr) {
-          // Fused digit planes: the thread keeps its residuals (columns tid + 256 k) in registers, the CTA agrees on the row's
-          // power-of-two scale, and the balanced base-256 digits go straight to the int8 planes - the same arithmetic as
-          // k_oz_slice_rows (chi2_ozaki.cuh), so the planes are the same bits; the FP64 row never goes through HBM.
+          // Fused digit planes: stage 2 writes the int8 planes of the tcgen05 contraction itself and the FP64 row never goes
+          // through HBM.  A thread owns FOUR CONSECUTIVE supernovae per trip (4 m .. 4 m + 3 for m = tid, tid + 256), keeps its
+          // <= 8 residuals in registers, the CTA agrees on the row's power-of-two scale with one barrier, and the balanced
+          // base-256 digits of the four values are one 64-bit add + XOR each and a 4 x S byte transpose (oz_digits4, the
+          // arithmetic of k_oz_slice_rows_reg: the planes are the same bits) - one 32-bit store per plane and trip, 128
+          // contiguous bytes per warp.  The static operands come from the quad-interleaved copies sn_zs4 / sn_obsp4
+          // ([4][sn_q4] with entry [q][m] = supernova 4 m + q, padded with copies of the last supernova), so every load is coalesced.
           double dv[8];
-          double mx = 0.0;
+          const int m4 = (int)(a.planes_ld >> 2);        // groups of four columns, a multiple of 32: whole warps drop out
+          const int q4 = s.sn_q4;
+#pragma unroll
+          for (int trip = 0; trip < 2; trip++) {
+            const int m = tid + trip * kS12Threads;
+            if (m < m4) {
+              const double2 z0 = __ldg(s.sn_zs4 + m), z1 = __ldg(s.sn_zs4 + q4 + m), z2 = __ldg(s.sn_zs4 + 2 * q4 + m), z3 = __ldg(s.sn_zs4 + 3 * q4 + m);
+              const double o0 = __ldg(s.sn_obsp4 + m), o1 = __ldg(s.sn_obsp4 + q4 + m), o2 = __ldg(s.sn_obsp4 + 2 * q4 + m), o3 = __ldg(s.sn_obsp4 + 3 * q4 + m);
+              dv[4 * trip + 0] = resid(z0, o0);
+              dv[4 * trip + 1] = resid(z1, o1);
+              dv[4 * trip + 2] = resid(z2, o2);
+              dv[4 * trip + 3] = resid(z3, o3);
+            } else {
+              dv[4 * trip + 0] = dv[4 * trip + 1] = dv[4 * trip + 2] = dv[4 * trip + 3] = 0.0;
+            }
+          }
+          // the row's power-of-two scale only needs the largest EXPONENT: an integer maximum over the high words of |delta|
+          // (NaN / Inf sort above every finite value), one REDUX per warp and one barrier
+          uint32_t mh = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) mh = max(mh, (uint32_t)__double2hiint(dv[k]) & 0x7fffffffu);
+          mh = __reduce_max_sync(0xffffffffu, mh);
+          uint32_t* s_mh = reinterpret_cast<uint32_t*>(sm.red);   // its own slot (the lean kernel has no block sums)
+          if (lane == 0) s_mh[warp] = mh;
+          // This barrier is also the row's LAST one: every thread has finished reading the grid nodes, so the next row may
+          // overwrite them, and the next row's parameter vector (parked here, before the barrier) is visible behind it.
+          if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
+          row_synced = true;
+          __syncthreads();
           {
-            // two SNe per trip, operands prefetched one trip ahead (the static arrays live in L2), as in the plain loop below
-            double2 zs0 = make_double2(1.0, 0.0), zs1 = zs0;
-            double ob0 = 0.0, ob1 = 0.0;
-            if (tid < n_sn) { zs0 = __ldg(s.sn_zs + tid); ob0 = __ldg(s.sn_obsp + tid); }
-            if (tid + kS12Threads < n_sn) { zs1 = __ldg(s.sn_zs + tid + kS12Threads); ob1 = __ldg(s.sn_obsp + tid + kS12Threads); }
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-              const double2 c0 = zs0, c1 = zs1;
-              const double o0 = ob0, o1 = ob1;
-              const int i0 = tid + 2 * t * kS12Threads, i1 = i0 + kS12Threads;
-              if (t < 3) {
-                if (i0 + 2 * kS12Threads < n_sn) { zs0 = __ldg(s.sn_zs + i0 + 2 * kS12Threads); ob0 = __ldg(s.sn_obsp + i0 + 2 * kS12Threads); }
-                if (i1 + 2 * kS12Threads < n_sn) { zs1 = __ldg(s.sn_zs + i1 + 2 * kS12Threads); ob1 = __ldg(s.sn_obsp + i1 + 2 * kS12Threads); }
-              }
-              dv[2 * t] = i0 < n_sn ? resid(c0, o0) : 0.0;
-              dv[2 * t + 1] = i1 < n_sn ? resid(c1, o1) : 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const double av = fabs(dv[k]);
-              mx = (av <= 1.7e308) ? fmax(mx, av) : __longlong_as_double(0x7ff0000000000000LL);   // NaN / Inf: the row is bad
-            }
+            const uint4 m0 = *reinterpret_cast<const uint4*>(s_mh), m1 = *reinterpret_cast<const uint4*>(s_mh + 4);
+            mh = max(max(max(m0.x, m0.y), max(m0.z, m0.w)), max(max(m1.x, m1.y), max(m1.z, m1.w)));
           }
-#pragma unroll
-          for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          if (lane == 0) sm.wsum[warp] = mx;   // free since the prefix offsets were formed
-          __syncthreads();
-#pragma unroll
-          for (int w = 0; w < kS12Threads / 32; w++) mx = fmax(mx, sm.wsum[w]);
-          const bool bad = !(mx <= 1.7e308);
+          const bool bad = mh >= 0x7ff00000u;
           const int S = a.planes_S, frac_bits = 6 + 8 * (S - 1);
-          int e = 0;
-          if (mx > 0.0 && !bad) e = ilogb(mx) + 1;
-          e = max(e, -900);
+          // 2^e = the next power of two above max |delta| (k_oz_slice_rows: ilogb + 1); a zero / denormal row takes the floor
+          const int e = (mh >> 20) ? (int)(mh >> 20) - 1022 : -900;
           const double up = __longlong_as_double((long long)(1023 + frac_bits - e) << 52);   // 2^(frac_bits - e)
-          const double lim = 1.01 * __longlong_as_double((long long)(1023 + frac_bits) << 52);
           if (tid == 0) a.rowscale[b] = bad ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)(1023 + e) << 52);
-          const unsigned long long bias = 0x0080808080808080ULL >> (8 * (8 - S));   // 0x80 at every digit position below the top one
-          // The digits are staged in shared memory - the grid nodes are dead once every thread has its residuals, which the
-          // barrier above guarantees - and leave the CTA as 16-byte stores (49 one-byte global stores per thread cost
-          // more than the slicing kernel they replace).
-          signed char* stage = reinterpret_cast<signed char*>(sm.gd);
-          const int pld = (int)a.planes_ld;
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const int i = tid + k * kS12Threads;
-            if (i < pld) {   // the padding columns n_sn .. planes_ld - 1 are zero digits
-              const long long v = i < n_sn ? __double2ll_rn(fmin(fmax(dv[k] * up, -lim), lim)) : 0LL;
-              const unsigned long long u = ((unsigned long long)v + bias) ^ bias;
-              const uint32_t ulo = (uint32_t)u, uhi = (uint32_t)(u >> 32);
-              signed char* q = stage + (S - 1) * pld + i;   // byte j of u is the digit of plane S - 1 - j
-#pragma unroll
-              for (int j = 0; j < 7; j++) {
-                if (j < S) *q = (signed char)((j < 4 ? ulo >> (8 * j) : uhi >> (8 * (j - 4))) & 0xffu);
-                q -= pld;
-              }
-            }
-          }
-          __syncthreads();
           signed char* __restrict__ prow = a.planes + b * a.planes_ld;
           const int64_t pstride = a.B * a.planes_ld;
-          const int ld16 = pld >> 4;   // planes_ld is a multiple of 128
-          for (int v = tid; v < S * ld16; v += kS12Threads) {
-            const int p = v / ld16, o = v - p * ld16;
-            *reinterpret_cast<uint4*>(prow + p * pstride + 16 * o) = *reinterpret_cast<const uint4*>(stage + p * pld + 16 * o);
+#pragma unroll
+          for (int trip = 0; trip < 2; trip++) {
+            const int m = tid + trip * kS12Threads;
+            if (m < m4) {
+              long long v[4];
+#pragma unroll
+              for (int q = 0; q < 4; q++)   // |v| <= 2^frac_bits for a finite row (a bad row's digits are garbage: its scale is NaN)
+                v[q] = __double2ll_rn(dv[4 * trip + q] * up);
+              if (4 * m + 4 > n_sn) {   // the group that straddles the end of the row, and the padding columns: zero digits
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (4 * m + q >= n_sn) v[q] = 0LL;
+              }
+              signed char* dst = prow + 4 * m;
+#define CL_STORE_PLANES(SS)                                                                 \
+              { uint32_t w[SS]; oz_digits4<SS>(v, w);                                        \
+                _Pragma("unroll") for (int p = 0; p < SS; p++) { *reinterpret_cast<uint32_t*>(dst) = w[p]; dst += pstride; } }
+              if (S == 7) CL_STORE_PLANES(7) else if (S == 6) CL_STORE_PLANES(6) else CL_STORE_PLANES(5)
+#undef CL_STORE_PLANES
+            }
           }
         } else {
         // two SNe per thread per trip (independent dependency chains); operands are prefetched one trip ahead
@@ -717,7 +734,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           }
           const double DM = dm_of(zq);
           // 5 log10 through the shared-memory table of the fast path (|err| < 4e-16) for normal positive arguments
-          auto log5 = [&](double x) { return (x > 1e-300 && x < 1e300) ? fast_5log10(x, tab_addr) : 5.0 * log10(x); };
+          auto log5 = [&](double x) { return normal_positive(x) ? fast_5log10(x, tab_addr) : 5.0 * log10(x); };
           double mu;
           if (s.sn_mu_fixed != nullptr && isfinite(__ldg(s.sn_mu_fixed + i))) {
             // SH0ES calibrator: fixed distance modulus, mu_corr = 5 log10(D_M(z_cosmo)/D_M(z_cmb)) still applies
@@ -815,10 +832,10 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     const double rd_out = (need_rd && tid == 0) ? sm.scal[1] : 0.0;
     // The theta row of the next iteration (loaded into a register at the top) is parked in the other buffer; no thread
     // reads that buffer in this iteration (the previous row's readers all passed this iteration's first barrier).
-    if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
+    if (stage_next && !row_synced) sm.theta[tb ^ 1][tid] = th_next;
     // The next iteration stores its grid nodes before its first barrier, so every thread must be done reading gd.
     if (need_red) block_sum<5>(v, sm.red);
-    else __syncthreads();
+    else if (!row_synced) __syncthreads();
 
     if (tid == 0) {
       double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
