@@ -64,8 +64,9 @@ struct cl_ctx {
   int64_t oz_cap_rows = 0;
   CUtensorMap tmWs{};
   // accuracy guard of the tcgen05 engine (friedmann.cuh: GuardArgs): static part of the a-priori bound and the fallback state
-  double oz_omega = 0.0;             // sqrt(sum_n (nnz_n 2^eW_n)^2) over the rows of W
-  int opt_guard = 1;
+  double oz_omega = 0.0;             // worst case: sqrt(sum_n (nnz_n 2^eW_n)^2) over the rows of W
+  double oz_omega_pr = 0.0;          // probabilistic: max_n sqrt(nnz_n) 2^eW_n
+  int opt_guard = 1, opt_guard_mode = 0;   // mode 0: probabilistic bound (lambda = 8), 1: worst case
   double guard_abs = 5e-7, guard_rel = 1e-12;
   int* d_guard = nullptr;            // [0] rows flagged since creation, [1] in the current pass, [2 + rb] row-block marks
   unsigned char* d_rowflag = nullptr;
@@ -423,8 +424,8 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
       d.sn_zs = reinterpret_cast<const double2*>(dz);
       TRY(upload(c, obsp.data(), obsp.size(), &d.sn_obsp));
       // quad-interleaved copies for the fused digit-plane path (friedmann.cuh): [q][m] = supernova 4 m + q, padded with the last one
-      const int q4 = 2 * kS12Threads;
-      if (n <= 4 * q4) {
+      const int q4 = ((n + 127) & ~127) / 4;   // covers the padded plane pitch (a multiple of 128 columns)
+      {
         std::vector<double> zs4((size_t)4 * q4 * 2), ob4((size_t)4 * q4);
         for (int q = 0; q < 4; q++)
           for (int m = 0; m < q4; m++) {
@@ -466,7 +467,7 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
       }
       c->uu = (double)uu;
       {  // static part of the digit-plane error bound: every row of W with its power-of-two scale (as k_oz_slice_rows forms it)
-        long double om2 = 0.0L;
+        long double om2 = 0.0L, ompr = 0.0L;
         for (int i = 0; i < n; i++) {
           double mx = 0.0;
           int nnz = 0;
@@ -474,8 +475,10 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
           const int e = std::max(mx > 0.0 ? ilogb(mx) + 1 : 0, -900);
           const long double t = (long double)nnz * ldexpl(1.0L, e);
           om2 += t * t;
+          ompr = std::max(ompr, sqrtl((long double)nnz) * ldexpl(1.0L, e));
         }
         c->oz_omega = (double)sqrtl(om2);
+        c->oz_omega_pr = (double)ompr;
       }
       if (d.sn_small) {
         std::vector<double> Wc((size_t)n * n);
@@ -563,6 +566,7 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (n == "stage12_lean") { c->opt_s12_lean = value != 0; return CL_OK; }
   if (n == "fuse_planes") { c->opt_fuse_planes = value != 0; return CL_OK; }
   if (n == "chi2_guard") { c->opt_guard = value != 0; return CL_OK; }
+  if (n == "chi2_guard_mode") { if (value != 0 && value != 1) return fail(c, CL_E_INVALID, "chi2_guard_mode must be 0 (probabilistic bound) or 1 (worst case)"); c->opt_guard_mode = (int)value; return CL_OK; }
   if (n == "gemm_dynamic") { c->opt_gemm_dynamic = value ? 1 : 0; return CL_OK; }
   if (n == "gemm_group_rb") { c->opt_group_rb = (int)value; return CL_OK; }
   if (n == "gemm_diag_skip") { c->opt_diag_skip = value ? 1 : 0; return CL_OK; }   // DMMA engine only
@@ -589,11 +593,16 @@ extern "C" int cl_set_option_f64(cl_ctx* c, const char* name, double value) {
 
 // eps_S of the digit-plane error bound: 2^(2 - 8 S) (1 + (S - 1) 256 / 255)
 static double oz_eps(int S) { return ldexp(1.0 + (S - 1) * (256.0 / 255.0), 2 - 8 * S); }
+constexpr double kGuardLambda = 8.0;   // the probabilistic bound is exceeded with probability < 2 exp(-lambda^2 / 2) = 2.5e-14 per row
+// coefficient of the linear term of the selected a-priori bound (friedmann.cuh: GuardArgs)
+static double oz_kappa(const cl_ctx* c) {
+  return c->opt_guard_mode ? oz_eps(c->opt_slices) * c->oz_omega : kGuardLambda * oz_eps(c->opt_slices) * c->oz_omega_pr;
+}
 
 extern "C" int cl_guard_info(cl_ctx* c, double out[4]) {
   if (!c || !out) return CL_E_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
-  out[0] = out[1] = 0.0; out[2] = c->oz_omega; out[3] = oz_eps(c->opt_slices) * c->oz_omega;
+  out[0] = out[1] = 0.0; out[2] = c->opt_guard_mode ? c->oz_omega : c->oz_omega_pr; out[3] = oz_kappa(c);
   if (c->d_guard) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     int h[2] = {0, 0};
@@ -861,7 +870,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   const bool guard = planes && c->opt_guard;
   GuardArgs q{};
   if (guard) {
-    q.rowscale = c->d_rscale; q.kappa = oz_eps(c->opt_slices) * c->oz_omega; q.tol_abs = c->guard_abs; q.tol_rel = c->guard_rel;
+    q.rowscale = c->d_rscale; q.kappa = oz_kappa(c); q.kappa_sq = oz_eps(c->opt_slices) * c->oz_omega; q.tol_abs = c->guard_abs; q.tol_rel = c->guard_rel;
     q.guard = c->d_guard; q.rowflag = c->d_rowflag; q.only_flagged = 0;
     CUDA_TRY(c, cudaMemsetAsync(c->d_guard + 1, 0, (1 + (size_t)(rows + 127) / 128) * sizeof(int), st));
   }

@@ -601,6 +601,46 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           }
           return (ob + obs_off) - 5.0 * log10(hermite_dm(s, sm.gd, sm.off, zq));  // outside the grid / non-positive distance
         };
+        // Four supernovae at once, branch-free: the in-range case (every supernova of a sane parameter vector) is straight-line
+        // code, so the four dependency chains interleave and their shared-memory latencies overlap; whether ALL four took
+        // the fast formulas is one flag, and the rare group with an exception (a redshift outside the grid, a NaN / Inf /
+        // non-positive distance) is redone by the scalar function above.  Same arithmetic per supernova: same bits.
+        auto resid4 = [&](const double2 (&zs)[4], const double (&ob)[4], double (&d)[4]) {
+          double zq[4], w[4], dm[4];
+          uint32_t j[4];
+          bool ok = true;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            zq[q] = shift ? fma(zs[q].x, fma(zs[q].y, rdif, ravg), -1.0) : zs[q].x;
+            w[q] = fma(zq[q], inv_step, -0.5) + kMagic;
+            const uint32_t jj = (uint32_t)__double2loint(w[q]);
+            ok = ok && __double2hiint(w[q]) == 0x43380000 && jj <= imax;
+            j[q] = min(jj, imax);   // a valid address also when the group is going to be redone
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double t = fma(zq[q], inv_step, -(w[q] - kMagic));
+            const uint32_t a0 = gd_base + ((j[q] + (j[q] >> 4)) << 4);
+            const double2 n0 = lds_d2(a0);
+            double hd1, base;
+            asm volatile("ld.shared.f64 %0, [%1+24];" : "=d"(hd1) : "r"(a0));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(base) : "r"(off_base + ((j[q] >> 4) << 3)));
+            dm[q] = fma(t, fma(0.5 * t, hd1 - n0.y, n0.y), n0.x + base);
+            ok = ok && normal_positive(dm[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) d[q] = (ob[q] + obs_off) - fast_5log10(dm[q], tab_base);
+          if (!ok) {   // (unrolled: a run-time index would move the operand arrays to local memory)
+#pragma unroll
+            for (int q = 0; q < 4; q++) d[q] = resid(zs[q], ob[q]);
+          }
+        };
+        // static operands of supernovae 4 m .. 4 m + 3 from the quad-interleaved copies ([q][m], coalesced for consecutive m)
+        const int q4 = s.sn_q4;
+        auto load4 = [&](int m, double2 (&zs)[4], double (&ob)[4]) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) { zs[q] = __ldg(s.sn_zs4 + q * q4 + m); ob[q] = __ldg(s.sn_obsp4 + q * q4 + m); }
+        };
         if (LEAN && a.planes != nullptr) {
           // Fused digit planes: stage 2 writes the int8 planes of the tcgen05 contraction itself and the FP64 row never goes
           // through HBM.  A thread owns FOUR CONSECUTIVE supernovae per trip (4 m .. 4 m + 3 for m = tid, tid + 256), keeps its
@@ -611,20 +651,18 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           // ([4][sn_q4] with entry [q][m] = supernova 4 m + q, padded with copies of the last supernova), so every load is coalesced.
           double dv[8];
           const int m4 = (int)(a.planes_ld >> 2);        // groups of four columns, a multiple of 32: whole warps drop out
-          const int q4 = s.sn_q4;
 #pragma unroll
           for (int trip = 0; trip < 2; trip++) {
             const int m = tid + trip * kS12Threads;
+            double d[4] = {0.0, 0.0, 0.0, 0.0};
             if (m < m4) {
-              const double2 z0 = __ldg(s.sn_zs4 + m), z1 = __ldg(s.sn_zs4 + q4 + m), z2 = __ldg(s.sn_zs4 + 2 * q4 + m), z3 = __ldg(s.sn_zs4 + 3 * q4 + m);
-              const double o0 = __ldg(s.sn_obsp4 + m), o1 = __ldg(s.sn_obsp4 + q4 + m), o2 = __ldg(s.sn_obsp4 + 2 * q4 + m), o3 = __ldg(s.sn_obsp4 + 3 * q4 + m);
-              dv[4 * trip + 0] = resid(z0, o0);
-              dv[4 * trip + 1] = resid(z1, o1);
-              dv[4 * trip + 2] = resid(z2, o2);
-              dv[4 * trip + 3] = resid(z3, o3);
-            } else {
-              dv[4 * trip + 0] = dv[4 * trip + 1] = dv[4 * trip + 2] = dv[4 * trip + 3] = 0.0;
+              double2 zs[4];
+              double ob[4];
+              load4(m, zs, ob);
+              resid4(zs, ob, d);
             }
+#pragma unroll
+            for (int q = 0; q < 4; q++) dv[4 * trip + q] = d[q];
           }
           // the row's power-of-two scale only needs the largest EXPONENT: an integer maximum over the high words of |delta|
           // (NaN / Inf sort above every finite value), one REDUX per warp and one barrier
@@ -672,29 +710,21 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
             }
           }
         } else {
-        // two SNe per thread per trip (independent dependency chains); operands are prefetched one trip ahead
-        // because all of L1 is carved out as shared memory and the static arrays live in L2
-        const double2* __restrict__ zsp = s.sn_zs + tid;
-        const double* __restrict__ obp = s.sn_obsp + tid;
-        double* __restrict__ outp = to_smem ? (sm.vec + CL_MAX_BAO + CL_MAX_CC + tid) : (Rrow + tid);
-        const int n_pair = (n_sn - tid + 2 * kS12Threads - 1) / (2 * kS12Threads);  // trips for this thread
-        int i = tid;
-        double2 zs0 = make_double2(1.0, 0.0), zs1 = zs0;
-        double ob0 = 0.0, ob1 = 0.0;
-        if (i < n_sn) { zs0 = __ldg(zsp); ob0 = __ldg(obp); }
-        if (i + kS12Threads < n_sn) { zs1 = __ldg(zsp + kS12Threads); ob1 = __ldg(obp + kS12Threads); }
-        for (int trip = 0; trip < n_pair; trip++) {
-          const double2 c0 = zs0, c1 = zs1;
-          const double o0 = ob0, o1 = ob1;
-          const bool v1 = i + kS12Threads < n_sn;
-          zsp += 2 * kS12Threads; obp += 2 * kS12Threads;
-          if (i + 2 * kS12Threads < n_sn) { zs0 = __ldg(zsp); ob0 = __ldg(obp); }
-          if (i + 3 * kS12Threads < n_sn) { zs1 = __ldg(zsp + kS12Threads); ob1 = __ldg(obp + kS12Threads); }
-          const double d0 = resid(c0, o0);
-          const double d1 = resid(c1, o1);
-          outp[0] = d0;
-          if (v1) outp[kS12Threads] = d1;
-          outp += 2 * kS12Threads; i += 2 * kS12Threads;
+        // four consecutive supernovae per thread and trip; the residuals leave as two 16-byte stores (the row is 128-byte aligned)
+        double* __restrict__ outp = to_smem ? (sm.vec + CL_MAX_BAO + CL_MAX_CC) : Rrow;
+        const int m4 = (n_sn + 3) >> 2;
+        for (int m = tid; m < m4; m += kS12Threads) {
+          double2 zs[4];
+          double ob[4], d[4];
+          load4(m, zs, ob);
+          resid4(zs, ob, d);
+          if (4 * m + 4 <= n_sn && !to_smem && mode != MODE_RESID) {   // MODE_RESID rows are packed (pitch n_sn): scalar stores
+            *reinterpret_cast<double2*>(outp + 4 * m) = make_double2(d[0], d[1]);
+            *reinterpret_cast<double2*>(outp + 4 * m + 2) = make_double2(d[2], d[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (4 * m + q < n_sn) outp[4 * m + q] = d[q];
+          }
         }
         }
       } else {
@@ -891,20 +921,27 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 // ---- finalize: combine the SN chi2 partials of stage 3 with the scalar terms ----
 // Accuracy guard of the int8 digit-plane engine ("error bound"): with S planes every residual row and
 // every row of W carries FRAC = 8 S - 2 fractional bits below its power-of-two scale, and the products with i + j >= S are
-// dropped, so per component  |dy_n| <= 2^eR_b 2^eW_n nnz_n eps_S,  eps_S = 2^(2 - 8 S) (1 + (S - 1) 256 / 255),  hence
-//   |d chi2_b| <= 2 sqrt(chi2_b) rho_b + rho_b^2,   rho_b = 2^eR_b kappa,   kappa = eps_S sqrt(sum_n (nnz_n 2^eW_n)^2)
-// (kappa is static: formed by cl_create).  Rows whose bound exceeds max(tol_abs, tol_rel chi2) are flagged and recomputed
-// on the FP64 tensor pipe by the fallback pass (k_chi2_gemm restricted to the flagged 128-row blocks).
+// dropped, so every term of y_n = sum_k W_nk r_k is off by at most  c_n 2^eR_b,  c_n = 2^eW_n eps_S,
+// eps_S = 2^(2 - 8 S) (1 + (S - 1) 256 / 255).  Two a-priori bounds on |d chi2_b| = |2 y.dy + dy.dy| follow:
+//   worst case (every error at its maximum, all of one sign):  2 sqrt(chi2_b) rho_b + rho_b^2,  rho_b = 2^eR_b kappa_wc,
+//       kappa_wc = eps_S sqrt(sum_n (nnz_n 2^eW_n)^2);
+//   probabilistic (the term errors are roundings of balanced digits: bounded, mean zero, independent; Hoeffding over the
+//       N (N + 1) / 2 terms of y.dy):  2 lambda sqrt(chi2_b) 2^eR_b kappa_pr + rho_b^2,  kappa_pr = eps_S max_n sqrt(nnz_n) 2^eW_n,
+//       exceeded with probability < 2 exp(-lambda^2 / 2) per row (lambda = 8: 2.5e-14).
+// `kappa` below is the coefficient of the linear term of the selected bound (cl_set_option "chi2_guard_mode": 0 =
+// probabilistic, the default; 1 = worst case), `kappa_sq` the worst-case one of the quadratic term (both static: formed by
+// cl_create).  Rows whose bound exceeds max(tol_abs, tol_rel chi2) are flagged and recomputed on the FP64 tensor pipe by the
+// fallback pass (k_chi2_gemm restricted to the flagged 128-row blocks).
 struct GuardArgs {
   const double* rowscale;   // nullptr = guard off
-  double kappa, tol_abs, tol_rel;
+  double kappa, kappa_sq, tol_abs, tol_rel;
   int* guard;               // [0] rows flagged since cl_create, [1] rows flagged in this pass, [2 + rb] row-block marks
   unsigned char* rowflag;   // [B] 1 = this row is recomputed by the fallback pass
   int only_flagged;         // fallback pass: rewrite the flagged rows only (and do not flag again)
 };
 __device__ __forceinline__ bool guard_row(const GuardArgs& q, int64_t b, double chi2_sn) {
-  const double rho = q.rowscale[b] * q.kappa;
-  const double bound = fma(2.0 * sqrt(fmax(chi2_sn, 0.0)), rho, rho * rho);
+  const double rho = q.rowscale[b] * q.kappa, rho_sq = q.rowscale[b] * q.kappa_sq;
+  const double bound = fma(2.0 * sqrt(fmax(chi2_sn, 0.0)), rho, rho_sq * rho_sq);
   const bool flag = bound > fmax(q.tol_abs, q.tol_rel * chi2_sn);   // NaN rows (bad residuals) compare false: chi2 stays NaN
   q.rowflag[b] = flag ? 1 : 0;
   if (flag) { q.guard[2 + (b >> 7)] = 1; atomicAdd(q.guard + 1, 1); atomicAdd(q.guard, 1); }

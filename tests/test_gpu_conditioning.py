@@ -120,12 +120,15 @@ def test_fp64_engine_vs_extended_precision(prepared, kind, cond, n_sn):
     assert np.all(err <= _tol(p)), (kind, cond, n_sn, p["cond"], err.max(), p["ref_err"].max(), np.abs(p["truth"]).max())
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("kind,cond,n_sn", CASES)
-def test_digit_plane_engine_guarded_vs_extended_precision(prepared, kind, cond, n_sn):
-    """Default engine (7 planes, guard on): every value meets the bar, and flagged rows carry the FP64 engine's bits."""
+def test_digit_plane_engine_guarded_vs_extended_precision(prepared, kind, cond, n_sn, mode):
+    """Default engine (7 planes, guard on): every value meets the bar, and flagged rows carry the FP64 engine's bits - with the
+    probabilistic bound (mode 0, the default) and with the worst-case bound (mode 1); either bound really bounds the error."""
     from cosmology_model_fit_b200 import Engine
     p = prepared(kind, cond, n_sn)
     with Engine(p["spec"]) as e:
+        e.set_option("chi2_guard_mode", mode)
         got = e.components(p["theta"])[:, 0]
         info = e.guard_info()
         e.set_option("chi2_guard", 0)
@@ -138,7 +141,7 @@ def test_digit_plane_engine_guarded_vs_extended_precision(prepared, kind, cond, 
     # (+ the rounding of the FP64 contraction itself, which the bound does not cover)
     scale = np.ldexp(1.0, np.frexp(np.abs(p["R"]).max(axis=1))[1])
     rho = scale * info["kappa"]
-    bound = 2 * np.sqrt(np.abs(fp64)) * rho + rho**2
+    bound = 2 * np.sqrt(np.abs(fp64)) * rho + (rho if mode else 0.0)**2   # (mode 0: the quadratic term is the worst-case one, ~1e-17)
     assert np.all(np.abs(raw - fp64) <= bound + 4.0 * p["ref_err"] + 1e-13 * np.abs(fp64)), (np.abs(raw - fp64).max(), bound.max())
     flagged = bound > np.maximum(5e-7, 1e-12 * np.abs(raw))
     # rows the guard recomputed are bit-identical to the FP64 engine; the others to the unguarded planes
@@ -147,7 +150,7 @@ def test_digit_plane_engine_guarded_vs_extended_precision(prepared, kind, cond, 
     calm = bound < 0.5 * np.maximum(5e-7, 1e-12 * np.abs(raw))
     assert np.array_equal(got[calm], raw[calm])
     assert info["rows_last_pass"] >= int(sure.sum()) and info["rows_last_pass"] <= int((~calm).sum())
-    if kind == "outlier":
+    if kind == "outlier" and mode == 1:
         assert flagged.all() and info["rows_last_pass"] == p["theta"].shape[0]
 
 
@@ -189,6 +192,7 @@ def test_guard_is_batch_independent():
     sp, _ = _case("modes", 1e8, 1701)
     theta = uniform_theta(sp.theta_box, 700, seed=5)
     with Engine(sp) as e:
+        e.set_option("chi2_guard_mode", 1)     # worst-case bound
         e.set_option("chi2_guard_abs", 2e-8)   # a threshold inside this batch's range of bounds (1e-8 .. 3e-8): it splits the batch
         full = e.chi_squared(theta)
         n_flag = e.guard_info()["rows_last_pass"]
