@@ -36,6 +36,10 @@ UNIT = "evals/s"
 #: tcgen05.mma kind::i8 issue rate measured on this pool's B200 (profiles/r02_ubench_umma_i8.log), int8 TOP/s
 I8_PEAK_TOPS = 4485.0
 #: DRAM bytes per launch of k_chi2_ozaki<S> from ncu --set full (profiles/), keyed by (planes, N, B)
+#: FP64 pipe of one B200: 64 DFMA per clock and SM (DMMA issue peak measured 37.1 TFLOP/s, profiles/r01_ubench_fp64.log)
+FP64_PIPE_TFLOPS = 37.1
+#: algorithmic FP64 flops of stage 1+2 per evaluation: 9 per grid node + 40 per supernova
+S12_FLOPS_PER_EVAL = lambda n_sn, n_grid: 9.0 * n_grid + 40.0 * n_sn
 OZ_DRAM_BYTES = {(7, 1701, 65536): 0.910e9}   # profiles/r02m_ncu_full_summary.txt: 0.879e9 read + 0.031e9 written
 
 
@@ -159,7 +163,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = args.steps * n / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, spec, world, sample_rows=n),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
@@ -173,9 +177,9 @@ def workload_config(args, spec, world, sample_rows=None):
     cfg = {"workload": f"W0 sn.pantheon shape: flat LCDM + v-step(z_turn=0.15), theta=(M,H0,Om,v), Pantheon+ N={args.n_sn} "
                        f"full covariance (synthetic SPD stand-in), z-grid 4000, batch {args.batch} per GPU",
            "n_sn": args.n_sn, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "n_grid": int(spec.z_grid.size),
-           "parallelism": f"theta rows sharded over {world} GPU(s), statics replicated, NCCL all-gather of logL",
-           "l2": "no explicit flush: each step writes+reads the residual matrix (B*N*8 = 0.9 GB) which exceeds the 126 MB L2; "
-                 "theta batches rotate between steps"}
+           "parallelism": f"theta rows sharded over {world} GPU(s), statics replicated, NCCL all-gather of logL (the library's own communicator)",
+           "l2": "no explicit flush: each step writes+reads the int8 digit planes of the residual rows (7 B*N = 0.8 GB at B = 65536) which "
+                 "exceed the 126 MB L2; theta batches rotate between steps"}
     if sample_rows is not None:
         cfg["cpu_sample_rows_per_step"] = sample_rows
     return cfg
@@ -194,12 +198,19 @@ def main():
     ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "dmma"], help="stage-3 engine of the headline run")
     ap.add_argument("--slices", type=int, default=7, choices=[5, 6, 7], help="int8 digit planes of the tcgen05 engine")
     ap.add_argument("--no-alt", action="store_true", help="skip timing the other stage-3 engines")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch rows per GPU (default, the metric's shape); strong: --batch rows in total, split over the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.global_batch = args.batch * world if args.scaling == "weak" else args.batch
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit("--scaling strong needs --batch divisible by the number of GPUs")
+        args.batch //= world          # rows per GPU from here on
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -227,15 +238,20 @@ def main():
     n_rot = 4  # distinct theta batches rotated between steps
     host_batches = [theta_batch(spec, B, seed=1000 + rank * 16 + i) for i in range(n_rot)]
     d_theta = [torch.from_numpy(h).to(dev) for h in host_batches]
-    d_out = torch.empty(B, dtype=torch.float64, device=dev)
-    d_all = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    d_all = torch.empty(B * world, dtype=torch.float64, device=dev)
+    d_out = d_all[rank * B:(rank + 1) * B]      # this rank's results, gathered in place
     stream = torch.cuda.Stream(dev)  # a non-default stream: the kernels, the NCCL gather and the timing events share it
     torch.cuda.set_stream(stream)
+    sh = None
+    if world > 1:   # the library's own NCCL communicator (cl_comm_init); torch.distributed ships the id and keeps the barriers
+        from cosmology_model_fit_b200.parallel import ShardedEngine
+        sh = ShardedEngine(spec, device=local_rank, engine=eng)
 
     def step(i):
-        eng.eval_device(d_theta[i % n_rot].data_ptr(), B, nd, OUT_LOGLIKE, d_out.data_ptr(), stream.cuda_stream)
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_out)
+            eng.eval_allgather_device(d_theta[i % n_rot].data_ptr(), B, nd, OUT_LOGLIKE, d_all.data_ptr(), stream.cuda_stream)
+        else:
+            eng.eval_device(d_theta[i % n_rot].data_ptr(), B, nd, OUT_LOGLIKE, d_out.data_ptr(), stream.cuda_stream)
 
     peak_tf = dgemm_peak_tflops(torch, dev)
     torch.cuda.synchronize(dev)
@@ -280,13 +296,32 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end from HOST buffers: H2D of theta and D2H of logL inside the timed region, every step ----
-    # 1 GPU: Engine.log_likelihood(batch) -> cl_eval (pinned staging inside the library).
-    # N GPUs: ShardedEngine.log_likelihood(global batch): each rank uploads its row shard, evaluates, NCCL all-gather,
-    #         and every rank downloads the full result vector (what a sampler driving N GPUs needs).
+    # 1 GPU: Engine.log_likelihood(batch, out=) -> cl_eval, page-locked caller buffers (DMA as they are); the same with ordinary
+    #        numpy arrays (one staging copy each way inside the library) is reported beside it as e2e_pageable.
+    # N GPUs: ShardedEngine.log_likelihood(global batch, root=0) -> cl_eval_allgather: each rank uploads its row shard,
+    #        evaluates, one ncclAllGather inside the library, rank 0 downloads the gathered vector (the master / worker shape
+    #        of the reference's Pool.map); the variant where EVERY rank downloads it is reported as e2e_all_ranks.
     e2e_steps = max(3, min(args.steps, 10))
+
+    def time_e2e(call):
+        for i in range(2):
+            call(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            call(i)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return B * world * e2e_steps / dt
+
+    e2e_extra = {}
     if world > 1:
-        from cosmology_model_fit_b200.parallel import ShardedEngine
-        sh = ShardedEngine(spec, device=local_rank, engine=eng)
         global_batches = [np.concatenate([theta_batch(spec, B, seed=1000 + r * 16 + i) for r in range(world)]) for i in range(2)]
         pinned_global = []
         for gb in global_batches:   # page-locked global batches and result vector (Engine.pinned_empty): DMA without staging copies
@@ -294,9 +329,13 @@ def main():
             pb[...] = gb
             pinned_global.append(pb)
         pinned_all = eng.pinned_empty((B * world,))
-        e2e_call = lambda i: sh.log_likelihood(pinned_global[i % 2], out=pinned_all)
-        e2e_api = "ShardedEngine.log_likelihood(global batch, out=) on page-locked host arrays: H2D of the row shard, cl_eval_device, NCCL all-gather, D2H of the full vector on every rank"
-        h2d, d2h = B * nd * 8, B * world * 8
+        e2e_value = time_e2e(lambda i: sh.log_likelihood(pinned_global[i % 2], out=pinned_all if rank == 0 else None, root=0))
+        e2e_extra["e2e_all_ranks"] = {"value": time_e2e(lambda i: sh.log_likelihood(pinned_global[i % 2], out=pinned_all)), "unit": UNIT,
+                                      "d2h_bytes_per_step": B * world * 8 * world,
+                                      "note": "every rank downloads the gathered vector (SPMD samplers that all need every value)"}
+        e2e_api = ("ShardedEngine.log_likelihood(global batch, out=, root=0) on page-locked host arrays -> cl_eval_allgather: H2D of the row shard on "
+                   "every rank, ncclAllGather inside the library, D2H of the gathered vector on rank 0")
+        h2d, d2h = B * nd * 8 * world, B * world * 8
     else:
         # theta batches and the result buffer live in page-locked arrays (Engine.pinned_empty): cl_eval moves them by DMA
         pinned_batches = []
@@ -305,23 +344,11 @@ def main():
             pb[...] = hb
             pinned_batches.append(pb)
         pinned_out = eng.pinned_empty((B,))
-        e2e_call = lambda i: eng.log_likelihood(pinned_batches[i % n_rot], out=pinned_out)
+        e2e_value = time_e2e(lambda i: eng.log_likelihood(pinned_batches[i % n_rot], out=pinned_out))
+        e2e_extra["e2e_pageable"] = {"value": time_e2e(lambda i: eng.log_likelihood(host_batches[i % n_rot])), "unit": UNIT,
+                                     "note": "ordinary numpy arrays in and out (what emcee / nautilus hand over): one staging copy each way inside cl_eval"}
         e2e_api = "Engine.log_likelihood(batch, out=) on Engine.pinned_empty() host arrays -> cl_eval (DMA from / to the caller's page-locked buffers)"
         h2d, d2h = B * nd * 8, B * 8
-    for i in range(2):
-        e2e_call(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_call(i)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
 
     # ---- the other stage-3 engines on the same batches (rank 0, one GPU): device-resident, 20 steps each ----
     engines = None
@@ -355,7 +382,7 @@ def main():
         flops = B * (N * N + 2.0 * N)  # algorithmic FP64: forward-substitution-equivalent MACs*2
         pk = measured_peaks()
         hbm_peak = pk.get("hbm_gbs", 6650.0)
-        s12_bytes = B * (8.0 * nd + 8.0 * N + 8.0)  # theta in, residual row out, aux
+        s12_bytes = B * (8.0 * nd + (args.slices if args.engine == "tcgen05" else 8.0) * N + 8.0 * 8)  # theta in, digit planes (or the FP64 row) out, aux
         if args.engine == "dmma":
             ach = flops / (gemm_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "k_chi2_gemm (stage 3, FP64 DMMA)", "achieved": ach, "peak": peak_tf,
@@ -387,24 +414,37 @@ def main():
                                       "DESIGN.md section 4"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64",
             "dtype_note": "all stages FP64" if args.engine == "dmma" else
                           "FP64 throughout; stage 3 multiplies exact int8 digit planes of the FP64 operands (int32 accumulation, FP64 recombination)",
             "data": "synthetic", "config": workload_config(args, spec, world),
             "roofline": roofline,
-            "roofline_stage12": {"bound": "hbm", "kernel": "k_friedmann_residuals (stage 1+2)", "achieved": s12_bytes / (s12_ms * 1e-3) / 1e9,
-                                 "peak": hbm_peak, "unit": "GB/s", "frac": s12_bytes / (s12_ms * 1e-3) / 1e9 / hbm_peak,
-                                 "avg_kernel_ms": s12_ms, "note": "FP64-ALU bound, not HBM bound (SURVEY.md T5)"},
+            "roofline_stage12": {"bound": "fp64", "kernel": "k_friedmann_residuals (stage 1+2: Friedmann grid, SN residuals, digit planes)",
+                                 "achieved": B * S12_FLOPS_PER_EVAL(N, int(spec.z_grid.size)) / (s12_ms * 1e-3) / 1e12, "peak": FP64_PIPE_TFLOPS, "unit": "TFLOP/s",
+                                 "frac": B * S12_FLOPS_PER_EVAL(N, int(spec.z_grid.size)) / (s12_ms * 1e-3) / 1e12 / FP64_PIPE_TFLOPS,
+                                 "avg_kernel_ms": s12_ms, "algorithmic_flops_per_eval": S12_FLOPS_PER_EVAL(N, int(spec.z_grid.size)),
+                                 "hbm_gbs": s12_bytes / (s12_ms * 1e-3) / 1e9, "hbm_frac": s12_bytes / (s12_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "note": "FP64-ALU / issue bound, not HBM bound (SURVEY.md T5): algorithmic FP64 flops (9 G + 40 N, SURVEY.md 8(d)) against the "
+                                         "FP64 pipe (64 DFMA/clk/SM = 37.1 TFLOP/s, profiles/r01_ubench_fp64.log); ncu: FP64 pipe 39 % of cycles, "
+                                         "issue slots 58 % (profiles/r03*_ncu_s12_summary.txt); HBM traffic = theta in + 7 digit planes out"},
             "stage_ms": {"stage12": s12_ms, "stage3_planes": planes_ms, "stage3_contraction": gemm_ms, "finalize": float(np.mean(hist[:, 2])),
                          "total": float(np.mean(hist[:, 3]))},
-            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": int(launches), "clocks": clocks, "parity_check": "64 rows vs oracle ok",
             "engine": eng.describe() + f", stage 3: {args.engine}" + (f" {args.slices} planes" if args.engine == "tcgen05" else ""),
         }
+        line.update(e2e_extra)
         if engines:
             line["engines"] = engines
+            d = engines["dmma_fp64"]
+            ach = flops / (d["contraction_ms"] * 1e-3) / 1e12
+            line["roofline_fp64"] = {"bound": "tensor", "kernel": "k_chi2_gemm (stage 3 on the FP64 tensor pipe, chi2_engine = 0)", "achieved": ach,
+                                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "avg_kernel_ms": d["contraction_ms"],
+                                     "evals_per_s": d["evals_per_s"],
+                                     "note": "the north star's FP64 DMMA GEMM, timed in the same run: algorithmic N^2 + 2N flops per eval against cuBLAS DGEMM "
+                                             "8192^3 measured in this run (DMMA issue peak 37.1 TFLOP/s)"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(spec, host_batches[0])
         print(json.dumps(line), flush=True)

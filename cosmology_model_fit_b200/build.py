@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcosmolike_b200.so")
 SOURCES = ["cosmolike.cu"]
-DEPS = ["cosmolike.cu", "friedmann.cuh", "chi2_gemm.cuh", "chi2_ozaki.cuh", "digits.cuh", "devspec.h", os.path.join("..", "..", "include", "cosmolike.h")]
+DEPS = ["cosmolike.cu", "friedmann.cuh", "chi2_gemm.cuh", "chi2_ozaki.cuh", "digits.cuh", "multi.cuh", "devspec.h", os.path.join("..", "..", "include", "cosmolike.h")]
 
 
 def nvcc_path():

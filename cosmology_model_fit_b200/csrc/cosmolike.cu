@@ -21,6 +21,7 @@
 #include "chi2_ozaki.cuh"
 #include "devspec.h"
 #include "friedmann.cuh"
+#include "multi.cuh"
 
 using namespace cosmolike;
 
@@ -71,6 +72,13 @@ struct cl_ctx {
   int* d_guard = nullptr;            // [0] rows flagged since creation, [1] in the current pass, [2 + rb] row-block marks
   unsigned char* d_rowflag = nullptr;
   double *d_part_fb = nullptr, *d_part_u_fb = nullptr;   // [T][cap] partials of the FP64 fallback pass
+  // multi-GPU (multi.cuh): NCCL communicator of this context and the gather / grid buffers
+  NcclComm comm = nullptr;
+  int comm_rank = 0, comm_size = 0;
+  double* d_gather = nullptr;          // [comm_size][gather_cap] gathered results (host-memory variant)
+  int64_t gather_cap = 0;
+  double *d_grid_part = nullptr, *h_grid_part = nullptr;   // per-block partial reductions of a grid chunk
+  int64_t grid_part_cap = 0;
   std::string err, desc;
   std::mutex mu;
 };
@@ -314,6 +322,10 @@ extern "C" int cl_destroy(cl_ctx* c) {
   if (c->d_counter) cudaFree(c->d_counter);
   for (void* p : {(void*)c->d_guard, (void*)c->d_rowflag, (void*)c->d_part_fb, (void*)c->d_part_u_fb}) if (p) cudaFree(p);
   for (void* p : {(void*)c->d_Ws, (void*)c->d_Rs, (void*)c->d_wscale, (void*)c->d_rscale}) if (p) cudaFree(p);
+  if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
+  if (c->d_gather) cudaFree(c->d_gather);
+  if (c->d_grid_part) cudaFree(c->d_grid_part);
+  if (c->h_grid_part) cudaFreeHost(c->h_grid_part);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   for (auto& r : c->evring) for (auto& e : r) if (e) cudaEventDestroy(e);
@@ -1006,6 +1018,255 @@ extern "C" int cl_eval_sn_moments(cl_ctx* c, const double* theta, int64_t B, int
   if (!c) return CL_E_INVALID;
   if (!c->d_W || c->ds.col_offset < 0) return fail(c, CL_E_INVALID, "sn moments need a large SN block with an offset column");
   return eval_host(c, theta, B, ld, CL_OUT_CHI2, out, 3, true);
+}
+
+// ---- multi-GPU: NCCL communicator per context, sharded evaluation with an all-gather of the results ----
+#define NCCL_TRY(ctx, expr)                                                                                              \
+  do {                                                                                                                   \
+    int r_ = (expr);                                                                                                     \
+    if (r_ != 0) return fail(ctx, CL_E_CUDA, "%s failed: %s", #expr, nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "NCCL error"); \
+  } while (0)
+
+extern "C" int cl_comm_unique_id(void* uid) {
+  if (!uid) return fail(nullptr, CL_E_INVALID, "uid is NULL");
+  NcclApi& api = nccl_api();
+  if (!api.handle) return fail(nullptr, CL_E_INVALID, "NCCL unavailable: %s", api.why ? api.why : "?");
+  static_assert(sizeof(NcclUid) == CL_NCCL_UID_BYTES, "ncclUniqueId is 128 bytes");
+  int r = api.GetUniqueId(reinterpret_cast<NcclUid*>(uid));
+  if (r != 0) return fail(nullptr, CL_E_CUDA, "ncclGetUniqueId failed: %s", api.GetErrorString(r));
+  return CL_OK;
+}
+
+extern "C" int cl_comm_init(cl_ctx* c, int rank, int nranks, const void* uid) {
+  if (!c || !uid) return CL_E_INVALID;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, CL_E_INVALID, "bad rank %d of %d", rank, nranks);
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->comm) return fail(c, CL_E_INVALID, "the context already has a communicator");
+  NcclApi& api = nccl_api();
+  if (!api.handle) return fail(c, CL_E_INVALID, "NCCL unavailable: %s", api.why ? api.why : "?");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  NcclUid id;
+  memcpy(&id, uid, sizeof id);
+  NCCL_TRY(c, api.CommInitRank(&c->comm, nranks, id, rank));
+  c->comm_rank = rank; c->comm_size = nranks;
+  return CL_OK;
+}
+
+extern "C" int cl_comm_destroy(cl_ctx* c) {
+  if (!c) return CL_E_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->comm) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    nccl_api().CommDestroy(c->comm);
+    c->comm = nullptr; c->comm_size = 0; c->comm_rank = 0;
+  }
+  return CL_OK;
+}
+
+extern "C" int cl_comm_info(const cl_ctx* c, int* rank, int* nranks) {
+  if (!c) return CL_E_INVALID;
+  if (rank) *rank = c->comm_rank;
+  if (nranks) *nranks = c->comm_size;
+  return CL_OK;
+}
+
+// host -> device copy of rows [r0, r0 + rows) of a caller's theta (page-locked: DMA as it is; pageable: through the staging area)
+static int upload_theta(cl_ctx* c, const double* theta, int64_t r0, int64_t rows, int64_t ld, bool pinned, cudaStream_t st) {
+  const int nd = c->ds.ndim;
+  if (pinned) {
+    CUDA_TRY(c, cudaMemcpy2DAsync(c->d_theta, nd * sizeof(double), theta + r0 * ld, ld * sizeof(double), nd * sizeof(double),
+                                  (size_t)rows, cudaMemcpyHostToDevice, st));
+  } else {
+    if (ld == nd) memcpy(c->h_theta, theta + r0 * ld, (size_t)rows * nd * sizeof(double));
+    else for (int64_t i = 0; i < rows; i++) memcpy(c->h_theta + i * nd, theta + (r0 + i) * ld, nd * sizeof(double));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_theta, c->h_theta, rows * nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  return CL_OK;
+}
+
+extern "C" int cl_eval_allgather_device(cl_ctx* c, const double* d_theta, int64_t B, int64_t ld, int what, double* d_out_all, void* stream) {
+  int rc = check_eval_args(c, d_theta, B, ld, d_out_all);
+  if (rc != CL_OK) return rc;
+  if (what < CL_OUT_CHI2 || what > CL_OUT_LOGPROB) return fail(c, CL_E_INVALID, "bad output selector");
+  if (!c->comm) return fail(c, CL_E_INVALID, "no communicator: call cl_comm_init first");
+  if (B == 0) return CL_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  c->ev = c->evring[c->n_timed % cl_ctx::kRing];
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  double* mine = d_out_all + (int64_t)c->comm_rank * B;
+  for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
+    int64_t rows = std::min(c->max_rows, B - r0);
+    rc = run_pass(c, d_theta + r0 * ld, rows, ld, what, mine + r0, nullptr, false, st, r0 == 0);
+    if (rc != CL_OK) return rc;
+  }
+  NCCL_TRY(c, nccl_api().AllGather(mine, d_out_all, (size_t)B, kNcclFloat64, c->comm, st));   // in place: mine = recv + rank * count
+  CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+  c->n_timed++;
+  return CL_OK;
+}
+
+extern "C" int cl_eval_allgather(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int what, double* out_all, int root) {
+  if (!c) return CL_E_INVALID;
+  if (!c->comm) return fail(c, CL_E_INVALID, "no communicator: call cl_comm_init first");
+  if (what < CL_OUT_CHI2 || what > CL_OUT_LOGPROB) return fail(c, CL_E_INVALID, "bad output selector");
+  if (root >= c->comm_size) return fail(c, CL_E_INVALID, "root %d out of range", root);
+  const bool receive = root < 0 || root == c->comm_rank;
+  if (B < 0 || (B > 0 && (!theta || (receive && !out_all)))) return fail(c, CL_E_INVALID, "NULL buffer");
+  if (ld < c->ds.ndim) return fail(c, CL_E_INVALID, "ld (%lld) < ndim (%d)", (long long)ld, c->ds.ndim);
+  if (B == 0) return CL_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int nd = c->ds.ndim, W = c->comm_size;
+  if (B > c->gather_cap) {
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (c->d_gather) cudaFree(c->d_gather);
+    c->d_gather = nullptr; c->gather_cap = 0;
+    CUDA_TRY(c, cudaMalloc(&c->d_gather, (size_t)W * B * sizeof(double)));
+    c->gather_cap = B;
+  }
+  c->ev = c->evring[c->n_timed % cl_ctx::kRing];
+  const bool theta_pinned = is_page_locked(theta), out_pinned = receive && is_page_locked(out_all);
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  double* mine = c->d_gather + (int64_t)c->comm_rank * B;
+  int rc;
+  for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
+    int64_t rows = std::min(c->max_rows, B - r0);
+    rc = ensure_rows(c, rows);
+    if (rc != CL_OK) return rc;
+    rc = ensure_pinned(c, theta_pinned ? 0 : rows * nd, (receive && !out_pinned) ? (int64_t)W * B : 0);
+    if (rc != CL_OK) return rc;
+    if (r0 > 0 && !theta_pinned) CUDA_TRY(c, cudaStreamSynchronize(st));   // the staging buffer is reused
+    rc = upload_theta(c, theta, r0, rows, ld, theta_pinned, st);
+    if (rc != CL_OK) return rc;
+    rc = run_pass(c, c->d_theta, rows, nd, what, mine + r0, nullptr, false, st, r0 == 0);
+    if (rc != CL_OK) return rc;
+    if (r0 + rows < B) CUDA_TRY(c, cudaStreamSynchronize(st));   // d_theta is reused by the next pass
+  }
+  NCCL_TRY(c, nccl_api().AllGather(mine, c->d_gather, (size_t)B, kNcclFloat64, c->comm, st));
+  if (receive) CUDA_TRY(c, cudaMemcpyAsync(out_pinned ? out_all : c->h_out, c->d_gather, (size_t)W * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (receive && !out_pinned) memcpy(out_all, c->h_out, (size_t)W * B * sizeof(double));
+  c->n_timed++;
+  return CL_OK;
+}
+
+// ---- profile-likelihood grids generated on the device ----
+extern "C" int cl_eval_grid(cl_ctx* c, const cl_grid* grid, int64_t first, int64_t count, int what, double* out, cl_grid_stats* stats) {
+  if (!c || !grid || !stats) return CL_E_INVALID;
+  const bool moments = what == CL_GRID_PROFILE || what == CL_GRID_MARGINAL;
+  if (!moments && (what < CL_OUT_CHI2 || what > CL_OUT_LOGPROB)) return fail(c, CL_E_INVALID, "bad output selector");
+  if (moments && (!c->d_W || c->ds.col_offset < 0)) return fail(c, CL_E_INVALID, "offset profiling needs a large SN block with an offset column");
+  const int nd = c->ds.ndim;
+  if (grid->n_axes < 1 || grid->n_axes > nd) return fail(c, CL_E_INVALID, "n_axes out of range");
+  DevGrid dg{};
+  dg.ndim = nd; dg.n_axes = grid->n_axes;
+  long double total = 1.0L;
+  bool used[CL_MAX_DIM] = {};
+  for (int a = 0; a < grid->n_axes; a++) {
+    const int col = grid->col[a];
+    if (col < 0 || col >= nd || used[col]) return fail(c, CL_E_INVALID, "axis %d: bad or repeated theta column", a);
+    if (grid->n[a] < 1) return fail(c, CL_E_INVALID, "axis %d has no points", a);
+    used[col] = true;
+    dg.col[a] = col; dg.n[a] = grid->n[a]; dg.lo[a] = grid->lo[a]; dg.hi[a] = grid->hi[a];
+    dg.step[a] = grid->n[a] > 1 ? (grid->hi[a] - grid->lo[a]) / (double)(grid->n[a] - 1) : 0.0;   // np.linspace
+    total *= (long double)grid->n[a];
+  }
+  for (int j = 0; j < nd; j++) dg.fixed[j] = grid->fixed[j];
+  if (first < 0 || count < 0 || (long double)first + (long double)count > total) return fail(c, CL_E_INVALID, "slice [%lld, +%lld) outside the grid", (long long)first, (long long)count);
+  const bool as_chi2 = moments || what == CL_OUT_CHI2;
+  stats->best = as_chi2 ? INFINITY : -INFINITY; stats->index = -1; stats->log_sum = -INFINITY; stats->count = count;
+  stats->larger_is_better = as_chi2 ? 0 : 1; stats->reserved = 0;
+  if (count == 0) return CL_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  GridStats gs;
+  const bool out_pinned = out && is_page_locked(out);
+  c->ev = c->evring[c->n_timed % cl_ctx::kRing];
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  for (int64_t r0 = 0; r0 < count; r0 += c->max_rows) {
+    const int64_t rows = std::min(c->max_rows, count - r0);
+    int rc = ensure_rows(c, rows);
+    if (rc != CL_OK) return rc;
+    const int64_t blocks = (rows + 255) / 256;
+    if (blocks > c->grid_part_cap) {
+      CUDA_TRY(c, cudaStreamSynchronize(st));
+      if (c->d_grid_part) cudaFree(c->d_grid_part);
+      if (c->h_grid_part) cudaFreeHost(c->h_grid_part);
+      c->d_grid_part = c->h_grid_part = nullptr; c->grid_part_cap = 0;
+      const int64_t cap = std::max<int64_t>(blocks, (c->max_rows + 255) / 256);
+      CUDA_TRY(c, cudaMalloc(&c->d_grid_part, cap * 4 * sizeof(double)));
+      CUDA_TRY(c, cudaMallocHost(&c->h_grid_part, cap * 4 * sizeof(double)));
+      c->grid_part_cap = cap;
+    }
+    if (out && !out_pinned) { rc = ensure_pinned(c, 0, rows); if (rc != CL_OK) return rc; }
+    k_grid_theta<<<(unsigned)blocks, 256, 0, st>>>(dg, first + r0, rows, c->d_theta);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    // d_out holds 4 doubles per row: the engine's output in [0, 3 rows) and, when the caller wants them, the values behind it
+    rc = run_pass(c, c->d_theta, rows, nd, moments ? CL_OUT_CHI2 : what, c->d_out, nullptr, moments, st, r0 == 0);
+    if (rc != CL_OK) return rc;
+    GridReduceArgs ra{};
+    ra.src = c->d_out; ra.moments = moments ? (what == CL_GRID_MARGINAL ? 2 : 1) : 0; ra.as_chi2 = as_chi2 ? 1 : 0;
+    ra.rows = rows; ra.first = first + r0; ra.vals = out ? c->d_out + 3 * rows : nullptr; ra.part = c->d_grid_part;
+    k_grid_reduce<<<(unsigned)blocks, 256, 0, st>>>(ra);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_grid_part, c->d_grid_part, blocks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out) CUDA_TRY(c, cudaMemcpyAsync(out_pinned ? out + r0 : c->h_out, ra.vals, rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (r0 + rows >= count) CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (out && !out_pinned) memcpy(out + r0, c->h_out, rows * sizeof(double));
+    for (int64_t b = 0; b < blocks; b++) grid_fold(gs, c->h_grid_part[4 * b], c->h_grid_part[4 * b + 1], c->h_grid_part[4 * b + 2], c->h_grid_part[4 * b + 3]);
+  }
+  c->n_timed++;
+  stats->best = as_chi2 ? gs.best : -0.5 * gs.best;
+  stats->index = gs.index >= 0.0 ? (int64_t)gs.index : -1;
+  stats->log_sum = gs.sum > 0.0 ? gs.lmax + log(gs.sum) : -INFINITY;
+  return CL_OK;
+}
+
+extern "C" int cl_grid_allreduce(cl_ctx* c, cl_grid_stats* stats) {
+  if (!c || !stats) return CL_E_INVALID;
+  if (!c->comm) return fail(c, CL_E_INVALID, "no communicator: call cl_comm_init first");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int W = c->comm_size;
+  int rc = ensure_scratch(c, (int64_t)W * 4 * sizeof(double));
+  if (rc != CL_OK) return rc;
+  rc = ensure_pinned(c, 0, (int64_t)W * 4);
+  if (rc != CL_OK) return rc;
+  double mine[4] = {stats->best, (double)stats->index, stats->log_sum, (double)stats->count};
+  double* slot = c->d_scratch + 4 * c->comm_rank;
+  CUDA_TRY(c, cudaMemcpyAsync(slot, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));   // `mine` is a stack buffer
+  NCCL_TRY(c, nccl_api().AllGather(slot, c->d_scratch, 4, kNcclFloat64, c->comm, st));
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_out, c->d_scratch, (size_t)W * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  // fold in rank order: the same bits on every rank
+  const bool larger = stats->larger_is_better != 0;
+  double best = larger ? -INFINITY : INFINITY, index = -1.0, lmax = -INFINITY, sum = 0.0;
+  int64_t count = 0;
+  for (int r = 0; r < W; r++) {
+    const double* p = c->h_out + 4 * r;
+    const bool better = larger ? p[0] > best : p[0] < best;
+    if (p[1] >= 0.0 && (better || (p[0] == best && (index < 0.0 || p[1] < index)))) { best = p[0]; index = p[1]; }
+    if (p[2] > -INFINITY) {
+      if (p[2] > lmax) { sum = sum * exp(lmax - p[2]) + 1.0; lmax = p[2]; }
+      else sum += exp(p[2] - lmax);
+    }
+    count += (int64_t)p[3];
+  }
+  stats->best = best; stats->index = index >= 0.0 ? (int64_t)index : -1;
+  stats->log_sum = sum > 0.0 ? lmax + log(sum) : -INFINITY;
+  stats->count = count;
+  return CL_OK;
 }
 
 // ---- helper exports: one stage-1/2 launch in a non-EVAL mode, results through pinned staging ----

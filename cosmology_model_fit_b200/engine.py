@@ -27,7 +27,25 @@ ABI_SYMBOLS = (
     "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
     "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split", "cl_host_alloc", "cl_host_free",
     "cl_set_option_f64", "cl_guard_info",
+    "cl_comm_unique_id", "cl_comm_init", "cl_comm_destroy", "cl_comm_info", "cl_eval_allgather", "cl_eval_allgather_device",
+    "cl_eval_grid", "cl_grid_allreduce",
 )
+
+#: cl_eval_grid selectors beyond OUT_CHI2 / OUT_LOGLIKE / OUT_LOGPROB (include/cosmolike.h CL_GRID_*)
+GRID_PROFILE, GRID_MARGINAL = 16, 17
+NCCL_UID_BYTES = 128
+
+
+class ClGrid(C.Structure):
+    """ctypes mirror of cl_grid (include/cosmolike.h)."""
+    _fields_ = [("n_axes", C.c_int32), ("col", C.c_int32 * 12), ("n", C.c_int64 * 12), ("lo", C.c_double * 12),
+                ("hi", C.c_double * 12), ("fixed", C.c_double * 12)]
+
+
+class ClGridStats(C.Structure):
+    """ctypes mirror of cl_grid_stats."""
+    _fields_ = [("best", C.c_double), ("index", C.c_int64), ("log_sum", C.c_double), ("count", C.c_int64),
+                ("larger_is_better", C.c_int32), ("reserved", C.c_int32)]
 
 #: chi-squared engines for large SN blocks (include/cosmolike.h CL_CHI2_ENGINE_*)
 CHI2_ENGINE_DMMA, CHI2_ENGINE_TCGEN05 = 0, 1
@@ -79,12 +97,37 @@ def load_library():
     lib.cl_guard_info.argtypes = [ctxp, C.c_double * 4]
     lib.cl_host_alloc.argtypes = [ctxp, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.cl_host_free.argtypes = [ctxp, C.c_void_p]
+    lib.cl_comm_unique_id.argtypes = [C.c_void_p]
+    lib.cl_comm_init.argtypes = [ctxp, C.c_int, C.c_int, C.c_void_p]
+    lib.cl_comm_destroy.argtypes = [ctxp]
+    lib.cl_comm_info.argtypes = [ctxp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cl_eval_allgather.argtypes = [ctxp, _dp, i64, i64, C.c_int, _dp, C.c_int]
+    lib.cl_eval_allgather_device.argtypes = [ctxp, C.c_void_p, i64, i64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cl_eval_grid.argtypes = [ctxp, C.POINTER(ClGrid), i64, i64, C.c_int, _dp, C.POINTER(ClGridStats)]
+    lib.cl_grid_allreduce.argtypes = [ctxp, C.POINTER(ClGridStats)]
     _lib = lib
     return lib
 
 
 def _p(a):
     return a.ctypes.data_as(_dp)
+
+
+def _point_at_bundled_nccl():
+    """The library binds NCCL at run time (dlopen of libnccl.so.2).  In a process that already imported torch the bundled
+    library is loaded and found by its SONAME; otherwise point $COSMOLIKE_NCCL_LIB at the wheel's copy if there is one."""
+    if os.environ.get("COSMOLIKE_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        sp = importlib.util.find_spec("nvidia.nccl")
+        for root in (sp.submodule_search_locations or []) if sp else []:
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["COSMOLIKE_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
 
 
 class Engine:
@@ -211,6 +254,67 @@ class Engine:
     def eval_device(self, d_theta: int, B: int, ld: int, what: int, d_out: int, stream: int = 0):
         """Asynchronous evaluation on raw device pointers (ints), e.g. torch tensors' data_ptr()."""
         self._check(self.lib.cl_eval_device(self._ctx, C.c_void_p(d_theta), B, ld, what, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    # -- multi-GPU (one process per GPU): NCCL communicator inside the library ----------------------------------
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        """The 128-byte NCCL id rank 0 creates and ships to the other ranks (cl_comm_unique_id)."""
+        _point_at_bundled_nccl()
+        lib = load_library()
+        buf = C.create_string_buffer(NCCL_UID_BYTES)
+        rc = lib.cl_comm_unique_id(buf)
+        if rc != 0:
+            msg = lib.cl_last_error(None)
+            raise EngineError(f"cl_comm_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, uid: bytes):
+        """Collective over all ranks: binds an NCCL communicator to this context (cl_comm_init)."""
+        _point_at_bundled_nccl()
+        if len(uid) != NCCL_UID_BYTES:
+            raise ValueError("uid must be the 128 bytes of Engine.nccl_unique_id()")
+        self._check(self.lib.cl_comm_init(self._ctx, int(rank), int(world), C.create_string_buffer(uid, NCCL_UID_BYTES)))
+
+    def comm_info(self):
+        r, w = C.c_int(), C.c_int()
+        self._check(self.lib.cl_comm_info(self._ctx, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def eval_allgather(self, theta_local, what, out_all=None, root=-1):
+        """Collective: this rank's rows -> the results of every rank in rank order (cl_eval_allgather).  root >= 0: only
+        that rank receives (returns None elsewhere)."""
+        t = np.ascontiguousarray(np.atleast_2d(theta_local), dtype=np.float64)
+        rank, world = self.comm_info()
+        receive = root < 0 or root == rank
+        if receive and out_all is None:
+            out_all = np.empty(world * t.shape[0])
+        self._check(self.lib.cl_eval_allgather(self._ctx, _p(t), t.shape[0], t.shape[1], int(what),
+                                               _p(out_all) if receive else None, int(root)))
+        return out_all if receive else None
+
+    def eval_allgather_device(self, d_theta: int, B: int, ld: int, what: int, d_out_all: int, stream: int = 0):
+        self._check(self.lib.cl_eval_allgather_device(self._ctx, C.c_void_p(d_theta), B, ld, what, C.c_void_p(d_out_all), C.c_void_p(stream)))
+
+    # -- profile-likelihood grids generated on the device (BASELINE.json config 4) -------------------------------
+    def make_grid(self, axes, fixed=None):
+        """cl_grid from {theta column: (lo, hi, n)} (insertion order = axis order, last axis fastest) and {column: value}."""
+        g = ClGrid()
+        g.n_axes = len(axes)
+        for a, (col, (lo, hi, n)) in enumerate(axes.items()):
+            g.col[a], g.lo[a], g.hi[a], g.n[a] = int(col), float(lo), float(hi), int(n)
+        for col, v in (fixed or {}).items():
+            g.fixed[int(col)] = float(v)
+        return g
+
+    def eval_grid(self, grid, first, count, what, want_values=False, allreduce=False):
+        """Evaluates the points first .. first + count - 1 of the flattened grid on the device (cl_eval_grid); returns
+        (stats dict, values or None).  allreduce=True combines the stats over the communicator's ranks (cl_grid_allreduce)."""
+        st = ClGridStats()
+        out = np.empty(count) if want_values else None
+        self._check(self.lib.cl_eval_grid(self._ctx, C.byref(grid), int(first), int(count), int(what), _p(out) if want_values else None, C.byref(st)))
+        if allreduce:
+            self._check(self.lib.cl_grid_allreduce(self._ctx, C.byref(st)))
+        return {"best": st.best, "index": st.index, "log_sum": st.log_sum, "count": st.count}, out
 
     # -- helper exports ---------------------------------------------------------------------------------------
     def distances(self, theta, zq):

@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 #define CL_ABI_VERSION 4u
+#define CL_NCCL_UID_BYTES 128 /* sizeof(ncclUniqueId) */
 #define CL_MAX_DIM 12      /* max length of one parameter vector theta */
 #define CL_MAX_VEL 3       /* max peculiar-velocity template amplitudes (step: 1, dipole xyz: 3) */
 #define CL_MAX_GAUSS 4     /* max extra Gaussian terms of each kind */
@@ -293,6 +294,54 @@ int cl_set_option_f64(cl_ctx* ctx, const char* name, double value);
  * out[1] = rows recomputed by the most recent pass, out[2] = Omega and out[3] = the coefficient of the linear term
  * (lambda eps_S Omega_pr or eps_S Omega_wc) for the current mode and plane count.  Synchronises the device. */
 int cl_guard_info(cl_ctx* ctx, double out[4]);
+
+/* ---- multi-GPU: one process per GPU, one context per process, NCCL bound at run time (dlopen of libnccl.so.2, or the path
+ * in $COSMOLIKE_NCCL_LIB) -------------------------------------------------------------------------------------------------
+ * The likelihood of every parameter vector is independent - the reference farms rows out with multiprocessing.Pool /
+ * numba prange (sn/pantheon.py:119-125, bao/desi.py:100-106) - so a batch is row-sharded over the ranks, every rank holds the
+ * static operands, and the only communication is the all-gather of the per-row results over NVLink.
+ * cl_comm_unique_id: rank 0 obtains the 128-byte NCCL id and ships it to the other ranks by any means (MPI, a file, a socket,
+ * torch.distributed); cl_comm_init: collective over all ranks, binds the communicator to the context's device. */
+int cl_comm_unique_id(void* uid /* CL_NCCL_UID_BYTES */);
+int cl_comm_init(cl_ctx* ctx, int rank, int nranks, const void* uid);
+int cl_comm_destroy(cl_ctx* ctx);            /* also done by cl_destroy */
+int cl_comm_info(const cl_ctx* ctx, int* rank, int* nranks);   /* nranks = 0: no communicator */
+
+/* Sharded evaluation (collective): this rank's B_local rows theta_local[B_local][ld] (HOST memory; the same B_local on every
+ * rank - pad the last shard) -> out_all[nranks * B_local] in rank order.  root < 0: every rank receives the gathered vector;
+ * root >= 0: only that rank downloads it (out_all may be NULL elsewhere) - the master/worker shape of the reference's
+ * Pool.map.  Page-locked buffers are moved by DMA directly, as in cl_eval. */
+int cl_eval_allgather(cl_ctx* ctx, const double* theta_local, int64_t B_local, int64_t ld, int what, double* out_all, int root);
+/* Same with DEVICE pointers, asynchronous on `stream`: d_out_all[nranks * B_local]; this rank's results are written in place
+ * at d_out_all + rank * B_local and gathered with one ncclAllGather.  The caller synchronises. */
+int cl_eval_allgather_device(cl_ctx* ctx, const double* d_theta_local, int64_t B_local, int64_t ld, int what, double* d_out_all, void* stream);
+
+/* ---- profile-likelihood grids generated on the device (BASELINE.json config 4; not in the reference) ---------------------
+ * A Cartesian grid over n_axes theta columns, axis a = np.linspace(lo[a], hi[a], n[a]) (LAST axis fastest: the order of
+ * np.meshgrid(..., indexing="ij").ravel()); the other columns are `fixed`.  cl_eval_grid evaluates the points
+ * first .. first + count - 1 of the flattened grid: theta never crosses PCIe, and the values only do when `out` is given. */
+typedef struct cl_grid {
+  int32_t n_axes;
+  int32_t col[CL_MAX_DIM];   /* theta column of axis a */
+  int64_t n[CL_MAX_DIM];     /* points of axis a */
+  double lo[CL_MAX_DIM], hi[CL_MAX_DIM];
+  double fixed[CL_MAX_DIM];  /* value of every theta column that is not an axis (indexed by column) */
+} cl_grid;
+/* what: CL_OUT_CHI2 / CL_OUT_LOGLIKE / CL_OUT_LOGPROB, or for a large Cholesky SN block the chi2 with the magnitude offset
+ * handled in closed form from the two-dot epilogue (cl_eval_sn_moments): */
+enum { CL_GRID_PROFILE = 16 /* min_M chi2 = yy - yu^2/uu */, CL_GRID_MARGINAL = 17 /* -2 ln int dM exp(-chi2/2) */ };
+typedef struct cl_grid_stats {
+  double best;      /* smallest chi2 (largest log L / log P for the CL_OUT_LOG* selectors) over the points evaluated */
+  int64_t index;    /* its flattened grid index (the smallest one among ties), -1 if no finite value */
+  double log_sum;   /* ln sum exp(-chi2/2)  (ln sum exp(log L) for the CL_OUT_LOG* selectors) */
+  int64_t count;    /* points evaluated */
+  int32_t larger_is_better;   /* set by cl_eval_grid: 1 for the CL_OUT_LOG* selectors, 0 for chi2-like values */
+  int32_t reserved;
+} cl_grid_stats;
+int cl_eval_grid(cl_ctx* ctx, const cl_grid* grid, int64_t first, int64_t count, int what, double* out /* nullable [count] */, cl_grid_stats* stats);
+/* Collective: combines the stats of every rank's slice of the grid (one all-gather of 32 bytes per rank, folded in rank
+ * order on every rank: the same bits everywhere). */
+int cl_grid_allreduce(cl_ctx* ctx, cl_grid_stats* stats);
 
 /* Library / device description string, e.g. "cosmolike_b200 abi 3, sm_100a, NVIDIA B200 (148 SMs)". */
 const char* cl_describe(const cl_ctx* ctx);

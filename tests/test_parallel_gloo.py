@@ -44,6 +44,27 @@ WORKER = textwrap.dedent("""
         assert np.max(np.abs(got - g["chi2"][:B])) < 1e-7, (dist.get_rank(), B)
         buf = np.empty(B)
         assert eng.chi_squared(theta, out=buf) is buf and np.array_equal(buf, got)
+        only0 = eng.chi_squared(theta, root=0)          # master / worker shape: only rank 0 receives
+        assert (only0 is None) == (dist.get_rank() != 0)
+        if only0 is not None:
+            assert np.array_equal(only0, got)
+    # a Cartesian grid sharded by contiguous slices of the flattened index, reduced to (best, index, log-sum-exp)
+    from cosmology_model_fit_b200.parallel import grid_points, grid_stats_of
+    axes = {{1: (0.2, 0.4, 7), 0: (-0.2, 0.2, 5)}}       # axis 0 = column 1 (slowest), axis 1 = column 0 (fastest)
+    fixed = {{2: -3.0}}
+    stats, vals, (first, count) = eng.grid(axes, fixed, OUT_CHI2, want_values=True)
+    full = orc._eval(grid_points(axes, fixed, sp.ndim, 0, 35), OUT_CHI2)
+    assert np.array_equal(vals, full[first:first + count])
+    want = grid_stats_of(full, 0)
+    assert stats["index"] == want["index"] == int(np.argmin(full)) and stats["best"] == want["best"] == full.min()
+    assert abs(stats["log_sum"] - want["log_sum"]) < 1e-12 and stats["count"] == 35
+    om, dm = np.meshgrid(np.linspace(0.2, 0.4, 7), np.linspace(-0.2, 0.2, 5), indexing="ij")
+    pts = grid_points(axes, fixed, sp.ndim, 0, 35)
+    assert np.array_equal(pts[:, 1], om.ravel()) and np.array_equal(pts[:, 0], dm.ravel()) and np.all(pts[:, 2] == -3.0)
+    from cosmology_model_fit_b200.spec import OUT_LOGLIKE
+    ll_stats, _, _ = eng.grid(axes, fixed, OUT_LOGLIKE)
+    assert ll_stats["index"] == want["index"] and abs(ll_stats["best"] + 0.5 * want["best"]) < 1e-12
+    assert abs(ll_stats["log_sum"] - want["log_sum"]) < 1e-12
     dist.barrier()
     dist.destroy_process_group()
     print("rank" + os.environ["RANK"] + "ok", flush=True)
