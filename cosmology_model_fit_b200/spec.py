@@ -300,7 +300,9 @@ class LikelihoodSpec:
 
     def c_spec(self) -> ClSpec:
         s = ClSpec()
-        keep = self._keep = []
+        # the arrays the struct points to live as long as the struct itself (every call returns an independent struct: an
+        # Oracle and an Engine built from one LikelihoodSpec must not invalidate each other's pointers)
+        keep = s._keep = []
 
         def arr(a, dtype=np.float64):
             a = np.ascontiguousarray(np.asarray(a, dtype=dtype))

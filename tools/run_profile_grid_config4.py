@@ -44,7 +44,7 @@ if h0_mode == "explicit":
 sh = ShardedEngine(sp, device=local, rank=rank, world=world) if world == 1 else ShardedEngine(sp, device=local)
 eng = sh.engine
 warm = eng.make_grid(axes, fixed)
-eng.eval_grid(warm, 0, 4096, GRID_PROFILE)                                # workspace, digit planes of W
+eng.eval_grid(warm, 0, 65536, GRID_PROFILE)                               # workspace at its full size, digit planes of W
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
