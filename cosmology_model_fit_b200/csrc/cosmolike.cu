@@ -378,19 +378,23 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
     d.grid_uniform = uni ? 1 : 0;
     d.step = step; d.inv_step = 1.0 / step; d.z_last = s.z_grid[s.n_grid - 1];
     if (uni) {
-      std::vector<double> ln1pz(s.n_grid + 17);
-      for (int i = 0; i < s.n_grid + 17; i++) ln1pz[i] = (double)log1pl((long double)i * (long double)step);
-      TRY(upload(c, ln1pz.data(), ln1pz.size(), &d.grid_ln1pz));
+      // theta-independent node tables of the grid pass, transposed: entry [k][t] belongs to node 16 t + k (friedmann.cuh)
+      const int nt = kS12Threads, nk = kPPT + 1;
+      std::vector<double> ln1pz((size_t)nk * nt);
+      for (int t = 0; t < nt; t++)
+        for (int k = 0; k < nk; k++) ln1pz[(size_t)k * nt + t] = (double)log1pl((long double)(kPPT * t + k) * (long double)step);
+      TRY(upload(c, ln1pz.data(), ln1pz.size(), &d.grid_ln1pz_T));
       if (s.family == CL_FAMILY_FULL) {
         // Omnu_z(z_i) with the reference's formula (cmb/data_planck_act_compression.py:53-66); independent of theta
-        std::vector<double> om(s.n_grid + 17);
+        std::vector<double> om((size_t)nk * nt);
         const cl_cmb_consts& k = s.cmbc;
-        for (int i = 0; i < s.n_grid + 17; i++) {
-          double zp1 = 1.0 + (double)i * step, r = k.nu_m0 / zp1, mz = r * r, ws = 0.0;
-          for (int q = 0; q < 5; q++) ws += sqrt(k.nu_q2[q] + mz) * k.nu_w[q];
-          om[i] = zp1 * zp1 * zp1 * zp1 * ws / k.nu_rho0;
-        }
-        TRY(upload(c, om.data(), om.size(), &d.grid_omnu));
+        for (int t = 0; t < nt; t++)
+          for (int kk = 0; kk < nk; kk++) {
+            double zp1 = 1.0 + (double)(kPPT * t + kk) * step, r = k.nu_m0 / zp1, mz = r * r, ws = 0.0;
+            for (int q = 0; q < 5; q++) ws += sqrt(k.nu_q2[q] + mz) * k.nu_w[q];
+            om[(size_t)kk * nt + t] = zp1 * zp1 * zp1 * zp1 * ws / k.nu_rho0;
+          }
+        TRY(upload(c, om.data(), om.size(), &d.grid_omnu_T));
       }
     }
   }

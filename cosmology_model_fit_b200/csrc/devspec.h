@@ -24,8 +24,8 @@ struct DevSpec {
   double nu_inv_rho0;  // 1 / k.nu_rho0
   // z grid
   const double* z_grid;
-  const double* grid_omnu;   // [G + 17] Omnu_z(z) at the same nodes (theta-independent): FULL family grid pass
-  const double* grid_ln1pz;  // [G + 17] ln(1 + z) at the np.linspace nodes (and 17 nodes beyond): wCDM / CPL grid pass
+  const double* grid_omnu_T;   // [17][256] Omnu_z(z) at node 16 t + k (theta-independent), transposed: FULL family grid pass
+  const double* grid_ln1pz_T;  // [17][256] ln(1 + z) at the np.linspace nodes, transposed: wCDM / CPL grid pass
   int G, grid_uniform;
   double step;      // z_grid[i] == i*step bit-for-bit when grid_uniform (np.linspace from 0), except the last node
   double z_last;    // z_grid[G-1] (np.linspace stores `stop` there exactly)

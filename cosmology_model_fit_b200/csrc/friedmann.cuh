@@ -301,22 +301,31 @@ __device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, dou
 // closed-form fits (cmb/data_planck_act_compression.py:86-124).  Every term of the reference is a product of powers of
 // wb and wm, e.g. (wb^b)^p (wm^m)^q = exp(p b ln wb + q m ln wm): two logs and one exp per term instead of the 14 pow()
 // calls of the literal form (agreement ~4e-16 relative, the fits are needed to 1e-9).
-__device__ __noinline__ void cmb_fits(const cl_cmb_consts& k, double wb, double wm, bool want_zstar, bool want_rdrag,
-                                      double* zstar, double* rdrag) {
+// The fits are spread over threads: term k of the seven exponentials is one thread's work (two logs + one exp: the serial
+// form - 2 logs + 7 exps on one thread - kept every other warp of the CTA waiting at the barrier behind the grid pass).
+//   z* = T0 + s1 391.67 T1 + s2 937.42 T2,   r_d = 1 / (a1 T3 + a3 T4 + a6 T5) - a8 T6
+constexpr int kFitTerms = 7;
+__device__ __forceinline__ double cmb_fit_term(const cl_cmb_consts& k, double wb, double wm, int term) {
   const double lb = log(wb), lm = log(wm);
-  if (want_zstar) {
-    const double Lb = k.zstar_b * lb, Lm = k.zstar_m * lm;
-    *zstar = exp(-0.7316314841257655 * Lm) +
-             k.zstar_s1 * 391.6723594873167 * exp(0.9368102670600895 * Lb - 0.35300106475765136 * Lm) +
-             k.zstar_s2 * 937.4224935298015 * exp(0.0192950634264157 * Lm - 0.04285000485853785 * Lb);
+  const double zb = k.zstar_b * lb, zm = k.zstar_m * lm, rb = k.rdrag_b * lb, rm = k.rdrag_m * lm;
+  double arg;
+  switch (term) {
+    case 0: arg = -0.7316314841257655 * zm; break;
+    case 1: arg = 0.9368102670600895 * zb - 0.35300106475765136 * zm; break;
+    case 2: arg = 0.0192950634264157 * zm - 0.04285000485853785 * zb; break;
+    case 3: arg = 0.05032 * rb; break;
+    case 4: arg = 0.7720642 * rb + 0.24346362 * rm; break;
+    case 5: arg = 0.5350899 * rm; break;
+    default: arg = -0.315473 * rm; break;
   }
-  if (want_rdrag) {
-    const double Lb = k.rdrag_b * lb, Lm = k.rdrag_m * lm;
-    const double a1 = 0.00257366, a2 = 0.05032, a3 = 0.013, a4 = 0.7720642, a5 = 0.24346362, a6 = 0.00641072,
-                 a7 = 0.5350899, a8 = 32.7525, a9 = 0.315473;
-    const double den = a1 * exp(a2 * Lb) + a3 * exp(a4 * Lb + a5 * Lm) + a6 * exp(a7 * Lm);
-    *rdrag = 1.0 / den - a8 * exp(-a9 * Lm);
-  }
+  return exp(arg);
+}
+__device__ __forceinline__ double zstar_from_terms(const cl_cmb_consts& k, const double* t) {
+  return t[0] + k.zstar_s1 * 391.6723594873167 * t[1] + k.zstar_s2 * 937.4224935298015 * t[2];
+}
+__device__ __forceinline__ double rdrag_from_terms(const double* t) {
+  const double den = 0.00257366 * t[3] + 0.013 * t[4] + 0.00641072 * t[5];
+  return 1.0 / den - 32.7525 * t[6];
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -325,24 +334,27 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// block-wide sums of NV values (fixed order -> deterministic); result valid in every thread
+// block-wide sums of the values selected by `mask` (fixed order -> deterministic); result valid in every thread.  ONE barrier:
+// the scratch is double-buffered by the caller (`s_red` alternates between rows), so a row's reads cannot meet the next
+// row's writes - a thread reaches those only behind the next row's barriers.
 template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*8] */) {
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*8] */, unsigned mask) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < NV; q++) {
+    if (!((mask >> q) & 1u)) continue;
     double w = warp_sum(v[q]);
     if (lane == 0) s_red[q * 8 + warp] = w;
   }
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < NV; q++) {
+    if (!((mask >> q) & 1u)) continue;
     double a = 0.0;
 #pragma unroll
     for (int w = 0; w < kS12Threads / 32; w++) a += s_red[q * 8 + w];
     v[q] = a;
   }
-  __syncthreads();
 }
 
 struct S12Smem {
@@ -350,9 +362,9 @@ struct S12Smem {
   double off[kS12Threads];  // D_M at the first node of each chunk
   double2 logtab[128];
   double wsum[8];
-  double red[5 * 8];
+  double red[2][5 * 8];   // block-sum scratch, alternating between rows
   double vec[CL_MAX_BAO + CL_MAX_CC + CL_SN_SMALL_MAX];
-  double scal[4];  // z*, r_drag
+  double scal[8];  // the seven exponential terms of the z* / r_drag fits
   double theta[2][CL_MAX_DIM];  // this row's and the next row's parameter vector
 };
 
@@ -439,34 +451,22 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       if (CL_S12_DBG && (a.dbg & 1)) {   // timing experiment (profiling build): no grid pass, results invalid
         run = 1.0;
       } else if (s.grid_uniform) {
-        // Static node tables (ln(1+z_i), Omnu_z(z_i)).  A thread owns 16 CONSECUTIVE nodes, so reading the tables from global
-        // memory directly costs 32 sectors per warp load; instead each warp copies its 512 entries with coalesced loads
-        // into the .x / .y halves of the very grid slots its threads are about to fill (a slot is read one step before
-        // it is overwritten), and only the 17th node of a chunk, which lives in the neighbour's first slot, is read
-        // from global memory.
+        // Static node tables (ln(1+z_i), Omnu_z(z_i)).  A thread owns 16 CONSECUTIVE nodes, so the tables are stored transposed
+        // ([k][thread] = node 16 thread + k, k = 0..16, built by cl_create): every load is coalesced across the warp, nothing is
+        // staged in shared memory, and the loads run a few nodes ahead of their use (the stores to shared memory are
+        // volatile asm statements with a memory clobber, so the compiler keeps this placement).
         constexpr bool kTabLn = DE == CL_DE_WCDM || DE == CL_DE_CPL, kTabOm = FAM == CL_FAMILY_FULL;
-        if (kTabLn || kTabOm) {
-#pragma unroll 4
-          for (int it = 0; it < kPPT; it++) {
-            const int node = warp * (32 * kPPT) + 32 * it + lane;
-            if (node < G + 17) {
-              const uint32_t slot = gd_addr + (uint32_t)pad_idx(node) * 16u;
-              if (kTabLn) asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot), "d"(__ldg(s.grid_ln1pz + node)) : "memory");
-              if (kTabOm) asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot + 8u), "d"(__ldg(s.grid_omnu + node)) : "memory");
-            }
-          }
-          __syncwarp();
-        }
-        auto tab = [&](int k, double& ln, double& om) {   // table entries of node i0 + k, k = 0..16 (compile-time after unrolling)
-          ln = 0.0; om = 0.0;
-          if (k < kPPT) {
-            if (kTabLn) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ln) : "r"(dst + 16u * k) : "memory");
-            if (kTabOm) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(om) : "r"(dst + 16u * k + 8u) : "memory");
-          } else {
-            if (kTabLn) ln = __ldg(s.grid_ln1pz + i0 + k);
-            if (kTabOm) om = __ldg(s.grid_omnu + i0 + k);
-          }
+        constexpr int kAhead = 2;
+        double lnv[kPPT + 1], omv[kPPT + 1];   // indexed by compile-time constants after unrolling: only a window is ever live
+        auto fetch = [&](int k) {
+          lnv[k] = 0.0; omv[k] = 0.0;
+          // (volatile: the compiler would otherwise hoist all 17 loads to the top of the unrolled loop and spill)
+          if (kTabLn) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(lnv[k]) : "l"(s.grid_ln1pz_T + k * kS12Threads + tid));
+          if (kTabOm) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(omv[k]) : "l"(s.grid_omnu_T + k * kS12Threads + tid));
         };
+        auto tab = [&](int k, double& ln, double& om) { ln = lnv[k]; om = omv[k]; if (k + kAhead <= kPPT) fetch(k + kAhead); };
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) fetch(k);
         const double Ks = c.K * s.step, zp1_0 = fma((double)i0, s.step, 1.0);
         double ln_i, om_i;
         tab(0, ln_i, om_i);
@@ -518,14 +518,11 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       if (lane == 31) sm.wsum[warp] = inc;
       run = inc - run;  // exclusive prefix within the warp
     }
-    // scalar work on the last thread while the others finish their grid points
-    if (tid == kS12Threads - 1 && (need_cmb || need_rd)) {
-      double obh2 = c.obh2;
-      double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
-      double zs = 0.0, rd = 0.0;
-      cmb_fits(s.k, obh2, wm, need_cmb, need_rd, &zs, &rd);
-      sm.scal[0] = zs;
-      sm.scal[1] = rd;
+    // the closed-form fits: one exponential term per thread on the CTA's last threads (they own no grid nodes: 16 * 249 < G)
+    if (tid >= kS12Threads - kFitTerms && (need_cmb || need_rd)) {
+      const double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
+      const int term = tid - (kS12Threads - kFitTerms);
+      if (term >= 3 ? need_rd : need_cmb) sm.scal[term] = cmb_fit_term(s.k, c.obh2, wm, term);
     }
     __syncthreads();
 
@@ -670,7 +667,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 8; k++) mh = max(mh, (uint32_t)__double2hiint(dv[k]) & 0x7fffffffu);
           mh = __reduce_max_sync(0xffffffffu, mh);
-          uint32_t* s_mh = reinterpret_cast<uint32_t*>(sm.red);   // its own slot (the lean kernel has no block sums)
+          uint32_t* s_mh = reinterpret_cast<uint32_t*>(sm.red[0]);   // its own slot (the lean kernel has no block sums)
           if (lane == 0) s_mh[warp] = mh;
           // This barrier is also the row's LAST one: every thread has finished reading the grid nodes, so the next row may
           // overwrite them, and the next row's parameter vector (parked here, before the barrier) is visible behind it.
@@ -789,7 +786,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     // BAO theory (bao_theory, bao/desi_cmb_union3.py:76-94 / bao/desi_cmb_pantheon.py:85-99)
     const bool do_bao = (mode == MODE_EVAL || mode == MODE_BAO) && n_bao > 0;
     if (do_bao && tid < n_bao) {
-      double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : sm.scal[1]);
+      double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : rdrag_from_terms(sm.scal));
       double z = __ldg(s.bao_z + tid);
       double DM = hermite_dm(s, sm.gd, sm.off, z);
       double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.gd, z) : DH_of_z<FAM, DE>(s, c, z);
@@ -817,7 +814,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     double zstar = 0.0;
     if (need_cmb) {
-      zstar = sm.scal[0];
+      zstar = zstar_from_terms(s.k, sm.scal);
       if (tid < s.n_gl) {
         double hw = zstar / 2.0;
         double z = hw * __ldg(s.gl_x + tid) + hw;
@@ -859,13 +856,15 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         }
       }
     }
-    const double rd_out = (need_rd && tid == 0) ? sm.scal[1] : 0.0;
+    const double rd_out = (need_rd && tid == 0) ? rdrag_from_terms(sm.scal) : 0.0;
     // The theta row of the next iteration (loaded into a register at the top) is parked in the other buffer; no thread
     // reads that buffer in this iteration (the previous row's readers all passed this iteration's first barrier).
     if (stage_next && !row_synced) sm.theta[tb ^ 1][tid] = th_next;
     // The next iteration stores its grid nodes before its first barrier, so every thread must be done reading gd.
-    if (need_red) block_sum<5>(v, sm.red);
-    else if (!row_synced) __syncthreads();
+    if (need_red) {
+      const unsigned mask = (need_cmb ? 3u : 0u) | (n_bao > 0 ? 4u : 0u) | (n_cc > 0 ? 8u : 0u) | (sn_small ? 16u : 0u);
+      block_sum<5>(v, sm.red[tb], mask);
+    } else if (!row_synced) __syncthreads();
 
     if (tid == 0) {
       double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
@@ -909,7 +908,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         a.aux[AUX_SN_SMALL * a.B + b] = v[4];
       }
     }
-    // (the two barriers inside block_sum order this iteration's shared-memory reads before the next writes)
+    // (the barrier inside block_sum orders this iteration's shared-memory reads before the next row's writes)
   }
 }
 #undef mode
