@@ -79,6 +79,11 @@ struct cl_ctx {
   int64_t gather_cap = 0;
   double *d_grid_part = nullptr, *h_grid_part = nullptr;   // per-block partial reductions of a grid chunk
   int64_t grid_part_cap = 0;
+  // device-side proposals (cl_propose_eval)
+  double *d_prop_u = nullptr, *d_prop_val = nullptr, *d_prop_keep = nullptr;   // [cap][ndim], [cap], kept rows (u | theta | value)
+  unsigned char* d_prop_inside = nullptr;
+  int* d_prop_cnt = nullptr;             // [0] accepted total, [1] inside total, [2 ..] per-block counts / first slots
+  int64_t prop_cap = 0, prop_keep_cap = 0;
   std::string err, desc;
   std::mutex mu;
 };
@@ -324,6 +329,7 @@ extern "C" int cl_destroy(cl_ctx* c) {
   for (void* p : {(void*)c->d_Ws, (void*)c->d_Rs, (void*)c->d_wscale, (void*)c->d_rscale}) if (p) cudaFree(p);
   if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
   if (c->d_gather) cudaFree(c->d_gather);
+  for (void* p : {(void*)c->d_prop_u, (void*)c->d_prop_val, (void*)c->d_prop_keep, (void*)c->d_prop_inside, (void*)c->d_prop_cnt}) if (p) cudaFree(p);
   if (c->d_grid_part) cudaFree(c->d_grid_part);
   if (c->h_grid_part) cudaFreeHost(c->h_grid_part);
   if (c->h_theta) cudaFreeHost(c->h_theta);
@@ -1128,6 +1134,7 @@ extern "C" int cl_eval_allgather(cl_ctx* c, const double* theta, int64_t B, int6
   if (B > c->gather_cap) {
     CUDA_TRY(c, cudaStreamSynchronize(st));
     if (c->d_gather) cudaFree(c->d_gather);
+  for (void* p : {(void*)c->d_prop_u, (void*)c->d_prop_val, (void*)c->d_prop_keep, (void*)c->d_prop_inside, (void*)c->d_prop_cnt}) if (p) cudaFree(p);
     c->d_gather = nullptr; c->gather_cap = 0;
     CUDA_TRY(c, cudaMalloc(&c->d_gather, (size_t)W * B * sizeof(double)));
     c->gather_cap = B;
@@ -1270,6 +1277,77 @@ extern "C" int cl_grid_allreduce(cl_ctx* c, cl_grid_stats* stats) {
   stats->best = best; stats->index = index >= 0.0 ? (int64_t)index : -1;
   stats->log_sum = sum > 0.0 ? lmax + log(sum) : -INFINITY;
   stats->count = count;
+  return CL_OK;
+}
+
+// ---- proposals of a nested sampler: generate, evaluate, select on the device ----
+extern "C" int cl_propose_eval(cl_ctx* c, const cl_proposal* prop, int64_t n, uint64_t seed, uint64_t offset, int what, double thresh,
+                               int64_t max_keep, double* u_out, double* theta_out, double* val_out, int64_t counts[3]) {
+  if (!c || !prop || !counts) return CL_E_INVALID;
+  if (what < CL_OUT_CHI2 || what > CL_OUT_LOGPROB) return fail(c, CL_E_INVALID, "bad output selector");
+  const int nd = c->ds.ndim;
+  if (prop->ndim != nd) return fail(c, CL_E_INVALID, "proposal ndim %d != spec ndim %d", prop->ndim, nd);
+  if (n < 1 || max_keep < 1 || !u_out || !theta_out || !val_out) return fail(c, CL_E_INVALID, "bad proposal arguments");
+  if (n > c->max_rows) return fail(c, CL_E_INVALID, "n (%lld) exceeds max_rows_per_pass (%lld)", (long long)n, (long long)c->max_rows);
+  std::lock_guard<std::mutex> lk(c->mu);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  int rc = ensure_rows(c, n);
+  if (rc != CL_OK) return rc;
+  const int64_t blocks = (n + 255) / 256;
+  if (n > c->prop_cap) {
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    for (void** p : {(void**)&c->d_prop_u, (void**)&c->d_prop_val, (void**)&c->d_prop_inside, (void**)&c->d_prop_cnt}) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->prop_cap = 0;
+    const int64_t cap = std::max<int64_t>(n, std::min<int64_t>(c->max_rows, 65536));
+    CUDA_TRY(c, cudaMalloc(&c->d_prop_u, cap * nd * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_prop_val, cap * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&c->d_prop_inside, cap));
+    CUDA_TRY(c, cudaMalloc(&c->d_prop_cnt, (2 + (cap + 255) / 256) * sizeof(int)));
+    c->prop_cap = cap;
+  }
+  if (max_keep > c->prop_keep_cap) {
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (c->d_prop_keep) cudaFree(c->d_prop_keep);
+    c->d_prop_keep = nullptr; c->prop_keep_cap = 0;
+    CUDA_TRY(c, cudaMalloc(&c->d_prop_keep, max_keep * (2 * nd + 1) * sizeof(double)));
+    c->prop_keep_cap = max_keep;
+  }
+  DevProposal dp{};
+  dp.ndim = nd;
+  for (int j = 0; j < nd; j++) {
+    dp.mu[j] = prop->mu[j]; dp.lo[j] = prop->lo[j]; dp.hi[j] = prop->hi[j]; dp.mean[j] = prop->mean[j]; dp.sigma[j] = prop->sigma[j];
+    dp.gauss[j] = prop->gauss[j];
+    for (int k = 0; k < nd; k++) dp.L[j * nd + k] = prop->L[j * nd + k];
+  }
+  c->ev = c->evring[c->n_timed % cl_ctx::kRing];
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+  k_propose<<<(unsigned)blocks, 256, 0, st>>>(dp, n, seed, offset, c->d_prop_u, c->d_theta, c->d_prop_inside);
+  c->launches++;
+  CUDA_TRY(c, cudaGetLastError());
+  rc = run_pass(c, c->d_theta, n, nd, what, c->d_prop_val, nullptr, false, st, true);
+  if (rc != CL_OK) return rc;
+  CUDA_TRY(c, cudaMemsetAsync(c->d_prop_cnt, 0, 2 * sizeof(int), st));
+  k_select_count<<<(unsigned)blocks, 256, 0, st>>>(c->d_prop_val, c->d_prop_inside, thresh, n, c->d_prop_cnt + 2, c->d_prop_cnt + 1);
+  k_select_scan<<<1, 1024, 0, st>>>(c->d_prop_cnt + 2, (int)blocks, c->d_prop_cnt);
+  double* keep_u = c->d_prop_keep; double* keep_t = keep_u + max_keep * nd; double* keep_v = keep_t + max_keep * nd;
+  k_select_scatter<<<(unsigned)blocks, 256, 0, st>>>(c->d_prop_val, c->d_prop_inside, thresh, n, nd, c->d_prop_cnt + 2, c->d_prop_u, c->d_theta,
+                                                     max_keep, keep_u, keep_t, keep_v);
+  c->launches += 3;
+  CUDA_TRY(c, cudaGetLastError());
+  int h_cnt[2] = {0, 0};
+  CUDA_TRY(c, cudaMemcpyAsync(h_cnt, c->d_prop_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  const int64_t kept = std::min<int64_t>(h_cnt[0], max_keep);
+  counts[0] = h_cnt[1]; counts[1] = h_cnt[0]; counts[2] = kept;
+  if (kept > 0) {   // the kept rows are few (the sampler asks for what it still needs): plain copies
+    CUDA_TRY(c, cudaMemcpyAsync(u_out, keep_u, kept * nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(theta_out, keep_t, kept * nd * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(val_out, keep_v, kept * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev[5], st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  c->n_timed++;
   return CL_OK;
 }
 

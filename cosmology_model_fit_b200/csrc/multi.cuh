@@ -145,3 +145,119 @@ inline void grid_fold(GridStats& s, double best, double index, double lmax, doub
 }
 
 }  // namespace cosmolike
+
+// ---- proposals of a nested sampler generated, evaluated and filtered on the device -------------------------------------
+// (the sampler front-end sized for the GPU; the reference drives nautilus, bao/desi_cmb_pantheon.py:153-170)
+namespace cosmolike {
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based, so row i of a batch always sees the same numbers whatever the launch
+// shape; cosmology_model_fit_b200/samplers.py carries the same generator in numpy for the CPU-driven twin of a run.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// two uniforms in (0, 1) from one Philox block: (53-bit integer + 1/2) 2^-53
+__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  return ((double)(((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct DevProposal {
+  int ndim;
+  double mu[CL_MAX_DIM], L[CL_MAX_DIM * CL_MAX_DIM], lo[CL_MAX_DIM], hi[CL_MAX_DIM], mean[CL_MAX_DIM], sigma[CL_MAX_DIM];
+  int gauss[CL_MAX_DIM];
+};
+
+// row i: z ~ uniform in the unit ball (normal direction by Box-Muller, radius U^(1/d)), u = mu + L z, theta = prior transform(u).
+// inside[i] = 1 when u lies in the open unit cube (the prior's support); other rows still get a finite theta (mu) so that the
+// likelihood pass can run over the whole batch without special cases - their values are ignored by the selection.
+__global__ void __launch_bounds__(256) k_propose(const __grid_constant__ DevProposal p, int64_t n, uint64_t seed, uint64_t offset,
+                                                 double* __restrict__ u_out, double* __restrict__ theta, unsigned char* __restrict__ inside) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = p.ndim;
+  const uint64_t row = offset + (uint64_t)i;
+  double z[CL_MAX_DIM];
+  double nrm2 = 0.0, ur = 0.5;
+  const int pairs = (d + 1) / 2;
+  for (int j = 0; j <= pairs; j++) {
+    uint32_t c[4] = {(uint32_t)row, (uint32_t)(row >> 32), (uint32_t)j, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double a = u53(c[0], c[1]), b = u53(c[2], c[3]);
+    if (j == pairs) { ur = a; break; }
+    const double r = sqrt(-2.0 * log(a));
+    double sn, cs;
+    sincospi(2.0 * b, &sn, &cs);
+    z[2 * j] = r * cs; nrm2 += z[2 * j] * z[2 * j];
+    if (2 * j + 1 < d) { z[2 * j + 1] = r * sn; nrm2 += z[2 * j + 1] * z[2 * j + 1]; }
+  }
+  const double scale = pow(ur, 1.0 / (double)d) / sqrt(nrm2);
+  bool in = true;
+  for (int r = 0; r < d; r++) {
+    double u = p.mu[r];
+    for (int k = 0; k <= r; k++) u = fma(p.L[r * d + k], z[k] * scale, u);
+    in = in && u > 0.0 && u < 1.0;
+    u_out[i * d + r] = u;
+  }
+  inside[i] = in ? 1 : 0;
+  for (int r = 0; r < d; r++) {
+    const double u = in ? u_out[i * d + r] : p.mu[r];
+    theta[i * d + r] = p.gauss[r] ? p.mean[r] + p.sigma[r] * normcdfinv(fmin(fmax(u, 1e-300), 1.0 - 1e-16)) : p.lo[r] + u * (p.hi[r] - p.lo[r]);
+  }
+}
+
+// ordered selection of the rows with inside && value > thresh: per-block counts, one-block scan, scatter of the first max_keep
+__global__ void __launch_bounds__(256) k_select_count(const double* __restrict__ val, const unsigned char* __restrict__ inside, double thresh,
+                                                      int64_t n, int* __restrict__ block_count, int* __restrict__ inside_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < n && inside[i];
+  const bool ok = in && val[i] > thresh;
+  const int c = __syncthreads_count(ok), ci = __syncthreads_count(in);
+  if (threadIdx.x == 0) { block_count[blockIdx.x] = c; if (ci) atomicAdd(inside_count, ci); }
+}
+__global__ void __launch_bounds__(1024) k_select_scan(int* __restrict__ block_count, int n_blocks, int* __restrict__ total) {
+  __shared__ int s_carry;
+  __shared__ int s_warp[32];
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blocks ? block_count[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += s_warp[w];
+    const int excl = s_carry + woff + inc - v;
+    if (i < n_blocks) block_count[i] = excl;   // exclusive prefix: first output slot of the block
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void __launch_bounds__(256) k_select_scatter(const double* __restrict__ val, const unsigned char* __restrict__ inside, double thresh, int64_t n, int d,
+                                                        const int* __restrict__ block_first, const double* __restrict__ u, const double* __restrict__ theta,
+                                                        int64_t max_keep, double* __restrict__ u_out, double* __restrict__ theta_out, double* __restrict__ val_out) {
+  __shared__ int s_warp[8];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = i < n && inside[i] && val[i] > thresh;
+  const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(ballot);
+  __syncthreads();
+  int slot = block_first[blockIdx.x] + __popc(ballot & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; w++) slot += s_warp[w];
+  if (ok && slot < max_keep) {
+    for (int r = 0; r < d; r++) { u_out[(int64_t)slot * d + r] = u[i * d + r]; theta_out[(int64_t)slot * d + r] = theta[i * d + r]; }
+    val_out[slot] = val[i];
+  }
+}
+
+}  // namespace cosmolike

@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split", "cl_host_alloc", "cl_host_free",
     "cl_set_option_f64", "cl_guard_info",
     "cl_comm_unique_id", "cl_comm_init", "cl_comm_destroy", "cl_comm_info", "cl_eval_allgather", "cl_eval_allgather_device",
-    "cl_eval_grid", "cl_grid_allreduce",
+    "cl_eval_grid", "cl_grid_allreduce", "cl_propose_eval",
 )
 
 #: cl_eval_grid selectors beyond OUT_CHI2 / OUT_LOGLIKE / OUT_LOGPROB (include/cosmolike.h CL_GRID_*)
@@ -40,6 +40,12 @@ class ClGrid(C.Structure):
     """ctypes mirror of cl_grid (include/cosmolike.h)."""
     _fields_ = [("n_axes", C.c_int32), ("col", C.c_int32 * 12), ("n", C.c_int64 * 12), ("lo", C.c_double * 12),
                 ("hi", C.c_double * 12), ("fixed", C.c_double * 12)]
+
+
+class ClProposal(C.Structure):
+    """ctypes mirror of cl_proposal."""
+    _fields_ = [("ndim", C.c_int32), ("gauss", C.c_int32 * 12), ("mu", C.c_double * 12), ("L", C.c_double * 144),
+                ("lo", C.c_double * 12), ("hi", C.c_double * 12), ("mean", C.c_double * 12), ("sigma", C.c_double * 12)]
 
 
 class ClGridStats(C.Structure):
@@ -105,6 +111,8 @@ def load_library():
     lib.cl_eval_allgather_device.argtypes = [ctxp, C.c_void_p, i64, i64, C.c_int, C.c_void_p, C.c_void_p]
     lib.cl_eval_grid.argtypes = [ctxp, C.POINTER(ClGrid), i64, i64, C.c_int, _dp, C.POINTER(ClGridStats)]
     lib.cl_grid_allreduce.argtypes = [ctxp, C.POINTER(ClGridStats)]
+    lib.cl_propose_eval.argtypes = [ctxp, C.POINTER(ClProposal), i64, C.c_uint64, C.c_uint64, C.c_int, C.c_double, i64, _dp, _dp, _dp,
+                                    C.POINTER(C.c_int64 * 3)]
     _lib = lib
     return lib
 
@@ -315,6 +323,28 @@ class Engine:
         if allreduce:
             self._check(self.lib.cl_grid_allreduce(self._ctx, C.byref(st)))
         return {"best": st.best, "index": st.index, "log_sum": st.log_sum, "count": st.count}, out
+
+    # -- nested-sampling proposals on the device ------------------------------------------------------------------
+    def propose_eval(self, mu, L, bounds, n, seed, offset, what, thresh, max_keep, gauss=None):
+        """n points uniform in the ellipsoid {mu + L z} of the unit cube, prior-transformed, evaluated and filtered on the
+        device (cl_propose_eval).  Returns (u, theta, values) of the accepted rows in draw order (at most max_keep) and the
+        counts (inside the cube, accepted, returned)."""
+        d = self.ndim
+        p = ClProposal()
+        p.ndim = d
+        L = np.asarray(L, dtype=np.float64)
+        for j in range(d):
+            p.mu[j], p.lo[j], p.hi[j] = float(mu[j]), float(bounds[j][0]), float(bounds[j][1])
+            for k in range(d):
+                p.L[j * d + k] = float(L[j, k])
+        for col, (mean, sigma) in (gauss or {}).items():
+            p.gauss[col], p.mean[col], p.sigma[col] = 1, float(mean), float(sigma)
+        u, th, val = np.empty((max_keep, d)), np.empty((max_keep, d)), np.empty(max_keep)
+        cnt = (C.c_int64 * 3)()
+        self._check(self.lib.cl_propose_eval(self._ctx, C.byref(p), int(n), int(seed), int(offset), int(what), float(thresh), int(max_keep),
+                                             _p(u), _p(th), _p(val), C.byref(cnt)))
+        k = cnt[2]
+        return u[:k], th[:k], val[:k], (cnt[0], cnt[1], cnt[2])
 
     # -- helper exports ---------------------------------------------------------------------------------------
     def distances(self, theta, zq):

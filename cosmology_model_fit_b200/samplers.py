@@ -130,6 +130,77 @@ class BoxPrior:
         return theta
 
 
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on numpy uint32 arrays (the generator of csrc/multi.cuh, bit for bit)."""
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & mask, p1 & mask, ((p0 >> np.uint64(32)) ^ c3 ^ k1) & mask, p0 & mask
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c0, c1, c2, c3
+
+
+def _u53(hi, lo):
+    return ((((hi >> np.uint64(5)) << np.uint64(26)) | (lo >> np.uint64(6))).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def ellipsoid_points(mu, L, n, seed, offset):
+    """The points k_propose (csrc/multi.cuh) draws for rows offset .. offset + n - 1: uniform in {mu + L z, |z| < 1}.  Same
+    integers; the floating-point steps (log, sincos, pow) agree with the device to a few ulp."""
+    d = len(mu)
+    row = np.arange(offset, offset + n, dtype=np.uint64)
+    lo32, hi32 = row & np.uint64(0xFFFFFFFF), row >> np.uint64(32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    pairs = (d + 1) // 2
+    z = np.empty((n, 2 * pairs))
+    for j in range(pairs + 1):
+        c = philox4x32_10(lo32, hi32, np.full(n, j, dtype=np.uint64), np.zeros(n, dtype=np.uint64), k0, k1)
+        a, b = _u53(c[0], c[1]), _u53(c[2], c[3])
+        if j == pairs:
+            ur = a
+            break
+        r = np.sqrt(-2.0 * np.log(a))
+        z[:, 2 * j], z[:, 2 * j + 1] = r * np.cos(2.0 * np.pi * b), r * np.sin(2.0 * np.pi * b)
+    z = z[:, :d]
+    z *= (ur ** (1.0 / d) / np.linalg.norm(z, axis=1))[:, None]
+    return np.asarray(mu) + z @ np.tril(np.asarray(L)).T
+
+
+class HostProposer:
+    """Proposals drawn with the counter-based generator on the host and evaluated by any `log_like_fn` (the CPU twin of
+    DeviceProposer: same points, same order)."""
+
+    def __init__(self, prior, log_like_fn, seed=0):
+        self.prior, self.log_like_fn, self.seed, self.offset = prior, log_like_fn, int(seed), 0
+
+    def draw(self, mu, L, n, thresh, need):
+        u = ellipsoid_points(mu, L, n, self.seed, self.offset)
+        self.offset += n
+        inside = np.all((u > 0.0) & (u < 1.0), axis=1)
+        u = u[inside]
+        theta = np.ascontiguousarray(self.prior.transform(u)) if len(u) else np.empty((0, self.prior.ndim))
+        ll = np.asarray(self.log_like_fn(theta), dtype=np.float64) if len(u) else np.empty(0)
+        good = np.flatnonzero(ll > thresh)
+        ok = good[:need]
+        return u[ok], theta[ok], ll[ok], (int(inside.sum()), len(good), len(ok)), n
+
+
+class DeviceProposer:
+    """Proposals generated, prior-transformed, evaluated and filtered on the GPU (cl_propose_eval): per call only the
+    accepted rows the sampler still needs come back over PCIe."""
+
+    def __init__(self, prior, engine, what=1, seed=0):
+        self.prior, self.engine, self.what, self.seed, self.offset = prior, engine, int(what), int(seed), 0
+
+    def draw(self, mu, L, n, thresh, need):
+        u, theta, ll, cnt = self.engine.propose_eval(mu, L, self.prior.bounds, n, self.seed, self.offset, self.what, thresh, need,
+                                                     gauss=self.prior.gauss)
+        self.offset += n
+        return u, theta, ll, cnt, n
+
+
 class NestedSampler:
     """Batched nested sampling sized for the GPU likelihood (the reference drives nautilus,
     `bao/desi_cmb_pantheon.py:154-170`, whose stock batches are ~100 points).
@@ -142,8 +213,9 @@ class NestedSampler:
     The same seed with the CPU oracle or the CUDA engine as `log_like_fn` follows the same path up to accept/reject flips
     at the 1e-9 level."""
 
-    def __init__(self, prior, log_like_fn, n_live=2000, n_replace=None, batch=65536, enlarge=1.3, seed=0, min_batch=1024):
+    def __init__(self, prior, log_like_fn, n_live=2000, n_replace=None, batch=65536, enlarge=1.3, seed=0, min_batch=1024, proposer=None):
         self.prior, self.log_like_fn = prior, log_like_fn
+        self.proposer = proposer   # HostProposer / DeviceProposer: counter-based proposals (the default draws with numpy's generator)
         self.ndim = prior.ndim
         self.n_live = int(n_live)
         self.n_replace = int(n_replace or max(1, n_live // 5))
@@ -191,12 +263,14 @@ class NestedSampler:
         for it in range(max_iter):
             order = np.argsort(ll, kind="stable")
             worst = order[:K]
-            for j, idx in enumerate(worst):
-                m = n - j
-                logw = log_x + np.log1p(-np.exp(-1.0 / m)) + ll[idx]
-                dead_theta.append(theta[idx]); dead_logw.append(logw); dead_ll.append(ll[idx])
-                logz = np.logaddexp(logz, logw)
-                log_x -= 1.0 / m
+            # the K deletions at live counts n, n - 1, ..., n - K + 1, vectorised (a Python loop over 8192 deletions per
+            # iteration cost more than the likelihood batch)
+            m = n - np.arange(K, dtype=np.float64)
+            shrink = np.concatenate([[0.0], np.cumsum(1.0 / m)])
+            logw = (log_x - shrink[:-1]) + np.log1p(-np.exp(-1.0 / m)) + ll[worst]
+            dead_theta.append(theta[worst]); dead_logw.append(logw); dead_ll.append(ll[worst])
+            logz = np.logaddexp(logz, np.logaddexp.reduce(logw))
+            log_x -= shrink[-1]
             thresh = ll[worst[-1]]
             keep = order[K:]
             mu, L = self._ellipsoid(u[keep])
@@ -205,6 +279,16 @@ class NestedSampler:
             while need > 0:
                 # enough proposals for the points still needed at the acceptance seen so far, never more than `batch`
                 n_prop = int(min(self.batch, max(self.min_batch, 1.2 * need / max(self._acc, 1e-4))))
+                if self.proposer is not None:
+                    u_ok, th_ok, ll_ok, (n_in, n_good, _), n_eval = self.proposer.draw(mu, L, n_prop, thresh, need)
+                    if np.isnan(ll_ok).any():
+                        raise ValueError("log_like_fn returned NaN")
+                    self.n_calls += 1
+                    self.n_evals += n_eval
+                    self._acc = 0.5 * self._acc + 0.5 * max(n_good, 1) / n_prop
+                    new_u.append(u_ok); new_theta.append(th_ok); new_ll.append(ll_ok)
+                    need -= len(ll_ok)
+                    continue
                 cand = self._draw(mu, L, n_prop)
                 if len(cand) == 0:
                     continue
@@ -223,9 +307,9 @@ class NestedSampler:
         # the live points share the remaining volume
         logw_live = log_x - np.log(n) + ll
         logz = np.logaddexp(logz, np.logaddexp.reduce(logw_live))
-        all_theta = np.vstack([np.array(dead_theta), theta])
-        all_logw = np.concatenate([np.array(dead_logw), logw_live])
-        all_ll = np.concatenate([np.array(dead_ll), ll])
+        all_theta = np.vstack(dead_theta + [theta])
+        all_logw = np.concatenate(dead_logw + [logw_live])
+        all_ll = np.concatenate(dead_ll + [ll])
         w = np.exp(all_logw - logz)
         info = float(np.sum(w * all_ll) - logz)            # H = int P ln(L/Z)
         return {"logz": float(logz), "logz_err": float(np.sqrt(max(info, 0.0) / n)), "information": info, "n_iter": it + 1,

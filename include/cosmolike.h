@@ -343,6 +343,24 @@ int cl_eval_grid(cl_ctx* ctx, const cl_grid* grid, int64_t first, int64_t count,
  * order on every rank: the same bits everywhere). */
 int cl_grid_allreduce(cl_ctx* ctx, cl_grid_stats* stats);
 
+/* ---- nested-sampling proposals generated, evaluated and filtered on the device (the reference drives
+ * nautilus with ~100 points per likelihood call: bao/desi_cmb_pantheon.py:153-170) -----------------------------------------
+ * n points uniform in the ellipsoid {mu + L z : |z| < 1} of the unit cube (counter-based Philox4x32-10: row i of the call
+ * sees the numbers of (seed, offset + i) whatever the batch size), mapped through the prior transform (uniform on [lo, hi]
+ * per column, or Gaussian mean + sigma ndtri(u) where gauss[col] != 0), evaluated with selector `what`, and the rows that lie
+ * inside the unit cube with value > thresh are returned IN DRAW ORDER, at most max_keep of them:
+ * u_out[max_keep][ndim], theta_out[max_keep][ndim], val_out[max_keep] (host memory; page-locked buffers move by DMA).
+ * counts[0] = rows inside the unit cube, counts[1] = rows accepted, counts[2] = rows returned = min(counts[1], max_keep). */
+typedef struct cl_proposal {
+  int32_t ndim;                          /* = the spec's ndim */
+  int32_t gauss[CL_MAX_DIM];
+  double mu[CL_MAX_DIM];
+  double L[CL_MAX_DIM * CL_MAX_DIM];     /* row-major [ndim][ndim], lower triangular */
+  double lo[CL_MAX_DIM], hi[CL_MAX_DIM], mean[CL_MAX_DIM], sigma[CL_MAX_DIM];
+} cl_proposal;
+int cl_propose_eval(cl_ctx* ctx, const cl_proposal* prop, int64_t n, uint64_t seed, uint64_t offset, int what, double thresh, int64_t max_keep,
+                    double* u_out, double* theta_out, double* val_out, int64_t counts[3]);
+
 /* Library / device description string, e.g. "cosmolike_b200 abi 3, sm_100a, NVIDIA B200 (148 SMs)". */
 const char* cl_describe(const cl_ctx* ctx);
 

@@ -135,3 +135,68 @@ def test_config3_nested_evidence_gpu_vs_oracle():
     s_cpu = np.sqrt((r_cpu["weights"][:, None] * (r_cpu["samples"] - m_cpu) ** 2).sum(0))
     assert np.all(np.abs(m_gpu - m_cpu) < 0.5 * s_cpu)
     print(f"config 3 ln Z: gpu {r_gpu['logz']:.4f} +- {r_gpu['logz_err']:.3f}, oracle {r_cpu['logz']:.4f}, evals {r_gpu['n_evals']} / {r_cpu['n_evals']}")
+
+
+def test_counter_based_proposals_known_answers_and_evidence():
+    """Philox4x32-10 against the Random123 known-answer vectors; the proposals are uniform in the ellipsoid; a nested run on
+    counter-based proposals (HostProposer) recovers the Gaussian evidence."""
+    from cosmology_model_fit_b200.samplers import HostProposer, ellipsoid_points, philox4x32_10
+    z = np.array([0])
+    assert [int(x[0]) for x in philox4x32_10(z, z, z, z, 0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = np.array([0xffffffff])
+    assert [int(x[0]) for x in philox4x32_10(f, f, f, f, 0xffffffff, 0xffffffff)] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    L = np.array([[0.2, 0.0, 0.0], [0.05, 0.1, 0.0], [-0.02, 0.03, 0.15]])
+    u = ellipsoid_points(np.full(3, 0.5), L, 200000, seed=9, offset=123)
+    zz = np.linalg.solve(L, (u - 0.5).T).T
+    r = np.linalg.norm(zz, axis=1)
+    assert r.max() < 1.0 and abs(np.mean(r < 0.5 ** (1 / 3.0)) - 0.5) < 0.01 and np.all(np.abs(zz.mean(0)) < 0.01)
+    assert np.array_equal(u[1000:1010], ellipsoid_points(np.full(3, 0.5), L, 10, seed=9, offset=1123))   # counter-based: batch shape is irrelevant
+    d = 3
+    C = np.diag([0.01, 0.02, 0.015]); Ci = np.linalg.inv(C); mu = np.array([0.2, -0.1, 0.3])
+    norm = -0.5 * (d * np.log(2 * np.pi) + np.linalg.slogdet(C)[1])
+    ll = lambda t: norm - 0.5 * np.einsum("ij,jk,ik->i", t - mu, Ci, t - mu)
+    bounds = np.array([(-2.0, 2.0)] * d)
+    prior = BoxPrior(bounds)
+    res = NestedSampler(prior, ll, n_live=800, n_replace=200, batch=8192, seed=3, proposer=HostProposer(prior, ll, seed=3)).run(dlogz=0.01)
+    want = -np.sum(np.log(bounds[:, 1] - bounds[:, 0]))
+    assert abs(res["logz"] - want) < 4 * res["logz_err"] + 0.02, (res["logz"], want, res["logz_err"])
+
+
+@pytest.mark.gpu
+def test_device_proposals_match_the_host_twin_and_config3_evidence():
+    """cl_propose_eval: the device draws the host twin's points (same Philox integers; floating-point steps within a few ulp),
+    returns the accepted rows in draw order, and a config-3 nested run driven by DeviceProposer agrees with the same run
+    driven by HostProposer + the CPU oracle."""
+    import oracle.oracle as O
+    from cases import spec
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.samplers import DeviceProposer, HostProposer, ellipsoid_points
+    from cosmology_model_fit_b200.spec import OUT_LOGLIKE
+    sp = spec("bao_desi_cmb_pantheon")
+    bounds = np.array([(-20.0, -19.0), (60.0, 75.0), (0.019, 0.025), (0.09, 0.14), (-3.0, 1.5)])
+    prior = BoxPrior(bounds)
+    orc = O.Oracle(sp)
+    mu = np.array([0.65, 0.5, 0.55, 0.6, 0.8])
+    L = np.linalg.cholesky(np.diag([0.02, 0.03, 0.02, 0.03, 0.4]) ** 2 + 1e-4)
+    with Engine(sp) as eng:
+        n = 5000
+        u_d, th_d, ll_d, cnt = eng.propose_eval(mu, L, bounds, n, 77, 1000, OUT_LOGLIKE, -np.inf, n)
+        u_h = ellipsoid_points(mu, L, n, 77, 1000)
+        inside = np.all((u_h > 0) & (u_h < 1), axis=1)
+        assert cnt[0] == inside.sum() and cnt[1] == cnt[2] == len(ll_d) == inside.sum()
+        assert 0 < inside.sum() < n                      # the test ellipsoid pokes out of the cube
+        assert np.max(np.abs(u_d - u_h[inside])) < 1e-13
+        assert np.max(np.abs(th_d - prior.transform(u_h[inside]))) < 1e-11
+        want = orc.log_likelihood(th_d, nthreads=0)
+        assert np.all(np.abs(2 * ll_d - 2 * want) <= np.maximum(1e-6, 1e-12 * np.abs(2 * want)))
+        thresh = np.median(ll_d)
+        u2, th2, ll2, cnt2 = eng.propose_eval(mu, L, bounds, n, 77, 1000, OUT_LOGLIKE, thresh, 100)
+        sel = np.flatnonzero(ll_d > thresh)
+        assert cnt2[1] == len(sel) and cnt2[2] == 100 and np.array_equal(ll2, ll_d[sel[:100]]) and np.array_equal(u2, u_d[sel[:100]])
+        kw = dict(n_live=300, n_replace=75, batch=4096, min_batch=512, seed=21)
+        r_gpu = NestedSampler(prior, eng.log_likelihood, proposer=DeviceProposer(prior, eng, OUT_LOGLIKE, seed=5), **kw).run(dlogz=0.1)
+    cpu_ll = lambda th: orc.log_likelihood(th, nthreads=0)
+    r_cpu = NestedSampler(prior, cpu_ll, proposer=HostProposer(prior, cpu_ll, seed=5), **kw).run(dlogz=0.1)
+    assert abs(r_gpu["logz"] - r_cpu["logz"]) < max(1e-6, 2 * r_cpu["logz_err"]), (r_gpu["logz"], r_cpu["logz"], r_cpu["logz_err"])
+    print(f"config 3 ln Z on device proposals: gpu {r_gpu['logz']:.4f}, host twin + oracle {r_cpu['logz']:.4f} +- {r_cpu['logz_err']:.3f}, "
+          f"proposals {r_gpu['n_evals']} / {r_cpu['n_evals']}")
