@@ -467,7 +467,7 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
                          bD0 + (uint32_t)((j0 * (NT * kOzKB)) >> 4), umma_idesc_i8(kOzM, cnt * NT), (zero && i == 0) ? 0u : 1u);
             }
             if (zero && i == 0) mbar_arrive(touched);   // the accumulate = 0 MMAs are in the pipe: B may follow
-            if (last_blk) umma_commit(lvl_full(i));     // round i completes level i
+            if (last_blk) umma_commit(lvl_full(i));     // round i completes level i (a commit after the round's FIRST instruction, which already completes it, measured slower)
           }
           umma_commit(emptyA(sa));
           umma_commit(emptyB(sb));
@@ -519,78 +519,75 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       t_pre += oz_clock() - tp0;
-      // h_n = sum_l 2^-8l acc_l[n] in Horner form from the TOP level down (the order in which the level groups complete,
-      // and the order in which the next tile's MMAs need them back); a level's TMEM columns are handed back to the MMA
-      // issuer as soon as this warp has read them.  int32 -> double through the 2^52 + 2^31
-      // bias (one logic op + one DADD; I2F.F64 runs at a fraction of the FP64 rate).
-      // h_n = sum_l 2^-8l acc_l[n].  int32 -> double through the 2^52 + 2^31 bias (one logic op + one DADD; I2F.F64 runs at
-      // a fraction of the FP64 rate).  The loads are software-pipelined at HALF-level granularity: while one half (NQ
-      // columns) is folded on the FP64 pipe, the tcgen05.ld of the next half (and the poll for the next level) are in flight.
-      // The level loop is ROLLED (one trip = one level = two half steps, one per register buffer): seven unrolled copies of the
-      // fold are ~20 KB of code that every warp walks once per tile, and the instruction fetch stalls of that walk were 18 %
-      // of the epilogue's time.
-      constexpr int NQ = NH / 2;
-      static_assert(NH % 2 == 0 && NQ % 4 == 0, "half levels are loaded with x16 / x8 / x4 tcgen05.ld");
+      // h_n = sum_l 2^-8l acc_l[n].  The levels are folded THREE AT A TIME in integer arithmetic: a group value
+      // g = acc_l 2^16 + acc_(l+1) 2^8 + acc_(l+2) (|g| < 2^47 for n_sn <= 16384) is built by two IMAD.WIDE on top of the
+      // 1.5 * 2^52 bias pattern, so one DADD turns it into a double and one DFMA adds it to h: 2 FP64 instructions per
+      // column for three levels instead of 6.  The epilogue's time after the tile's last MMA is what the next tile waits for
+      // (all of TMEM is in use), and it was bound by the FP64 pipe (14 FP64 instructions per column: 1800 cycles per tile)
+      // and by one load-wait-fold round trip per half level; tcgen05.ld itself moves 300 B/clk/SM (tools/ubench_tmem_ld.cu:
+      // 750 cycles for the whole tile).  Loads are software-pipelined in chunks of CH columns (all levels of a group per
+      // chunk); a group is read as soon as its LAST level is complete - the levels of a tile complete in order.
+      constexpr int CH = 8;
+      static_assert(NH % CH == 0, "chunks of eight columns");
+      constexpr int NCH = NH / CH, NG = (S + 2) / 3;
       double h[NH];
-      int32_t va[NQ], vb[NQ];
+      int32_t buf[2][3][CH];
       const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NH);
-      auto level_of = [&](int t) { return t; };   // levels are read in the order in which they complete
-      // Two waits per tile: level 0 (the epilogue starts under the MMAs of the tile's last block) and, before level 1 is
-      // read, the LAST level (levels complete in order, so nothing needs polling afterwards).  __syncwarp and the tcgen05
-      // fence only follow an actual wait.
-      auto poll_level = [&](int t) {
-        if (t > 1) return;
-        long long tw0 = oz_clock();
-        if (lane == 0) { if (t == 0) oz_wait_relaxed(lvl_full(0), pt, OZ_EPI_NS); else oz_spin(lvl_full(S - 1), pt); }   // one lane polls
-        __syncwarp();
-        t_wait += oz_clock() - tw0;
-        if (lane == 0 && t == 0) oz_trace(g, tr_i, 2000 + 100 * (warp - 2));   // first level complete (seen by this warp)
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      };
-      auto start_half = [&](int t, int q, int32_t* dst) {
-        const uint32_t a = trow + (uint32_t)(level_of(t) * NT + q * NQ);
+      auto issue_chunk = [&](int l0, int cnt, int c, int32_t (&dst)[3][CH]) {
         if (g.dbg_skip & 8) return;   // timing experiment: no TMEM loads (results invalid)
-        if (NQ >= 16) tmem_ld16(a, dst);
-        if (NQ % 16 >= 8) tmem_ld8(a + (NQ & ~15), dst + (NQ & ~15));
-        if (NQ % 8 >= 4) tmem_ld4(a + (NQ & ~7), dst + (NQ & ~7));
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (q < cnt) tmem_ld8(trow + (uint32_t)((l0 + q) * NT + c * CH), dst[q]);
       };
-      auto land_half = [&](int32_t* cur) {
+      auto land_chunk = [&](int cnt, int32_t (&cur)[3][CH]) {
         long long tl0 = oz_clock();
         tmem_ld_wait();
         t_ld += oz_clock() - tl0;
-        if (NQ >= 16) tmem_ld_fence(cur);
-        if (NQ % 16 >= 8) tmem_ld_fence8(cur + (NQ & ~15));
-        if (NQ % 8 >= 4) tmem_ld_fence4(cur + (NQ & ~7));
-      };
-      auto fold_half = [&](int t, const int32_t* cur, double* hq) {
-        const double wl = __longlong_as_double((long long)(1023 - 8 * level_of(t)) << 52);   // 2^-8l
-        if ((g.dbg_skip & 4) && t > 0) return;   // timing experiment: no FP64 work for the upper levels (results invalid)
 #pragma unroll
-        for (int n = 0; n < NQ; n++) {
-          const double d = __hiloint2double(0x43300000, cur[n] ^ (int)0x80000000) - 4503601774854144.0;
-          hq[n] = fma(d, wl, hq[n]);   // h += 2^-8l acc_l
-        }
+        for (int q = 0; q < 3; q++)
+          if (q < cnt) tmem_ld_fence8(cur[q]);
       };
 #pragma unroll
       for (int n = 0; n < NH; n++) h[n] = 0.0;
-      poll_level(0);
-      start_half(0, 0, va);
-#pragma unroll 1
-      for (int t = 0; t < S; t++) {
-        const int l = level_of(t);
-        land_half(va);
-        start_half(t, 1, vb);
-        fold_half(t, va, h);
-        land_half(vb);
-        // hand-over: the issuer polls the barrier of the level that is read last; the other levels are implied
-        if (l == S - 1) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      // group boundaries {0,1,2} {3,4,5} {6}: measured against {0,1,2} {3,4} {5,6} (a smaller tail after the tile's last MMA,
+      // but one more FP64 pair per column): 1.744 vs 1.756 ms at S = 7
+      constexpr int kG0[3] = {0, 3, 6};
+#pragma unroll
+      for (int gi = 0; gi < NG; gi++) {
+        const int l0 = kG0[gi], cnt = (gi + 1 < NG ? kG0[gi + 1] : S) - l0;
+        // wait for the group's last level (relaxed poll for the tile's first group, which starts under the MMAs of the last k block)
+        {
+          long long tw0 = oz_clock();
+          if (lane == 0) { if (gi == 0) oz_wait_relaxed(lvl_full(l0 + cnt - 1), pt, OZ_EPI_NS); else oz_spin(lvl_full(l0 + cnt - 1), pt); }
           __syncwarp();
-          if (lane == 0) mbar_arrive(lvl_empty(l));   // the tile is in registers: its TMEM columns may be overwritten
+          t_wait += oz_clock() - tw0;
+          if (lane == 0 && gi == 0) oz_trace(g, tr_i, 2000 + 100 * (warp - 2));   // first group complete (seen by this warp)
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        if (lane == 0 && t == S - 1) oz_trace(g, tr_i, 2010 + l + 100 * (warp - 2));   // last level in registers
-        if (t + 1 < S) { poll_level(t + 1); start_half(t + 1, 0, va); }
-        fold_half(t, vb, h + NQ);
+        const double wg = __longlong_as_double((long long)(1023 - 8 * (l0 + cnt - 1)) << 52);   // weight of the group's lowest level
+        issue_chunk(l0, cnt, 0, buf[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          land_chunk(cnt, buf[c & 1]);
+          if (c + 1 < NCH) issue_chunk(l0, cnt, c + 1, buf[(c + 1) & 1]);
+          if (gi == NG - 1 && c == NCH - 1) {
+            // hand-over: every TMEM read of the tile has landed; the issuer polls this one barrier
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lvl_empty(S - 1));
+            if (lane == 0) oz_trace(g, tr_i, 2010 + (S - 1) + 100 * (warp - 2));   // last level in registers
+          }
+          if ((g.dbg_skip & 4) && gi > 0) continue;   // timing experiment: no folds beyond the first group (results invalid)
+#pragma unroll
+          for (int n = 0; n < CH; n++) {
+            // {low word: lowest level + 2^31, high word: 1.5 * 2^52} + higher levels * 2^8, 2^16
+            long long t = ((long long)0x43380000 << 32) | (unsigned long long)(uint32_t)(buf[c & 1][cnt - 1][n] ^ (int)0x80000000);
+            if (cnt >= 2) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(t) : "r"(buf[c & 1][cnt - 2][n]), "r"(256));
+            if (cnt >= 3) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(t) : "r"(buf[c & 1][cnt - 3][n]), "r"(65536));
+            const double d = __longlong_as_double(t) - 6755401588539392.0;   // 1.5 * 2^52 + 2^31
+            h[c * CH + n] = fma(d, wg, h[c * CH + n]);
+          }
+        }
       }
       if (lane == 0) oz_trace(g, tr_i, 2020 + 100 * (warp - 2));   // all levels recombined
       pt ^= 1u;
