@@ -40,7 +40,7 @@ I8_PEAK_TOPS = 4485.0
 FP64_PIPE_TFLOPS = 37.1
 #: algorithmic FP64 flops of stage 1+2 per evaluation: 9 per grid node + 40 per supernova
 S12_FLOPS_PER_EVAL = lambda n_sn, n_grid: 9.0 * n_grid + 40.0 * n_sn
-OZ_DRAM_BYTES = {(7, 1701, 65536): 0.910e9}   # profiles/r02m_ncu_full_summary.txt: 0.879e9 read + 0.031e9 written
+OZ_DRAM_BYTES = {(7, 1701, 65536): 0.916e9}   # profiles/r03_ncu_full_summary.txt: 0.885e9 read + 0.031e9 written
 
 
 def build_spec(n_sn):

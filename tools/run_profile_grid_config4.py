@@ -44,7 +44,7 @@ if h0_mode == "explicit":
 sh = ShardedEngine(sp, device=local, rank=rank, world=world) if world == 1 else ShardedEngine(sp, device=local)
 eng = sh.engine
 warm = eng.make_grid(axes, fixed)
-eng.eval_grid(warm, 0, 65536, GRID_PROFILE)                               # workspace at its full size, digit planes of W
+eng.eval_grid(warm, 0, 65536, GRID_PROFILE, allreduce=world > 1)          # workspace at its full size, digit planes of W, NCCL connections
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
@@ -63,7 +63,7 @@ res = {"config": "profile grid (w0, wa, Om, H0) x Pantheon+ N=1701, M profiled a
        "grid_points_per_s": points / wall, "chi2_min": stats["best"], "argmin_index": int(stats["index"]),
        "log_sum_exp_minus_half_chi2": log_sum,
        "best": {"H0": best[1], "Om": best[2], "w0": best[3], "wa": best[4]}, "grid_shape": [n, n, n, n_h0],
-       "rows_this_rank": int(count)}
+       "rows_this_rank": int(count), "guard_rows_recomputed_this_rank": eng.guard_info()["rows_total"]}
 if rank == 0:
     # spot check: the profiled chi2 at the best point against direct chi_squared with M = M*(best) (closed form, profile.py)
     mom = eng.sn_moments(best[None, :])
