@@ -9,6 +9,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <set>
+#include <tuple>
 #include <atomic>
 #include <cmath>
 #include <mutex>
@@ -84,9 +87,24 @@ struct cl_ctx {
   unsigned char* d_prop_inside = nullptr;
   int* d_prop_cnt = nullptr;             // [0] accepted total, [1] inside total, [2 ..] per-block counts / first slots
   int64_t prop_cap = 0, prop_keep_cap = 0;
+  // CUDA graphs of small evaluations: one instantiated graph per (entry point, rows, selector, buffers); a call shape is
+  // captured the second time it is seen (the first call settles every allocation), and every change of an option or of a
+  // workspace pointer starts a new epoch, which drops the graphs
+  typedef std::tuple<int, int64_t, int, int, const void*, const void*, const void*, int64_t> GraphKey;
+  struct GraphEntry { cudaGraphExec_t exec; int64_t launches; };
+  std::map<GraphKey, GraphEntry> graphs;
+  std::set<GraphKey> graph_seen;
+  int opt_graph = 1;
+  int64_t graph_max_rows = 4096, graph_replays = 0;
   std::string err, desc;
   std::mutex mu;
 };
+
+static void drop_graphs(cl_ctx* c) {
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
+  c->graphs.clear();
+  c->graph_seen.clear();
+}
 
 static int fail(cl_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -327,6 +345,7 @@ extern "C" int cl_destroy(cl_ctx* c) {
   if (c->d_counter) cudaFree(c->d_counter);
   for (void* p : {(void*)c->d_guard, (void*)c->d_rowflag, (void*)c->d_part_fb, (void*)c->d_part_u_fb}) if (p) cudaFree(p);
   for (void* p : {(void*)c->d_Ws, (void*)c->d_Rs, (void*)c->d_wscale, (void*)c->d_rscale}) if (p) cudaFree(p);
+  drop_graphs(c);
   if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
   if (c->d_gather) cudaFree(c->d_gather);
   for (void* p : {(void*)c->d_prop_u, (void*)c->d_prop_val, (void*)c->d_prop_keep, (void*)c->d_prop_inside, (void*)c->d_prop_cnt}) if (p) cudaFree(p);
@@ -581,6 +600,14 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
 extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
   if (!c || !name) return CL_E_INVALID;
   std::string n(name);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);   // captured launches carry the options they were captured with
+  }
+  if (n == "cuda_graphs") { c->opt_graph = value != 0; return CL_OK; }
+  if (n == "cuda_graph_max_rows") { if (value < 0) return fail(c, CL_E_INVALID, "cuda_graph_max_rows must be >= 0"); c->graph_max_rows = value; return CL_OK; }
   if (n == "max_rows_per_pass") { if (value < 128) return fail(c, CL_E_INVALID, "max_rows_per_pass must be >= 128"); c->max_rows = value; return CL_OK; }
   if (n == "gemm_ctas") { c->opt_gemm_ctas = (int)value; return CL_OK; }
   if (n == "stage12_ctas") { c->opt_s12_ctas = (int)value; return CL_OK; }
@@ -607,6 +634,12 @@ extern "C" int cl_set_option(cl_ctx* c, const char* name, int64_t value) {
 extern "C" int cl_set_option_f64(cl_ctx* c, const char* name, double value) {
   if (!c || !name) return CL_E_INVALID;
   std::string n(name);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
+  }
   if (!(value >= 0.0)) return fail(c, CL_E_INVALID, "%s must be >= 0", name);
   if (n == "chi2_guard_abs") { c->guard_abs = value; return CL_OK; }
   if (n == "chi2_guard_rel") { c->guard_rel = value; return CL_OK; }
@@ -619,6 +652,14 @@ constexpr double kGuardLambda = 8.0;   // the probabilistic bound is exceeded wi
 // coefficient of the linear term of the selected a-priori bound (friedmann.cuh: GuardArgs)
 static double oz_kappa(const cl_ctx* c) {
   return c->opt_guard_mode ? oz_eps(c->opt_slices) * c->oz_omega : kGuardLambda * oz_eps(c->opt_slices) * c->oz_omega_pr;
+}
+
+extern "C" int cl_graph_info(cl_ctx* c, int64_t out[2]) {
+  if (!c || !out) return CL_E_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  out[0] = (int64_t)c->graphs.size();
+  out[1] = c->graph_replays;
+  return CL_OK;
 }
 
 extern "C" int cl_guard_info(cl_ctx* c, double out[4]) {
@@ -640,6 +681,7 @@ static int ensure_rows(cl_ctx* c, int64_t rows) {
   if (rows <= c->cap_rows) return CL_OK;
   int64_t cap = std::max<int64_t>(rows, std::min<int64_t>(c->max_rows, std::max<int64_t>(1024, c->cap_rows * 2)));
   CUDA_TRY(c, cudaDeviceSynchronize());  // the workspace may be in use on a caller-supplied stream
+  drop_graphs(c);
   for (double** p : {&c->d_theta, &c->d_out, &c->d_R, &c->d_aux, &c->d_part, &c->d_part_u, &c->d_part_fb, &c->d_part_u_fb}) { if (*p) cudaFree(*p); *p = nullptr; }
   int guard_total = 0;   // rows flagged since creation survive a regrowth of the workspace
   if (c->d_guard) { cudaMemcpy(&guard_total, c->d_guard, sizeof(int), cudaMemcpyDeviceToHost); cudaFree(c->d_guard); c->d_guard = nullptr; }
@@ -666,6 +708,7 @@ static int ensure_rows(cl_ctx* c, int64_t rows) {
 }
 
 static int ensure_pinned(cl_ctx* c, int64_t theta_elems, int64_t out_elems) {
+  if (theta_elems > c->h_theta_cap || out_elems > c->h_out_cap) { CUDA_TRY(c, cudaDeviceSynchronize()); drop_graphs(c); }
   if (theta_elems > c->h_theta_cap) {
     if (c->h_theta) cudaFreeHost(c->h_theta);
     c->h_theta = nullptr; c->h_theta_cap = 0;
@@ -684,6 +727,7 @@ static int ensure_pinned(cl_ctx* c, int64_t theta_elems, int64_t out_elems) {
 static int ensure_scratch(cl_ctx* c, int64_t bytes) {
   if (bytes <= c->scratch_bytes) return CL_OK;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  drop_graphs(c);
   if (c->d_scratch) cudaFree(c->d_scratch);
   c->d_scratch = nullptr; c->scratch_bytes = 0;
   CUDA_TRY(c, cudaMalloc(&c->d_scratch, bytes));
@@ -734,6 +778,7 @@ static int ensure_planes(cl_ctx* c, int64_t rows, cudaStream_t st) {
   const int S = c->opt_slices, n = c->ds.n_sn;
   if (c->oz_slices_built != S) {
     CUDA_TRY(c, cudaDeviceSynchronize());
+    drop_graphs(c);
     for (void** p : {(void**)&c->d_Ws, (void**)&c->d_Rs, (void**)&c->d_wscale, (void**)&c->d_rscale}) { if (*p) cudaFree(*p); *p = nullptr; }
     c->oz_cap_rows = 0;
     c->oz_ld = ((int64_t)n + 127) & ~127LL;
@@ -748,6 +793,7 @@ static int ensure_planes(cl_ctx* c, int64_t rows, cudaStream_t st) {
   }
   if (rows > c->oz_cap_rows) {
     CUDA_TRY(c, cudaDeviceSynchronize());
+    drop_graphs(c);
     for (void** p : {(void**)&c->d_Rs, (void**)&c->d_rscale}) { if (*p) cudaFree(*p); *p = nullptr; }
     c->oz_cap_rows = 0;
     const int64_t cap = std::max(rows, c->cap_rows);
@@ -926,6 +972,42 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   return CL_OK;
 }
 
+// ---- CUDA graphs of small evaluations ----
+// Returns 1 when the call was served by a graph replay, 0 when the caller must run it the ordinary way, < 0 on error.
+// `body` enqueues the work on `st` (no allocations, no synchronisation: the first call of a shape ran the ordinary way).
+template <typename Body>
+static int graph_run(cl_ctx* c, const cl_ctx::GraphKey& key, cudaStream_t st, Body body) {
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    if (!c->graph_seen.count(key)) { c->graph_seen.insert(key); return 0; }   // first sight: ordinary launches settle the workspace
+    if (c->graphs.size() >= 64) drop_graphs(c);
+    const int64_t l0 = c->launches;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const int64_t n_launch = c->launches - l0;
+    c->launches = l0;
+    if (rc != CL_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != CL_OK ? rc : 0;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { cudaGetLastError(); return 0; }
+    it = c->graphs.emplace(key, cl_ctx::GraphEntry{exec, n_launch}).first;
+  }
+  CUDA_TRY(c, cudaGraphLaunch(it->second.exec, st));
+  c->launches += it->second.launches;
+  c->graph_replays++;
+  return 1;
+}
+static bool graph_ok(const cl_ctx* c, int64_t rows) {
+  return c->opt_graph && c->opt_dbg == 0 && rows <= c->graph_max_rows && rows <= c->max_rows && rows <= c->cap_rows;
+}
+
 static int check_eval_args(cl_ctx* c, const double* theta, int64_t B, int64_t ld, const void* out) {
   if (!c) return CL_E_INVALID;
   if (B < 0 || (B > 0 && (!theta || !out))) return fail(c, CL_E_INVALID, "NULL buffer");
@@ -940,6 +1022,11 @@ extern "C" int cl_eval_device(cl_ctx* c, const double* d_theta, int64_t B, int64
   std::lock_guard<std::mutex> lk(c->mu);
   CUDA_TRY(c, cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  if (graph_ok(c, B) && st != cudaStreamLegacy && st != cudaStreamPerThread) {   // small batch on fixed buffers: one graph launch
+    const cl_ctx::GraphKey key{1, B, what, 1, d_theta, d_out, (const void*)st, ld};
+    rc = graph_run(c, key, st, [&]() { return run_pass(c, d_theta, B, ld, what, d_out, nullptr, false, st, false); });
+    if (rc != 0) return rc < 0 ? rc : CL_OK;
+  }
   c->ev = c->evring[c->n_timed % cl_ctx::kRing];
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
   for (int64_t r0 = 0; r0 < B; r0 += c->max_rows) {
@@ -983,6 +1070,29 @@ static int eval_host(cl_ctx* c, const double* theta, int64_t B, int64_t ld, int 
   CUDA_TRY(c, cudaSetDevice(c->device));
   const int nd = c->ds.ndim;
   cudaStream_t st = c->stream;
+  if (graph_ok(c, B) && c->h_theta_cap >= B * nd && c->h_out_cap >= B * 4) {
+    // small batch: host copy into the staging area, ONE graph launch (H2D, the whole pass, D2H), host copy out
+    const cl_ctx::GraphKey key{0, B, what, width + (moments ? 8 : 0), nullptr, nullptr, nullptr, 0};
+    if (ld == nd) memcpy(c->h_theta, theta, (size_t)B * nd * sizeof(double));
+    else for (int64_t i = 0; i < B; i++) memcpy(c->h_theta + i * nd, theta + i * ld, nd * sizeof(double));
+    rc = graph_run(c, key, st, [&]() {
+      cudaError_t e = cudaMemcpyAsync(c->d_theta, c->h_theta, B * nd * sizeof(double), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return fail(c, CL_E_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+      int r;
+      if (width == 1) r = run_pass(c, c->d_theta, B, nd, what, c->d_out, nullptr, false, st, false);
+      else if (width == 4) r = run_pass(c, c->d_theta, B, nd, CL_OUT_CHI2, nullptr, c->d_out, false, st, false);
+      else r = run_pass(c, c->d_theta, B, nd, CL_OUT_CHI2, c->d_out, nullptr, true, st, false);
+      if (r != CL_OK) return r;
+      e = cudaMemcpyAsync(c->h_out, c->d_out, B * width * sizeof(double), cudaMemcpyDeviceToHost, st);
+      return e == cudaSuccess ? (int)CL_OK : fail(c, CL_E_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    });
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      CUDA_TRY(c, cudaStreamSynchronize(st));
+      memcpy(out, c->h_out, (size_t)B * width * sizeof(double));
+      return CL_OK;
+    }
+  }
   c->ev = c->evring[c->n_timed % cl_ctx::kRing];
   const bool theta_pinned = is_page_locked(theta), out_pinned = is_page_locked(out);
   CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
@@ -1134,7 +1244,6 @@ extern "C" int cl_eval_allgather(cl_ctx* c, const double* theta, int64_t B, int6
   if (B > c->gather_cap) {
     CUDA_TRY(c, cudaStreamSynchronize(st));
     if (c->d_gather) cudaFree(c->d_gather);
-  for (void* p : {(void*)c->d_prop_u, (void*)c->d_prop_val, (void*)c->d_prop_keep, (void*)c->d_prop_inside, (void*)c->d_prop_cnt}) if (p) cudaFree(p);
     c->d_gather = nullptr; c->gather_cap = 0;
     CUDA_TRY(c, cudaMalloc(&c->d_gather, (size_t)W * B * sizeof(double)));
     c->gather_cap = B;

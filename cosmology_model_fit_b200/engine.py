@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "cl_create", "cl_destroy", "cl_last_error", "cl_eval", "cl_eval_device", "cl_eval_components",
     "cl_eval_sn_moments", "cl_distances", "cl_bao_theory", "cl_cmb", "cl_sn_residuals", "cl_last_timing",
     "cl_timing_history", "cl_launch_count", "cl_set_option", "cl_describe", "cl_stage3_split", "cl_host_alloc", "cl_host_free",
-    "cl_set_option_f64", "cl_guard_info",
+    "cl_set_option_f64", "cl_guard_info", "cl_graph_info",
     "cl_comm_unique_id", "cl_comm_init", "cl_comm_destroy", "cl_comm_info", "cl_eval_allgather", "cl_eval_allgather_device",
     "cl_eval_grid", "cl_grid_allreduce", "cl_propose_eval",
 )
@@ -100,6 +100,7 @@ def load_library():
     lib.cl_launch_count.restype = i64
     lib.cl_set_option.argtypes = [ctxp, C.c_char_p, i64]
     lib.cl_set_option_f64.argtypes = [ctxp, C.c_char_p, C.c_double]
+    lib.cl_graph_info.argtypes = [ctxp, C.POINTER(C.c_int64)]
     lib.cl_guard_info.argtypes = [ctxp, C.c_double * 4]
     lib.cl_host_alloc.argtypes = [ctxp, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.cl_host_free.argtypes = [ctxp, C.c_void_p]
@@ -192,6 +193,12 @@ class Engine:
         v = (C.c_double * 4)()
         self._check(self.lib.cl_guard_info(self._ctx, v))
         return {"rows_total": int(v[0]), "rows_last_pass": int(v[1]), "omega": v[2], "kappa": v[3]}
+
+    def graph_info(self):
+        """CUDA graphs of small evaluations (cl_graph_info): graphs held and replays since creation."""
+        v = (C.c_int64 * 2)()
+        self._check(self.lib.cl_graph_info(self._ctx, v))
+        return {"graphs": int(v[0]), "replays": int(v[1])}
 
     # -- evaluation -------------------------------------------------------------------------------------------
     def _theta(self, theta):

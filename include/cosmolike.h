@@ -275,6 +275,17 @@ int64_t cl_launch_count(const cl_ctx* ctx);
  * Returns CL_E_INVALID for unknown names. */
 int cl_set_option(cl_ctx* ctx, const char* name, int64_t value);
 
+/* CUDA graphs of small evaluations.  A call of cl_eval / cl_eval_components / cl_eval_sn_moments (pageable host buffers)
+ * or cl_eval_device (caller's stream) with at most "cuda_graph_max_rows" rows (option, default 4096; "cuda_graphs" = 0
+ * switches the mechanism off) is captured into a CUDA graph the SECOND time its shape is seen - entry point, rows, output
+ * selector and, for cl_eval_device, the two device pointers, ld and the stream - and replayed from then on: one graph
+ * launch (upload, stage 1+2, contraction, finalize, the accuracy-guard fallback, download) instead of ~10 stream operations,
+ * which is what a stock emcee / nautilus call of 75-100 rows costs most (sn/pantheon.py:119-125 hands over one row at a
+ * time).  Same kernels, same arguments, same bits.  Replays record no per-stage events: cl_last_timing / cl_timing_history /
+ * cl_stage3_split keep describing the most recent evaluation that was launched the ordinary way.  Every option change and
+ * every regrowth of a workspace drops the captured graphs.  out[0] = graphs held, out[1] = replays since cl_create. */
+int cl_graph_info(cl_ctx* ctx, int64_t out[2]);
+
 /* Floating-point options: "chi2_guard_abs" (default 5e-7), "chi2_guard_rel" (default 1e-12) - see cl_guard_info. */
 int cl_set_option_f64(cl_ctx* ctx, const char* name, double value);
 

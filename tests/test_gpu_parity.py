@@ -508,3 +508,66 @@ def test_offset_marginal_vs_bruteforce_integral_of_the_oracle(engines):
         integral = np.sum(0.5 * (w[1:] + w[:-1]) * np.diff(M))     # trapezoid: spectrally accurate for a Gaussian on +-12 sigma
         brute = c.min() - 2.0 * np.log(integral)
         assert abs(brute - marg[i]) < 1e-6 * max(1.0, abs(marg[i])), (brute, marg[i])
+
+
+@pytest.mark.parametrize("name", ["sn_pantheon", "bao_desi_cmb_pantheon", "bao_desi_cmb_union3"])
+def test_cuda_graph_replays_give_the_same_bits(name):
+    """Small evaluations are captured into a CUDA graph the second time a call shape is seen and replayed afterwards
+    (cl_graph_info): same kernels, same arguments -> the same bits as the ordinary launches, for every entry point that
+    takes host buffers, for new theta values in the same shape, after an option change (graphs dropped) and with the
+    mechanism switched off."""
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    g = golden(name)
+    th = [uniform_theta(g["bounds"], 75, seed=s) for s in (1, 2, 3)]
+    with Engine(spec(name)) as e:
+        e.set_option("cuda_graphs", 0)
+        want = [(e.chi_squared(t), e.log_probability(t), e.components(t)) for t in th]
+        assert e.graph_info() == {"graphs": 0, "replays": 0}
+        e.set_option("cuda_graphs", 1)
+        for rep in range(2):
+            for t, (w_chi2, w_lp, w_comp) in zip(th, want):
+                assert np.array_equal(e.chi_squared(t), w_chi2, equal_nan=True)
+                assert np.array_equal(e.log_probability(t), w_lp, equal_nan=True)
+                assert np.array_equal(e.components(t), w_comp, equal_nan=True)
+        info = e.graph_info()
+        assert info["graphs"] == 3 and info["replays"] == 3 * 5, info   # per entry point: one ordinary call, then capture + 5 launches
+        l0 = e.launch_count()
+        e.chi_squared(th[0])
+        assert e.launch_count() - l0 >= 2           # a replay counts the kernels it contains
+        e.set_option("chi2_guard", 1)               # any option change drops the graphs
+        assert e.graph_info()["graphs"] == 0
+        assert np.array_equal(e.chi_squared(th[1]), want[1][0], equal_nan=True)
+        # a different row count is a different shape; a batch above the limit is never captured
+        e.set_option("cuda_graph_max_rows", 50)
+        for _ in range(3):
+            assert np.array_equal(e.chi_squared(th[2]), want[2][0], equal_nan=True)
+        assert e.graph_info()["graphs"] == 0
+        for _ in range(3):
+            assert np.array_equal(e.chi_squared(th[2][:50]), want[2][0][:50], equal_nan=True)
+        assert e.graph_info()["graphs"] == 1
+
+
+def test_cuda_graph_device_entry_point():
+    """cl_eval_device on fixed device buffers and a caller's stream: captured on the second call, replayed afterwards; new
+    values written into the same theta buffer are picked up by the replay."""
+    import torch
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.spec import OUT_CHI2
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    g = golden("sn_pantheon")
+    sp = spec("sn_pantheon")
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    with Engine(sp) as e:
+        d_theta = torch.empty((128, sp.ndim), dtype=torch.float64, device=dev)
+        d_out = torch.empty(128, dtype=torch.float64, device=dev)
+        for k in range(4):
+            t = uniform_theta(g["bounds"], 128, seed=10 + k)
+            want = e.chi_squared(t[:, :])                      # host path (its own graph key)
+            d_theta.copy_(torch.from_numpy(t))
+            torch.cuda.synchronize(dev)
+            e.eval_device(d_theta.data_ptr(), 128, sp.ndim, OUT_CHI2, d_out.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            assert np.array_equal(d_out.cpu().numpy(), want, equal_nan=True), k
+        assert e.graph_info()["replays"] >= 2 + 2
