@@ -260,10 +260,16 @@ static bool lower_factor_from_invcov(const double* Cinv, int n, std::vector<doub
 
 // ---- kernel dispatch over the (family, dark-energy) instantiations ----
 typedef void (*S12Kernel)(const DevSpec, const Stage12Args);
-static S12Kernel pick_s12(int fam, int de, bool lean = false) {
+// lean: 0 = the full kernel, 1 = large SN block alone (late-time family), 2 = large SN block on the fast path with fused digit
+// planes + small probes (friedmann.cuh)
+static S12Kernel pick_s12(int fam, int de, int lean = 0) {
 #define CASE(F, D) if (fam == F && de == D) return k_friedmann_residuals<F, D, 0>;
-#define LEAN_CASE(D) if (lean && fam == CL_FAMILY_LATE && de == D) return k_friedmann_residuals<CL_FAMILY_LATE, D, 1>;
+#define LEAN_CASE(D) if (lean == 1 && fam == CL_FAMILY_LATE && de == D) return k_friedmann_residuals<CL_FAMILY_LATE, D, 1>;
+#define MID_CASE(F, D) if (lean == 2 && fam == F && de == D) return k_friedmann_residuals<F, D, 2>;
   LEAN_CASE(CL_DE_LCDM) LEAN_CASE(CL_DE_WCDM) LEAN_CASE(CL_DE_CPL) LEAN_CASE(CL_DE_THAWING)
+  MID_CASE(CL_FAMILY_LATE, CL_DE_LCDM) MID_CASE(CL_FAMILY_LATE, CL_DE_WCDM) MID_CASE(CL_FAMILY_LATE, CL_DE_CPL) MID_CASE(CL_FAMILY_LATE, CL_DE_THAWING)
+  MID_CASE(CL_FAMILY_FULL, CL_DE_LCDM) MID_CASE(CL_FAMILY_FULL, CL_DE_WCDM) MID_CASE(CL_FAMILY_FULL, CL_DE_CPL) MID_CASE(CL_FAMILY_FULL, CL_DE_THAWING)
+#undef MID_CASE
   CASE(CL_FAMILY_LATE, CL_DE_LCDM) CASE(CL_FAMILY_LATE, CL_DE_WCDM) CASE(CL_FAMILY_LATE, CL_DE_CPL) CASE(CL_FAMILY_LATE, CL_DE_THAWING)
   CASE(CL_FAMILY_FULL, CL_DE_LCDM) CASE(CL_FAMILY_FULL, CL_DE_WCDM) CASE(CL_FAMILY_FULL, CL_DE_CPL) CASE(CL_FAMILY_FULL, CL_DE_THAWING)
 #undef CASE
@@ -273,6 +279,12 @@ static S12Kernel pick_s12(int fam, int de, bool lean = false) {
 // the lean instantiation serves plain evaluations of a large SN block alone (see friedmann.cuh)
 static bool s12_lean(const DevSpec& d, int mode) {
   return mode == MODE_EVAL && d.family == CL_FAMILY_LATE && d.n_sn > 0 && !d.sn_small && d.n_bao == 0 && d.n_cc == 0 && d.cmb_mode == CL_CMB_NONE;
+}
+// the fast SN path of stage 2 (four consecutive supernovae per thread from the quad-interleaved static copies) with the digit
+// planes written in the same kernel: a thread must be able to hold its share of the row
+static bool s12_fusable(const DevSpec& d) {
+  return d.n_sn > 0 && !d.sn_small && d.sn_zs4 != nullptr && ((d.n_sn + 127) & ~127) <= 8 * kS12Threads && d.grid_uniform &&
+         (d.n_vel == 0 || d.vel_pm1) && d.sn_mu_fixed == nullptr && d.n_lin == 0;
 }
 
 static int validate(const cl_spec* s) {
@@ -580,7 +592,8 @@ extern "C" int cl_create(const cl_spec* spec, int device, cl_ctx** out) {
   // kernel attributes
   S12Kernel k12 = pick_s12(d.family, d.de_model);
   CTRY(cudaFuncSetAttribute(k12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
-  if (s12_lean(d, MODE_EVAL)) CTRY(cudaFuncSetAttribute(pick_s12(d.family, d.de_model, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
+  if (s12_lean(d, MODE_EVAL)) CTRY(cudaFuncSetAttribute(pick_s12(d.family, d.de_model, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
+  else if (s12_fusable(d)) CTRY(cudaFuncSetAttribute(pick_s12(d.family, d.de_model, 2), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S12Smem)));
   CTRY(cudaFuncSetAttribute(k_chi2_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CTRY(cudaFuncSetAttribute(k_chi2_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CTRY(cudaFuncSetAttribute(k_chi2_ozaki<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<5>::SMEM));
@@ -736,7 +749,9 @@ static int ensure_scratch(cl_ctx* c, int64_t bytes) {
 }
 
 static int launch_s12(cl_ctx* c, const Stage12Args& a, cudaStream_t st) {
-  S12Kernel k = pick_s12(c->ds.family, c->ds.de_model, c->opt_s12_lean && s12_lean(c->ds, a.mode));
+  // with digit planes to write: the SN-only or the small-probe instantiation (run_pass has checked that the spec qualifies)
+  const int lean = !c->opt_s12_lean ? 0 : s12_lean(c->ds, a.mode) ? 1 : (a.planes != nullptr ? 2 : 0);
+  S12Kernel k = pick_s12(c->ds.family, c->ds.de_model, lean);
   // ~64 CTAs per resident slot (three rows per CTA at B = 65536: measured 0.924 -> 0.887 ms against 8 per slot, one row per CTA is
   // slower again), and the same number of rows for every CTA (no ragged tail at small batches)
   int64_t want = c->opt_s12_ctas > 0 ? c->opt_s12_ctas : (int64_t)c->sm_count * 3 * 64;
@@ -913,8 +928,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   const bool planes = large && c->opt_engine == CL_CHI2_ENGINE_TCGEN05 && c->ds.n_sn <= 16384;
   // stage 2 writes the digit planes itself when the lean kernel runs its fast SN path and a thread can hold its share of the row
   const DevSpec& d = c->ds;
-  const bool fused = planes && c->opt_fuse_planes && c->opt_s12_lean && s12_lean(d, MODE_EVAL) && d.sn_zs4 != nullptr && ((d.n_sn + 127) & ~127) <= 8 * kS12Threads &&
-                     d.grid_uniform && (d.n_vel == 0 || d.vel_pm1) && d.sn_mu_fixed == nullptr && d.n_lin == 0 && !(c->opt_dbg & 2);
+  const bool fused = planes && c->opt_fuse_planes && c->opt_s12_lean && s12_fusable(d) && !(c->opt_dbg & 2);
   if (fused) {
     rc = ensure_planes(c, rows, st);
     if (rc != CL_OK) return rc;
@@ -954,7 +968,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
     if (fused) {   // the FP64 residual rows of the flagged blocks were never written: stage 1+2 again for those rows
       Stage12Args a2 = a;
       a2.planes = nullptr; a2.rowscale = nullptr; a2.guard = c->d_guard;
-      S12Kernel k = pick_s12(c->ds.family, c->ds.de_model, true);
+      S12Kernel k = pick_s12(c->ds.family, c->ds.de_model, s12_lean(c->ds, MODE_EVAL) ? 1 : 0);
       k<<<c->sm_count * 3, kS12Threads, sizeof(S12Smem), st>>>(c->ds, a2);
       c->launches++;
       CUDA_TRY(c, cudaGetLastError());

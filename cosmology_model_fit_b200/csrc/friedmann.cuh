@@ -305,8 +305,13 @@ __device__ double pchip_dh(const DevSpec& s, const double2* __restrict__ gd, dou
 // form - 2 logs + 7 exps on one thread - kept every other warp of the CTA waiting at the barrier behind the grid pass).
 //   z* = T0 + s1 391.67 T1 + s2 937.42 T2,   r_d = 1 / (a1 T3 + a3 T4 + a6 T5) - a8 T6
 constexpr int kFitTerms = 7;
-__device__ __forceinline__ double cmb_fit_term(const cl_cmb_consts& k, double wb, double wm, int term) {
-  const double lb = log(wb), lm = log(wm);
+// The two logarithms go through the shared-memory table of the SN pass (fast_5log10: |err| < 4e-16 absolute on 5 log10 x, i.e.
+// ~2e-16 on ln x - a quarter of libm's instruction count on what is a serial chain at the top of every row); arguments that
+// are not normal positive numbers take libm and give the reference's NaN / -inf.
+__device__ __forceinline__ double cmb_fit_term(const cl_cmb_consts& k, double wb, double wm, int term, uint32_t tab) {
+  constexpr double kLn10Over5 = 0.46051701859880917;   // ln x = (5 log10 x) ln(10) / 5
+  const double lb = normal_positive(wb) ? fast_5log10(wb, tab) * kLn10Over5 : log(wb);
+  const double lm = normal_positive(wm) ? fast_5log10(wm, tab) * kLn10Over5 : log(wm);
   const double zb = k.zstar_b * lb, zm = k.zstar_m * lm, rb = k.rdrag_b * lb, rm = k.rdrag_m * lm;
   double arg;
   switch (term) {
@@ -375,14 +380,20 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   // LEAN = 1: the instantiation for plain evaluations of a large SN block alone (no BAO / CMB / CC terms, no helper modes):
   // the probe switches below become compile-time constants and the dead phases drop out of the code (the full kernel is
   // ~140 KB of SASS, and instruction-fetch stalls showed in its profile)
+  // LEAN = 2: plain evaluations of a large SN block on the fast path TOGETHER WITH the small probes (BAO / compressed CMB /
+  // cosmic chronometers, switched at run time): stage 2 writes the digit planes itself here too.  The helper modes, the
+  // general SN path and the FP64 row stores drop out; the BAO / CC residuals are formed BEFORE the supernova pass by the
+  // CTA's LAST threads (which have no second supernova trip), so that the barrier of the row's power-of-two scale is also the
+  // one behind which the small residual vectors are complete, and the Gauss-Legendre nodes follow the plane stores.
   // (macros, not locals: a local copy of a kernel parameter occupies a register in the full kernel, which is at its 80-register cap)
 #define mode (LEAN ? (int)MODE_EVAL : a.mode)
-#define n_bao (LEAN ? 0 : s.n_bao)
-#define n_cc (LEAN ? 0 : s.n_cc)
-#define cmb_mode (LEAN ? (int)CL_CMB_NONE : s.cmb_mode)
+#define n_bao (LEAN == 1 ? 0 : s.n_bao)
+#define n_cc (LEAN == 1 ? 0 : s.n_cc)
+#define cmb_mode (LEAN == 1 ? (int)CL_CMB_NONE : s.cmb_mode)
 #define sn_small (LEAN ? false : (bool)s.sn_small)
   S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pt = LEAN == 2 ? kS12Threads - 1 - tid : tid;   // thread index of the small probes (LEAN = 2: from the top down)
   const int G = s.G;
   if (tid < 128) sm.logtab[tid] = s.logtab[tid];  // visible after the first __syncthreads of the loop body
   const uint32_t gd_addr = s12_smem_u32(sm.gd), tab_addr = s12_smem_u32(sm.logtab);
@@ -393,6 +404,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   int tb = 0;
   for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, tb ^= 1) {
     const double* __restrict__ th = sm.theta[tb];
+    const double* __restrict__ scal = sm.scal;
     // theta of the next row is staged into the other buffer while this row computes (its L2 latency would otherwise
     // stall every warp); the write happens after the first barrier of the iteration, when no thread can still be
     // reading that buffer for the previous row
@@ -428,7 +440,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           a.aux[AUX_FLAGS * a.B + b] = (double)flags;
           a.aux[AUX_LOGPRIOR * a.B + b] = lp;
         }
-        __syncthreads();
+          __syncthreads();
         if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
         __syncthreads();
         continue;
@@ -471,7 +483,11 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         double ln_i, om_i;
         tab(0, ln_i, om_i);
         double prev = Ks * rsqrt_pos(E2_at_node<FAM, DE>(c, zp1_0, ln_i, om_i));
-        if (i0 + kPPT < G) {  // all 17 nodes inside the grid
+        if (i0 < G) {
+          // The chunk that holds the grid's last node runs the same straight-line loop as every other one (a separate
+          // predicated loop made its warp execute both - and the whole CTA wait for it at the barrier behind the grid pass):
+          // the node tables and the shared-memory slots exist for all 16 * 256 positions, what is computed and stored beyond
+          // node G - 1 is never read (the interpolants stop at node G - 1, the chunk offsets behind this chunk are unused).
 #pragma unroll
           for (int k = 0; k < kPPT; k++) {
             const double zp1 = fma((double)(k + 1), s.step, zp1_0);  // 1 + z_grid[i0+k+1] to 1 ulp
@@ -484,16 +500,6 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           // the pad slot behind the chunk gets hd of the NEXT chunk's first node, so that the SN pass finds hd_{j+1} at a
           // fixed 24 bytes behind node j's pair, also across a chunk boundary
           asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + 16u * kPPT + 8u), "d"(prev) : "memory");
-        } else if (i0 < G) {
-#pragma unroll
-          for (int k = 0; k < kPPT; k++) {
-            const double zp1 = fma((double)(k + 1), s.step, zp1_0);
-            tab(k + 1, ln_i, om_i);
-            const double nxt = Ks * rsqrt_pos(E2_at_node<FAM, DE>(c, zp1, ln_i, om_i));
-            if (i0 + k < G) sts_d2(dst + 16u * k, run, prev);
-            if (i0 + k + 1 < G) run = fma(prev + nxt, 0.5, run);
-            prev = nxt;
-          }
         }
       } else if (i0 < G) {
         double prev = DH_of_z<FAM, DE>(s, c, __ldg(s.z_grid + i0));
@@ -522,7 +528,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (tid >= kS12Threads - kFitTerms && (need_cmb || need_rd)) {
       const double wm = (FAM == CL_FAMILY_FULL) ? c.och2 + c.obh2 + s.k.Omnu_h2 : c.Om * c.h * c.h;
       const int term = tid - (kS12Threads - kFitTerms);
-      if (term >= 3 ? need_rd : need_cmb) sm.scal[term] = cmb_fit_term(s.k, c.obh2, wm, term);
+      if (term >= 3 ? need_rd : need_cmb) sm.scal[term] = cmb_fit_term(s.k, c.obh2, wm, term, tab_addr);
     }
     __syncthreads();
 
@@ -545,6 +551,28 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       continue;
     }
 
+    // BAO theory (bao_theory, bao/desi_cmb_union3.py:76-94 / bao/desi_cmb_pantheon.py:85-99) and cosmic chronometers
+    // (ohd/cc.py:22-26): residual vectors into sm.vec
+    auto small_probe_residuals = [&]() {
+      if ((mode == MODE_EVAL || mode == MODE_BAO) && n_bao > 0 && pt < n_bao) {
+        double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : rdrag_from_terms(scal));
+        double z = __ldg(s.bao_z + pt);
+        double DM = hermite_dm(s, sm.gd, sm.off, z);
+        double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.gd, z) : DH_of_z<FAM, DE>(s, c, z);
+        int q = __ldg(s.bao_qty + pt);
+        double v;
+        if (q == CL_BAO_DV_OVER_RS) v = cbrt(z * DH * (DM * DM)) / rd;  // reference: x ** (1/3), equal to ~1e-16
+        else if (q == CL_BAO_DM_OVER_RS) v = DM / rd;
+        else if (q == CL_BAO_DH_OVER_RS) v = DH / rd;
+        else v = DM / DH;
+        if (mode == MODE_BAO) a.out[b * n_bao + pt] = v;
+        else sm.vec[pt] = __ldg(s.bao_val + pt) - v;
+      }
+      if (mode == MODE_EVAL && pt < n_cc)
+        sm.vec[CL_MAX_BAO + pt] = __ldg(s.cc_H + pt) - H_of_z<FAM, DE>(s, c, __ldg(s.cc_z + pt));
+    };
+    if (LEAN == 2) small_probe_residuals();
+
     // ================= stage 2: residuals =================
     const int n_sn = s.n_sn;
     bool row_synced = false;   // the fused digit-plane path ends the row's shared-memory traffic with its own barrier
@@ -553,7 +581,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       const int64_t ld = mode == MODE_RESID ? (int64_t)n_sn : a.ldR;
       double* __restrict__ Rrow = a.R + b * ld;
       const bool to_smem = sn_small && mode == MODE_EVAL;
-      if (s.grid_uniform && (s.n_vel == 0 || s.vel_pm1) && s.sn_mu_fixed == nullptr && s.n_lin == 0) {
+      if (LEAN == 2 || (s.grid_uniform && (s.n_vel == 0 || s.vel_pm1) && s.sn_mu_fixed == nullptr && s.n_lin == 0)) {
         // fast path.  Static per-SN operands: zs = {1 + z_cmb, w} (or {z_cmb, 0} without a velocity template) and
         // obsp = obs - 25 - 5 log10(1 + z_hel), so that delta = obsp - offset - 5 log10 D_M(z_cosmo):
         // mu_theory + mu_corr = 25 + 5 log10((1+z_hel) D_M(z_cosmo)), D_M(z_cmb) cancels.
@@ -638,7 +666,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; q++) { zs[q] = __ldg(s.sn_zs4 + q * q4 + m); ob[q] = __ldg(s.sn_obsp4 + q * q4 + m); }
         };
-        if (LEAN && a.planes != nullptr) {
+        if (LEAN == 2 || (LEAN && a.planes != nullptr)) {
           // Fused digit planes: stage 2 writes the int8 planes of the tcgen05 contraction itself and the FP64 row never goes
           // through HBM.  A thread owns FOUR CONSECUTIVE supernovae per trip (4 m .. 4 m + 3 for m = tid, tid + 256), keeps its
           // <= 8 residuals in registers, the CTA agrees on the row's power-of-two scale with one barrier, and the balanced
@@ -667,12 +695,17 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 8; k++) mh = max(mh, (uint32_t)__double2hiint(dv[k]) & 0x7fffffffu);
           mh = __reduce_max_sync(0xffffffffu, mh);
-          uint32_t* s_mh = reinterpret_cast<uint32_t*>(sm.red[0]);   // its own slot (the lean kernel has no block sums)
+          // its own slot: the SN-only kernel has no block sums; with small probes the grid scan's warp totals are free here
+          // (written before the row's first barrier, read before its second)
+          uint32_t* s_mh = reinterpret_cast<uint32_t*>(LEAN == 2 ? sm.wsum : sm.red[0]);
           if (lane == 0) s_mh[warp] = mh;
-          // This barrier is also the row's LAST one: every thread has finished reading the grid nodes, so the next row may
-          // overwrite them, and the next row's parameter vector (parked here, before the barrier) is visible behind it.
-          if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
-          row_synced = true;
+          // SN-only kernel: this barrier is also the row's LAST one - every thread has finished reading the grid nodes, so the
+          // next row may overwrite them, and the next row's parameter vector (parked here, before the barrier) is visible behind
+          // it.  With small probes it is the barrier behind which sm.vec is complete; the row ends with the block sum's.
+          if (LEAN != 2) {
+            if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
+            row_synced = true;
+          }
           __syncthreads();
           {
             const uint4 m0 = *reinterpret_cast<const uint4*>(s_mh), m1 = *reinterpret_cast<const uint4*>(s_mh + 4);
@@ -783,44 +816,25 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       continue;
     }
 
-    // BAO theory (bao_theory, bao/desi_cmb_union3.py:76-94 / bao/desi_cmb_pantheon.py:85-99)
-    const bool do_bao = (mode == MODE_EVAL || mode == MODE_BAO) && n_bao > 0;
-    if (do_bao && tid < n_bao) {
-      double rd = s.rd_mode == CL_RD_FIXED ? s.rd_fixed : (s.rd_mode == CL_RD_PARAM ? th[s.col_rd] : rdrag_from_terms(sm.scal));
-      double z = __ldg(s.bao_z + tid);
-      double DM = hermite_dm(s, sm.gd, sm.off, z);
-      double DH = s.dh_mode == CL_DH_PCHIP ? pchip_dh(s, sm.gd, z) : DH_of_z<FAM, DE>(s, c, z);
-      int q = __ldg(s.bao_qty + tid);
-      double v;
-      if (q == CL_BAO_DV_OVER_RS) v = cbrt(z * DH * (DM * DM)) / rd;  // reference: x ** (1/3), equal to ~1e-16
-      else if (q == CL_BAO_DM_OVER_RS) v = DM / rd;
-      else if (q == CL_BAO_DH_OVER_RS) v = DH / rd;
-      else v = DM / DH;
-      if (mode == MODE_BAO) a.out[b * n_bao + tid] = v;
-      else sm.vec[tid] = __ldg(s.bao_val + tid) - v;
-    }
+    if (LEAN != 2) small_probe_residuals();
     if (mode == MODE_BAO) {
       if (stage_next) sm.theta[tb ^ 1][tid] = th_next;
       __syncthreads();
       continue;
     }
 
-    // cosmic chronometers (ohd/cc.py:22-26)
-    if (mode == MODE_EVAL && tid < n_cc)
-      sm.vec[CL_MAX_BAO + tid] = __ldg(s.cc_H + tid) - H_of_z<FAM, DE>(s, c, __ldg(s.cc_z + tid));
-
     // Gauss-Legendre integrands (cmb/data_planck_act_compression.py:160-197): thread q < n_gl -> D_M node,
     // n_gl <= q < 2 n_gl -> r_s node (in scale factor)
     double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     double zstar = 0.0;
     if (need_cmb) {
-      zstar = zstar_from_terms(s.k, sm.scal);
-      if (tid < s.n_gl) {
+      zstar = zstar_from_terms(s.k, scal);
+      if (pt < s.n_gl) {
         double hw = zstar / 2.0;
-        double z = hw * __ldg(s.gl_x + tid) + hw;
-        v[0] = __ldg(s.gl_w + tid) * DH_of_z<FAM, DE>(s, c, z);
-      } else if (tid < 2 * s.n_gl) {
-        int q = tid - s.n_gl;
+        double z = hw * __ldg(s.gl_x + pt) + hw;
+        v[0] = __ldg(s.gl_w + pt) * DH_of_z<FAM, DE>(s, c, z);
+      } else if (pt < 2 * s.n_gl) {
+        int q = pt - s.n_gl;
         double a_lim = 1.0 / (1.0 + zstar);
         double hw = a_lim / 2.0;
         double av = hw * __ldg(s.gl_x + q) + hw;
@@ -830,19 +844,19 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       }
     }
     const bool need_red = need_cmb || n_bao > 0 || n_cc > 0 || sn_small;  // uniform
-    if (need_red) __syncthreads();  // sm.vec complete
+    if (need_red && LEAN != 2) __syncthreads();  // sm.vec complete (LEAN = 2: behind the barrier of the row scale)
 
     if (mode == MODE_EVAL) {
-      if (tid < n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
+      if (pt < n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
         double t = 0.0;
-        for (int i = 0; i < n_bao; i++) t += sm.vec[i] * __ldg(s.bao_W + i * n_bao + tid);
-        v[2] = t * sm.vec[tid];
+        for (int i = 0; i < n_bao; i++) t += sm.vec[i] * __ldg(s.bao_W + i * n_bao + pt);
+        v[2] = t * sm.vec[pt];
       }
-      if (tid < n_cc) {
+      if (pt < n_cc) {
         const double* d = sm.vec + CL_MAX_BAO;
         double t = 0.0;
-        for (int i = 0; i < n_cc; i++) t += d[i] * __ldg(s.cc_W + i * n_cc + tid);
-        v[3] = t * d[tid];
+        for (int i = 0; i < n_cc; i++) t += d[i] * __ldg(s.cc_W + i * n_cc + pt);
+        v[3] = t * d[pt];
       }
       if (sn_small && tid < n_sn) {
         const double* d = sm.vec + CL_MAX_BAO + CL_MAX_CC;
@@ -856,7 +870,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         }
       }
     }
-    const double rd_out = (need_rd && tid == 0) ? rdrag_from_terms(sm.scal) : 0.0;
+    const double rd_out = (need_rd && pt == 0) ? rdrag_from_terms(scal) : 0.0;
     // The theta row of the next iteration (loaded into a register at the top) is parked in the other buffer; no thread
     // reads that buffer in this iteration (the previous row's readers all passed this iteration's first barrier).
     if (stage_next && !row_synced) sm.theta[tb ^ 1][tid] = th_next;
@@ -866,7 +880,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       block_sum<5>(v, sm.red[tb], mask);
     } else if (!row_synced) __syncthreads();
 
-    if (tid == 0) {
+    if (pt == 0) {   // (LEAN = 2: the last thread, which owns no grid nodes - the next row's grid pass does not wait for this tail)
       double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
       if (need_cmb) {
         dm = (zstar / 2.0) * v[0];

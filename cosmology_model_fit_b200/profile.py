@@ -10,7 +10,6 @@ GEMM rows at all.  `Engine.sn_moments` returns (y.y, y.u, u.u) per row from the 
 """
 from __future__ import annotations
 
-import itertools
 
 import numpy as np
 
@@ -54,14 +53,16 @@ def sn_profile_grid(engine, axes, mode="profile", chunk=65536, h0_axis=None, h0_
     shape = [len(axes[c]) for c in cols]
     n = int(np.prod(shape))
     mom = np.empty((n, 3))
-    it = itertools.product(*[np.asarray(axes[c], dtype=np.float64) for c in cols])
+    ax = [np.asarray(axes[c], dtype=np.float64) for c in cols]
     done = 0
-    while done < n:
+    while done < n:   # arbitrary (non-linspace) axes: theta rows of a chunk by index arithmetic; np.linspace grids go through cl_eval_grid
         m = min(chunk, n - done)
         theta = np.empty((m, sp.ndim))
         for c, v in fixed.items():
             theta[:, c] = v
-        theta[:, cols] = np.fromiter(itertools.chain.from_iterable(itertools.islice(it, m)), dtype=np.float64, count=m * len(cols)).reshape(m, len(cols))
+        idx = np.unravel_index(np.arange(done, done + m), shape)    # C order: the last axis runs fastest (itertools.product order)
+        for k, c in enumerate(cols):
+            theta[:, c] = ax[k][idx[k]]
         mom[done:done + m] = engine.sn_moments(theta)
         done += m
     mom = mom.reshape(shape + [3])
