@@ -49,7 +49,7 @@ template <int S> struct OzCfg {
   static constexpr int B_BYTES = S * NT * kOzKB;
   static constexpr int A_UNITS = (3 * A_UNIT_BYTES + kOzBStages * B_BYTES <= 224 * 1024) ? 3 : 2;   // 7 planes: 3 x 56 KB + 2 x 28 KB = 224 KB, 231296 B with the rest (limit 232448)
   static constexpr int A_RING = A_UNITS * A_UNIT_BYTES, B_RING = kOzBStages * B_BYTES;
-  static constexpr int SMEM = 1024 + A_RING + B_RING + 2 * NT * 8 + 384;
+  static constexpr int SMEM = 1024 + A_RING + B_RING + 3 * NT * 8 + 384;   // 7 planes: 232320 B (limit 232448)
   static constexpr int FRAC_BITS = 6 + 8 * (S - 1);
   static constexpr int MAX_STACK = 256 / NT;   // digit planes of W one MMA may cover (N <= 256)
 };
@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(kOzThreads, 1)
 k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmW, const OzArgs g) {
   using C = OzCfg<S>;
   constexpr int NT = C::NT;
+  // (1.5 * 2^52 + 2^31) * (sum of the weights of the level groups behind the first): see the epilogue's fold
+  constexpr double kFoldC = 6755401588539392.0 * (S == 7 ? (0x1p-40 + 0x1p-48) : S == 6 ? 0x1p-40 : 0x1p-32);
   extern __shared__ unsigned char osm_raw[];
   const uint32_t base = (smem_u32(osm_raw) + 1023u) & ~1023u;
   unsigned char* base_ptr = osm_raw + (base - smem_u32(osm_raw));
@@ -296,7 +298,8 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   const uint32_t sB = base + C::A_RING;           // [kOzBStages][S planes][NT rows][64 B]
   double* s_cs = reinterpret_cast<double*>(base_ptr + C::A_RING + C::B_RING);  // [NT] column scales of the tile
   double* s_u = s_cs + NT;                                                     // [NT] u of the tile's columns (moments)
-  const uint32_t bars = base + C::A_RING + C::B_RING + 2 * NT * 8;
+  double* s_cc = s_u + NT;                                                     // [NT] -(bias constant) * column scale, see the epilogue
+  const uint32_t bars = base + C::A_RING + C::B_RING + 3 * NT * 8;
   auto fullA = [&](int s) { return bars + 8u * s; };
   auto emptyA = [&](int s) { return bars + 8u * (6 + s); };
   auto fullB = [&](int s) { return bars + 8u * (12 + s); };
@@ -514,7 +517,9 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (etid < NT) {
         const int col = c0 + etid;
-        s_cs[etid] = col >= 0 ? g.colscale[col] : 0.0;
+        const double cs = col >= 0 ? g.colscale[col] : 0.0;
+        s_cs[etid] = cs;
+        s_cc[etid] = -kFoldC * cs;   // exact: the column scale is a power of two
         if (g.part_u) s_u[etid] = col >= 0 ? g.u[col] : 0.0;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -530,6 +535,14 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       constexpr int CH = 8;
       static_assert(NH % CH == 0, "chunks of eight columns");
       constexpr int NCH = NH / CH, NG = (S + 2) / 3;
+      // FP64 work per column: ONE DFMA per group.  A group value arrives as the double t = kBias + g (the bias pattern with g
+      // in the low mantissa bits).  Group 0 removes its bias inside the DFMA, h = fma(t, w0, -kBias w0) = g w0 exactly; the
+      // later groups are added bias and all, h = fma(t, w, h), which carries kBias w along - small constants (1.5 * 2^12 and
+      // 1.5 * 2^4 at S = 7) next to which h keeps every bit it would keep anyway: if |h| is below them the sum's ulp is 2^-40
+      // (only the lowest digits of level 6 round, an absolute 2^-41 on a quantity whose TERMS carry errors of 2^-39 by the
+      // a-priori bound), if |h| is above them the rounding is the usual relative 2^-53.  Their exactly representable sum
+      // kFoldC comes off together with the column scale, y = fma(h, cs, -kFoldC cs), one rounding.  5 FP64 instructions per
+      // column instead of 8 (the epilogue's ~3.6 k cycles per tile are half FP64-pipe time, and what the next tile waits for).
       double h[NH];
       int32_t buf[2][3][CH];
       const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(half * NH);
@@ -552,6 +565,7 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       // group boundaries {0,1,2} {3,4,5} {6}: measured against {0,1,2} {3,4} {5,6} (a smaller tail after the tile's last MMA,
       // but one more FP64 pair per column): 1.744 vs 1.756 ms at S = 7
       constexpr int kG0[3] = {0, 3, 6};
+      constexpr double kBias = 6755401588539392.0;   // 1.5 * 2^52 + 2^31
 #pragma unroll
       for (int gi = 0; gi < NG; gi++) {
         const int l0 = kG0[gi], cnt = (gi + 1 < NG ? kG0[gi + 1] : S) - l0;
@@ -584,8 +598,7 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
             long long t = ((long long)0x43380000 << 32) | (unsigned long long)(uint32_t)(buf[c & 1][cnt - 1][n] ^ (int)0x80000000);
             if (cnt >= 2) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(t) : "r"(buf[c & 1][cnt - 2][n]), "r"(256));
             if (cnt >= 3) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(t) : "r"(buf[c & 1][cnt - 3][n]), "r"(65536));
-            const double d = __longlong_as_double(t) - 6755401588539392.0;   // 1.5 * 2^52 + 2^31
-            h[c * CH + n] = fma(d, wg, h[c * CH + n]);
+            h[c * CH + n] = fma(__longlong_as_double(t), wg, gi == 0 ? -kBias * wg : h[c * CH + n]);
           }
         }
       }
@@ -594,7 +607,7 @@ k_chi2_ozaki(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
       double acc = 0.0;
 #pragma unroll
       for (int n = 0; n < NH; n++) {
-        const double y = h[n] * s_cs[half * NH + n];
+        const double y = fma(h[n], s_cs[half * NH + n], s_cc[half * NH + n]);
         acc = fma(y, y, acc);
         h[n] = y;
       }

@@ -460,6 +460,36 @@ def test_lean_stage12_kernel_gives_the_full_kernels_bits(name):
         assert np.array_equal(a, b, equal_nan=True)
 
 
+@pytest.mark.parametrize("name", ["bao_desi_cmb_pantheon", "bao_desi_des5y_bbn_theta_star", "ohd_cc_des5y", "bao_desi_des5y_cc_theta_star",
+                                  "sn_pantheon_cmb", "bao_desi_des5y_rd"])
+def test_small_probe_stage12_kernel_against_the_full_kernel(name):
+    """A large SN block on the fast path together with BAO / compressed CMB / cosmic chronometers runs the small-probe
+    instantiation of stage 1+2 (digit planes written by stage 2, probes on the CTA's last threads, one barrier fewer); the
+    full kernel (`stage12_lean = 0`: FP64 residual rows + slicing kernel) must give the same digit planes - hence the same
+    SN chi2 bits - and the same small terms; prior rows and the CPL guard rows included, and the components one by one."""
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    g = golden(name)
+    theta = np.concatenate([g["theta"], uniform_theta(g["bounds"], 500, seed=12)])
+    res = []
+    for lean in (1, 0):
+        with Engine(spec(name)) as e:
+            e.set_option("stage12_lean", lean)
+            chi2 = e.chi_squared(theta)
+            planes_ms = e.stage3_split()[0]     # time of the separate slicing kernel (cl_stage3_split)
+            res.append((chi2, e.log_probability(theta * 1.01), e.log_likelihood(theta), e.components(theta), planes_ms))
+    (c1, p1, l1, k1, n1), (c0, p0, l0_, k0, n0) = res
+    assert n1 < 0.004 < n0                                           # the slicing kernel is gone from the default path
+    assert np.array_equal(k1[:, 0], k0[:, 0], equal_nan=True)        # SN chi2: same planes, same integers
+    assert np.array_equal(np.isneginf(p1), np.isneginf(p0))
+    for a, b in ((c1, c0), (l1, l0_), (k1, k0)):
+        fin = np.isfinite(b)
+        assert np.array_equal(fin, np.isfinite(a))
+        assert np.all(np.abs(a[fin] - b[fin]) <= 1e-9 * np.maximum(1.0, np.abs(b[fin])))
+    fin = np.isfinite(p0)
+    assert np.all(np.abs(p1[fin] - p0[fin]) <= 1e-9 * np.maximum(1.0, np.abs(p0[fin])))
+
+
 def test_nan_parameters_give_nan_like_numpy(engines):
     """NaN / Inf parameters and E^2 < 0 (Omega_m < 0) make D_M NaN; np.log10 in the reference then returns NaN and so must
     chi_squared / log_likelihood here (the table log10 of the fast SN path decodes bits and would otherwise return a finite
