@@ -199,3 +199,32 @@ def test_guard_is_batch_independent():
         part = np.concatenate([e.chi_squared(theta[:300]), e.chi_squared(theta[300:301]), e.chi_squared(theta[301:])])
     assert np.array_equal(full, part)
     assert 0 < n_flag < theta.shape[0], n_flag
+
+
+@pytest.mark.parametrize("name", ["bao_desi_cmb_pantheon", "bao_desi_des5y_bbn_theta_star"])
+def test_guard_fallback_of_the_small_probe_kernel(name):
+    """Configurations whose stage 2 writes the digit planes from the small-probe instantiation (SN block + BAO / CMB terms):
+    when the guard fires, the FP64 residual rows of the flagged blocks are regenerated by the FULL kernel and contracted on the
+    FP64 tensor pipe - the values are then the FP64 engine's, bit for bit, for flagged rows, and the small terms are untouched."""
+    from cases import golden, spec
+    from cosmology_model_fit_b200 import Engine
+    from cosmology_model_fit_b200.synthetic import uniform_theta
+    theta = uniform_theta(golden(name)["bounds"], 1000, seed=3)
+    with Engine(spec(name)) as e:
+        base = e.chi_squared(theta)
+        comp = e.components(theta)
+        assert e.guard_info()["rows_total"] == 0
+        e.set_option("chi2_guard_abs", 1e-30)
+        e.set_option("chi2_guard_rel", 0.0)          # every finite row exceeds this tolerance: all rows take the fallback
+        guarded = e.chi_squared(theta)
+        comp_g = e.components(theta)
+        n_flag = e.guard_info()["rows_last_pass"]
+        e.set_option("chi2_engine", 0)
+        fp64 = e.chi_squared(theta)
+        comp_f = e.components(theta)
+    fin = np.isfinite(fp64)
+    assert n_flag == int(fin.sum()) and n_flag > 900
+    assert np.array_equal(comp_g[:, 0], comp_f[:, 0], equal_nan=True)      # SN chi2: the FP64 engine's bits
+    assert np.array_equal(guarded, fp64, equal_nan=True)
+    assert np.allclose(comp_g[fin, 1:], comp[fin, 1:], rtol=1e-9, atol=1e-9)
+    assert np.all(np.abs(base[fin] - fp64[fin]) <= np.maximum(1e-6, 1e-12 * np.abs(fp64[fin])))
