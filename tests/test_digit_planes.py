@@ -80,3 +80,50 @@ def test_int32_headroom_bound():
     """Worst case of one level: S products of |d_i d_j| <= 2^14 over n terms; the library keeps the tcgen05 engine for
     n_sn <= 16384 (cosmolike.cu) where 7 * 2^14 * n < 2^31."""
     assert 7 * 2**14 * 16384 < 2**31 and 7 * 2**14 * 18725 > 2**31
+
+
+def _fma(a, b, c):
+    """Correctly rounded a * b + c (what DFMA computes), through exact rational arithmetic."""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+@pytest.mark.parametrize("S", [5, 6, 7])
+def test_epilogue_fold_one_fma_per_level_group(S):
+    """The epilogue's fold (csrc/chi2_ozaki.cuh): a group of up to three levels is built as the integer
+    g = a_l 2^16 + a_(l+1) 2^8 + a_(l+2) in the low mantissa bits of the double kBias + g; group 0 takes its bias off inside
+    its FMA (exact), the later groups are added bias and all, and the exactly representable sum of the carried constants
+    comes off together with the column scale: y = fma(h, cs, -C cs).  Against the exact value of sum_l 2^-8l a_l: relative
+    2^-52 when the high groups dominate, and never worse than an absolute 2^-40 (units of the level-0 digit product) when
+    they cancel - the a-priori bound already allows 2^-39 per TERM of the sum that produced a_l."""
+    from fractions import Fraction
+    rng = np.random.default_rng(100 + S)
+    kBias = 6755401588539392.0                                    # 1.5 * 2^52 + 2^31
+    assert kBias == 1.5 * 2.0**52 + 2.0**31
+    groups = {7: [(0, 3), (3, 3), (6, 1)], 6: [(0, 3), (3, 3)], 5: [(0, 3), (3, 2)]}[S]
+    C = kBias * sum(2.0 ** (-8 * (l0 + cnt - 1)) for l0, cnt in groups[1:])
+    assert Fraction(C) == Fraction(kBias) * sum(Fraction(1, 2 ** (8 * (l0 + cnt - 1))) for l0, cnt in groups[1:])   # representable
+    n_sn = 2048
+    n_abs = 0
+    for trial in range(400):
+        # level l holds l + 1 products of |d_i d_j| <= 2^14 over n_sn terms; every tenth trial has cancelling high levels
+        acc = [int(rng.integers(-(l + 1) * 2**14 * n_sn, (l + 1) * 2**14 * n_sn + 1)) for l in range(S)]
+        if trial % 10 == 0:
+            acc[0] = acc[1] = acc[2] = 0
+            acc[3] = int(rng.integers(-3, 4))
+        cs = 2.0 ** int(rng.integers(-30, 10))
+        h = None
+        for gi, (l0, cnt) in enumerate(groups):
+            g = sum(acc[l0 + q] << (8 * (cnt - 1 - q)) for q in range(cnt))
+            assert abs(g) < 2**51
+            t = kBias + g                                          # exact: the integer sits in the mantissa
+            assert Fraction(t) == Fraction(kBias) + g
+            wg = 2.0 ** (-8 * (l0 + cnt - 1))
+            h = _fma(t, wg, -kBias * wg) if gi == 0 else _fma(t, wg, h)
+        y = _fma(h, cs, -C * cs)
+        exact = sum(Fraction(acc[l], 2 ** (8 * l)) for l in range(S)) * Fraction(cs)
+        err = abs(Fraction(y) - exact)
+        rel = float(err / abs(exact)) if exact != 0 else 0.0
+        assert rel <= 2.0**-51 or float(err / Fraction(cs)) <= 2.0**-40, (trial, rel, float(err))
+        n_abs += rel > 2.0**-51
+    assert n_abs <= 40                                             # only the cancelling cases lean on the absolute bound
