@@ -393,7 +393,17 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
 #define sn_small (LEAN ? false : (bool)s.sn_small)
   S12Smem& sm = *reinterpret_cast<S12Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pt = LEAN == 2 ? kS12Threads - 1 - tid : tid;   // thread index of the small probes (LEAN = 2: from the top down)
+  // Thread layout of the small probes.  They are long dependent chains on a handful of threads (a BAO point is two PCHIP
+  // slopes with their divisions, a Gauss-Legendre node a 5-term neutrino sum and three square roots), so what matters is that
+  // they do NOT share a warp: a warp executes its lanes' different branches one after the other, and with everything indexed
+  // from thread 0 warp 0 ran the small-SN residuals, then the BAO points, then the chronometers, then its 32 Gauss-Legendre
+  // nodes while the other warps waited at the barrier (30 % of the stall samples of bao/desi_cmb_union3.py).  Now: BAO and
+  // chronometers from the top down (pt: warp 7), the small SN block below them (st: threads 223, 222, ...: warp 6 and down),
+  // the 200 Gauss-Legendre nodes from the bottom up (gt: warps 0-6; from the top down in the small-probe instantiation, whose
+  // low warps carry the second supernova trip), the scalar tail on thread 0.
+  const int pt = kS12Threads - 1 - tid;
+  const int st = kS12Threads - 33 - tid;
+  const int gt = LEAN == 2 ? pt : tid;
   const int G = s.G;
   if (tid < 128) sm.logtab[tid] = s.logtab[tid];  // visible after the first __syncthreads of the loop body
   const uint32_t gd_addr = s12_smem_u32(sm.gd), tab_addr = s12_smem_u32(sm.logtab);
@@ -756,7 +766,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
         // four consecutive supernovae per thread and trip; the residuals leave as two 16-byte stores (the row is 128-byte aligned)
         double* __restrict__ outp = to_smem ? (sm.vec + CL_MAX_BAO + CL_MAX_CC) : Rrow;
         const int m4 = (n_sn + 3) >> 2;
-        for (int m = tid; m < m4; m += kS12Threads) {
+        for (int m = to_smem ? st : tid; (unsigned)m < (unsigned)m4; m += kS12Threads) {   // (small block: threads 223, 222, ...)
           double2 zs[4];
           double ob[4], d[4];
           load4(m, zs, ob);
@@ -795,7 +805,8 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
           }
           return hermite_dm(s, sm.gd, sm.off, zq);
         };
-        for (int i = tid; i < n_sn; i += kS12Threads) {
+        // (a small SN block sits on threads 223, 222, ...: see the thread layout at the top)
+        for (int i = to_smem ? st : tid; (unsigned)i < (unsigned)n_sn; i += kS12Threads) {
           const double2 p0 = __ldg(pack + 2 * i), p1 = __ldg(pack + 2 * i + 1);  // {z_cmb, w0}, {1+z_hel, obs}
           double zq = p0.x;
           if (s.n_vel > 0) {
@@ -842,12 +853,12 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     double zstar = 0.0;
     if (need_cmb) {
       zstar = zstar_from_terms(s.k, scal);
-      if (pt < s.n_gl) {
+      if (gt < s.n_gl) {
         double hw = zstar / 2.0;
-        double z = hw * __ldg(s.gl_x + pt) + hw;
-        v[0] = __ldg(s.gl_w + pt) * DH_of_z<FAM, DE>(s, c, z);
-      } else if (pt < 2 * s.n_gl) {
-        int q = pt - s.n_gl;
+        double z = hw * __ldg(s.gl_x + gt) + hw;
+        v[0] = __ldg(s.gl_w + gt) * DH_of_z<FAM, DE>(s, c, z);
+      } else if (gt < 2 * s.n_gl) {
+        int q = gt - s.n_gl;
         double a_lim = 1.0 / (1.0 + zstar);
         double hw = a_lim / 2.0;
         double av = hw * __ldg(s.gl_x + q) + hw;
@@ -860,30 +871,36 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     if (need_red && LEAN != 2) __syncthreads();  // sm.vec complete (LEAN = 2: behind the barrier of the row scale)
 
     if (mode == MODE_EVAL) {
-      if (pt < n_bao) {  // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
+      // sum_i d[i] M[i * stride_i + ...]: the matrix elements come from L2 (all of L1 is carved out as shared memory), so they
+      // are fetched four at a time ahead of the multiply-adds; the additions keep their order (same bits as the plain loop)
+      auto dot_strided = [&](const double* __restrict__ d, const double* __restrict__ m, int n, int stride) {
         double t = 0.0;
-        for (int i = 0; i < n_bao; i++) t += sm.vec[i] * __ldg(s.bao_W + i * n_bao + pt);
-        v[2] = t * sm.vec[pt];
-      }
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+          const double m0 = __ldg(m + (i + 0) * stride), m1 = __ldg(m + (i + 1) * stride), m2 = __ldg(m + (i + 2) * stride),
+                       m3 = __ldg(m + (i + 3) * stride);
+          t += d[i] * m0; t += d[i + 1] * m1; t += d[i + 2] * m2; t += d[i + 3] * m3;
+        }
+        for (; i < n; i++) t += d[i] * __ldg(m + i * stride);
+        return t;
+      };
+      if (pt < n_bao)   // delta @ inv_cov @ delta (bao/desi_cmb_union3.py:97-100)
+        v[2] = dot_strided(sm.vec, s.bao_W + pt, n_bao, n_bao) * sm.vec[pt];
       if (pt < n_cc) {
         const double* d = sm.vec + CL_MAX_BAO;
-        double t = 0.0;
-        for (int i = 0; i < n_cc; i++) t += d[i] * __ldg(s.cc_W + i * n_cc + pt);
-        v[3] = t * d[pt];
+        v[3] = dot_strided(d, s.cc_W + pt, n_cc, n_cc) * d[pt];
       }
-      if (sn_small && tid < n_sn) {
+      if (sn_small && (unsigned)st < (unsigned)n_sn) {
         const double* d = sm.vec + CL_MAX_BAO + CL_MAX_CC;
-        double t = 0.0;
         if (s.sn_form == CL_SN_INVCOV) {  // delta @ inv_cov @ delta (sn/union3_1.py:57)
-          for (int i = 0; i < n_sn; i++) t += d[i] * __ldg(s.sn_mat_small + i * n_sn + tid);
-          v[4] = t * d[tid];
+          v[4] = dot_strided(d, s.sn_mat_small + st, n_sn, n_sn) * d[st];
         } else {  // |L^-1 delta|^2 with W = L^-1 (solve_triangular.py:5-14)
-          for (int i = 0; i <= tid; i++) t += __ldg(s.sn_mat_small + tid * n_sn + i) * d[i];
+          const double t = dot_strided(d, s.sn_mat_small + st * n_sn, st + 1, 1);
           v[4] = t * t;
         }
       }
     }
-    const double rd_out = (need_rd && pt == 0) ? rdrag_from_terms(scal) : 0.0;
+    const double rd_out = (need_rd && tid == 0) ? rdrag_from_terms(scal) : 0.0;
     // The theta row of the next iteration (loaded into a register at the top) is parked in the other buffer; no thread
     // reads that buffer in this iteration (the previous row's readers all passed this iteration's first barrier).
     if (stage_next && !row_synced) sm.theta[tb ^ 1][tid] = th_next;
@@ -893,7 +910,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       block_sum<5>(v, sm.red[tb], mask);
     } else if (!row_synced) __syncthreads();
 
-    if (pt == 0) {   // (LEAN = 2: the last thread, which owns no grid nodes - the next row's grid pass does not wait for this tail)
+    if (tid == 0) {   // (warp 0: the last warp also carries the fit terms of the next row in front of the grid-pass barrier)
       double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
       if (need_cmb) {
         dm = (zstar / 2.0) * v[0];
