@@ -959,9 +959,9 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
   const unsigned fgrid = (unsigned)((rows + 255) / 256);
   FinalizeArgs f{};
   f.B = rows; f.what = what; f.n_part = planes ? 2 * c->oz_T : c->T; f.sn_large = large ? 1 : 0;
-  f.part = c->d_part; f.aux = c->d_aux; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value; f.q = q;
+  f.part = c->d_part; f.aux = c->d_aux; f.theta = d_theta; f.ld = ld; f.out = d_out; f.comps = d_comps; f.guard_value = c->ds.guard_value; f.q = q;
   if (moments) k_sum_parts<<<fgrid, 256, 0, st>>>(c->d_part, c->d_part_u, f.n_part, rows, c->uu, d_out, q);   // d_out[rows][3] = (yy, yu, uu)
-  else k_finalize<<<fgrid, 256, 0, st>>>(f);
+  else k_finalize<<<fgrid, 256, 0, st>>>(c->ds, f);
   c->launches++;
   CUDA_TRY(c, cudaGetLastError());
   if (guard) {
@@ -978,7 +978,7 @@ static int run_pass(cl_ctx* c, const double* d_theta, int64_t rows, int64_t ld, 
     q.only_flagged = 1;
     f.q = q; f.part = c->d_part_fb; f.n_part = c->T;
     if (moments) k_sum_parts<<<fgrid, 256, 0, st>>>(c->d_part_fb, c->d_part_u_fb, c->T, rows, c->uu, d_out, q);
-    else k_finalize<<<fgrid, 256, 0, st>>>(f);
+    else k_finalize<<<fgrid, 256, 0, st>>>(c->ds, f);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
   }

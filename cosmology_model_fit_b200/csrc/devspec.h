@@ -10,7 +10,10 @@ namespace cosmolike {
 constexpr double kC_KMS = 299792.458;  // scipy.constants.c / 1000 (sn/pantheon.py:12)
 
 // aux planes written by the stage-1/2 kernel, [AUX_COUNT][B] (structure of arrays)
-enum { AUX_BAO = 0, AUX_CMB = 1, AUX_EXTRA = 2, AUX_CCNORM = 3, AUX_LOGPRIOR = 4, AUX_FLAGS = 5, AUX_SN_SMALL = 6, AUX_COUNT = 7 };
+// (raw block sums: the scalar algebra on top of them - compressed-CMB vector and chi2, chronometer normalisation, Gaussian
+// terms - is done by the finalize kernel, one thread per row, instead of by one thread of the stage-1/2 CTA while the CTA's
+// other warps wait for it at the next row's first barrier)
+enum { AUX_BAO = 0, AUX_GL_DM = 1, AUX_GL_RS = 2, AUX_CC = 3, AUX_LOGPRIOR = 4, AUX_FLAGS = 5, AUX_SN_SMALL = 6, AUX_ZSTAR = 7, AUX_COUNT = 8 };
 enum { FLAG_GUARD = 1, FLAG_OUTSIDE = 2 };
 
 // what the stage-1/2 kernel produces

@@ -381,6 +381,16 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*
   }
 }
 
+// compressed-CMB vector from the two Gauss-Legendre sums (cmb/data_planck_act_compression.py:160-212)
+__device__ __forceinline__ void cmb_vector(const DevSpec& s, const Cosmo& c, double zstar, double gl_dm, double gl_rs, double (&cmbv)[3],
+                                           double& rs, double& dm) {
+  dm = (zstar / 2.0) * gl_dm;
+  rs = ((1.0 / (1.0 + zstar)) / 2.0) * gl_rs;
+  const double Om_h2 = c.och2 + c.obh2 + s.k.Omnu_h2;
+  if (s.cmb_mode == CL_CMB_THETA_WB_WM) { cmbv[0] = rs / dm; cmbv[1] = c.obh2; cmbv[2] = Om_h2; }
+  else { cmbv[0] = 100 * sqrt(Om_h2) * dm / kC_KMS; cmbv[1] = M_PI * dm / rs; cmbv[2] = c.obh2; }
+}
+
 struct S12Smem {
   double2 gd[kPaddedGrid];  // {D_M relative to the first node of the 16-node chunk, hscale * dh} per grid node, padded
   double off[kS12Threads];  // D_M at the first node of each chunk
@@ -929,46 +939,25 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
       block_sum<5>(v, sm.red[tb], mask);
     } else if (!row_synced) __syncthreads();
 
-    if (tid == 0) {   // (warp 0: the last warp also carries the fit terms of the next row in front of the grid-pass barrier)
-      double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
-      if (need_cmb) {
-        dm = (zstar / 2.0) * v[0];
-        rs = ((1.0 / (1.0 + zstar)) / 2.0) * v[1];
-        double Om_h2 = c.och2 + c.obh2 + s.k.Omnu_h2;
-        if (cmb_mode == CL_CMB_THETA_WB_WM) { cmbv[0] = rs / dm; cmbv[1] = c.obh2; cmbv[2] = Om_h2; }
-        else { cmbv[0] = 100 * sqrt(Om_h2) * dm / kC_KMS; cmbv[1] = M_PI * dm / rs; cmbv[2] = c.obh2; }
-      }
+    if (tid == 0) {
       if (mode == MODE_CMB) {
+        double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
+        cmb_vector(s, c, zstar, v[0], v[1], cmbv, rs, dm);
         double* r = a.out + b * 8;
         r[0] = cmbv[0]; r[1] = cmbv[1]; r[2] = cmbv[2]; r[3] = zstar; r[4] = rs; r[5] = dm;
         r[6] = rd_out; r[7] = 100 * (rs / dm);
       } else {
-        double chi2_cmb = 0.0;
-        if (cmb_mode != CL_CMB_NONE) {
-          double d[3] = {s.cmb_prior[0] - cmbv[0], s.cmb_prior[1] - cmbv[1], s.cmb_prior[2] - cmbv[2]};
-          for (int j = 0; j < 3; j++) {
-            double t = 0.0;
-            for (int i = 0; i < 3; i++) t += d[i] * s.cmb_W[i * 3 + j];
-            chi2_cmb += t * d[j];
-          }
-        }
-        double extra = 0.0, ccnorm = 0.0;
-        if (n_cc > 0) {
-          double f = s.col_fcc >= 0 ? th[s.col_fcc] : 1.0;
-          extra += (s.cc_norm_sign < 0.0 ? 1.0 / (f * f) : f * f) * v[3];   // error-inflation form: chi2 * f ** -2 (ohd/cc_pantheon.py:63)
-          if (s.cc_norm_sign != 0.0) ccnorm = n_cc * log(2 * M_PI) + s.cc_logdet - s.cc_norm_sign * 2 * n_cc * log(f);
-        }
-        for (int g = 0; g < s.n_gc; g++) {
-          double r = (th[s.gc_col[g]] - s.gc_mean[g]) / s.gc_sigma[g];
-          extra += r * r;
-        }
+        // the raw block sums leave as they are: k_finalize does the scalar algebra (one thread per row there; here it was
+        // ~270 instructions with divisions, a square root and a logarithm on ONE thread whose warp the CTA then waited for at
+        // the next row's grid-pass barrier)
         a.aux[AUX_BAO * a.B + b] = v[2];
-        a.aux[AUX_CMB * a.B + b] = chi2_cmb;
-        a.aux[AUX_EXTRA * a.B + b] = extra;
-        a.aux[AUX_CCNORM * a.B + b] = ccnorm;
+        a.aux[AUX_GL_DM * a.B + b] = v[0];
+        a.aux[AUX_GL_RS * a.B + b] = v[1];
+        a.aux[AUX_CC * a.B + b] = v[3];
         a.aux[AUX_LOGPRIOR * a.B + b] = lp;
         a.aux[AUX_FLAGS * a.B + b] = 0.0;
         a.aux[AUX_SN_SMALL * a.B + b] = v[4];
+        a.aux[AUX_ZSTAR * a.B + b] = zstar;
       }
     }
     // (the barrier inside block_sum orders this iteration's shared-memory reads before the next row's writes)
@@ -1015,13 +1004,15 @@ struct FinalizeArgs {
   int what, n_part, sn_large;
   const double* part;  // [n_part][B] per-column-tile partial sums of |W r|^2
   const double* aux;   // [AUX_COUNT][B]
+  const double* theta; // [B][ld] the pass's parameter vectors (the scalar terms need a few of their columns)
+  int64_t ld;
   double* out;         // [B]
   double* comps;       // nullable [B][4]
   double guard_value;
   GuardArgs q;
 };
 
-__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FinalizeArgs f) {
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ DevSpec s, const __grid_constant__ FinalizeArgs f) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= f.B) return;
   if (f.q.only_flagged && (f.q.guard[1] == 0 || !f.q.rowflag[b])) return;
@@ -1038,13 +1029,37 @@ __global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ Finali
   if (f.sn_large) for (int t = 0; t < f.n_part; t++) sn += f.part[(int64_t)t * f.B + b];
   else sn = f.aux[AUX_SN_SMALL * f.B + b];
   if (f.q.rowscale && !f.q.only_flagged) guard_row(f.q, b, sn);
-  double bao = f.aux[AUX_BAO * f.B + b], cmb = f.aux[AUX_CMB * f.B + b], extra = f.aux[AUX_EXTRA * f.B + b];
+  // scalar algebra on the raw block sums of stage 1+2 (bao/desi_cmb_union3.py:103-135, ohd/cc.py:29-33, ohd/cc_pantheon.py:63)
+  const double* __restrict__ th = f.theta + b * f.ld;
+  const double bao = f.aux[AUX_BAO * f.B + b];
+  double cmb = 0.0, extra = 0.0, ccnorm = 0.0;
+  if (s.cmb_mode != CL_CMB_NONE) {
+    Cosmo c;
+    unpack(s, th, c);
+    double cmbv[3], rs, dm;
+    cmb_vector(s, c, f.aux[AUX_ZSTAR * f.B + b], f.aux[AUX_GL_DM * f.B + b], f.aux[AUX_GL_RS * f.B + b], cmbv, rs, dm);
+    const double d[3] = {s.cmb_prior[0] - cmbv[0], s.cmb_prior[1] - cmbv[1], s.cmb_prior[2] - cmbv[2]};
+    for (int j = 0; j < 3; j++) {
+      double t = 0.0;
+      for (int i = 0; i < 3; i++) t += d[i] * s.cmb_W[i * 3 + j];
+      cmb += t * d[j];
+    }
+  }
+  if (s.n_cc > 0) {
+    const double fcc = s.col_fcc >= 0 ? th[s.col_fcc] : 1.0;
+    extra += (s.cc_norm_sign < 0.0 ? 1.0 / (fcc * fcc) : fcc * fcc) * f.aux[AUX_CC * f.B + b];   // error-inflation form: chi2 * f ** -2 (ohd/cc_pantheon.py:63)
+    if (s.cc_norm_sign != 0.0) ccnorm = s.n_cc * log(2 * M_PI) + s.cc_logdet - s.cc_norm_sign * 2 * s.n_cc * log(fcc);
+  }
+  for (int g = 0; g < s.n_gc; g++) {
+    const double r = (th[s.gc_col[g]] - s.gc_mean[g]) / s.gc_sigma[g];
+    extra += r * r;
+  }
   if (f.comps) { f.comps[b * 4] = sn; f.comps[b * 4 + 1] = bao; f.comps[b * 4 + 2] = cmb; f.comps[b * 4 + 3] = extra; }
   if (!f.out) return;
   double chi2 = sn + bao + cmb + extra;
   if (f.what == CL_OUT_CHI2) f.out[b] = chi2;
   else {
-    double ll = -0.5 * (chi2 + f.aux[AUX_CCNORM * f.B + b]);
+    double ll = -0.5 * (chi2 + ccnorm);
     f.out[b] = f.what == CL_OUT_LOGLIKE ? ll : lp + ll;
   }
 }
