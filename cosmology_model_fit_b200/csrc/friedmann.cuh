@@ -361,8 +361,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // block-wide sums of the values selected by `mask` (fixed order -> deterministic); result valid in every thread.  ONE barrier:
 // the scratch is double-buffered by the caller (`s_red` alternates between rows), so a row's reads cannot meet the next
 // row's writes - a thread reaches those only behind the next row's barriers.
+// `finish` = false stops behind the barrier (the caller adds the eight partials of a value itself: block_partials_sum).
 template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*8] */, unsigned mask) {
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*8] */, unsigned mask, bool finish = true) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < NV; q++) {
@@ -371,6 +372,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /* [NV*
     if (lane == 0) s_red[q * 8 + warp] = w;
   }
   __syncthreads();
+  if (!finish) return;
 #pragma unroll
   for (int q = 0; q < NV; q++) {
     if (!((mask >> q) & 1u)) continue;
@@ -389,6 +391,14 @@ __device__ __forceinline__ void cmb_vector(const DevSpec& s, const Cosmo& c, dou
   const double Om_h2 = c.och2 + c.obh2 + s.k.Omnu_h2;
   if (s.cmb_mode == CL_CMB_THETA_WB_WM) { cmbv[0] = rs / dm; cmbv[1] = c.obh2; cmbv[2] = Om_h2; }
   else { cmbv[0] = 100 * sqrt(Om_h2) * dm / kC_KMS; cmbv[1] = M_PI * dm / rs; cmbv[2] = c.obh2; }
+}
+
+// the eight warp partials of value q in warp order (the order block_sum itself uses: same bits)
+__device__ __forceinline__ double block_partials_sum(const double* s_red, int q) {
+  double a = 0.0;
+#pragma unroll
+  for (int w = 0; w < kS12Threads / 32; w++) a += s_red[q * 8 + w];
+  return a;
 }
 
 struct S12Smem {
@@ -934,31 +944,31 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
     // reads that buffer in this iteration (the previous row's readers all passed this iteration's first barrier).
     if (stage_next && !row_synced) sm.theta[tb ^ 1][tid] = th_next;
     // The next iteration stores its grid nodes before its first barrier, so every thread must be done reading gd.
-    if (need_red) {
-      const unsigned mask = (need_cmb ? 3u : 0u) | (n_bao > 0 ? 4u : 0u) | (n_cc > 0 ? 8u : 0u) | (sn_small ? 16u : 0u);
-      block_sum<5>(v, sm.red[tb], mask);
-    } else if (!row_synced) __syncthreads();
+    const unsigned mask = (need_cmb ? 3u : 0u) | (n_bao > 0 ? 4u : 0u) | (n_cc > 0 ? 8u : 0u) | (sn_small ? 16u : 0u);
+    if (need_red) block_sum<5>(v, sm.red[tb], mask, mode != MODE_EVAL);
+    else if (!row_synced) __syncthreads();
 
-    if (tid == 0) {
-      if (mode == MODE_CMB) {
-        double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
-        cmb_vector(s, c, zstar, v[0], v[1], cmbv, rs, dm);
-        double* r = a.out + b * 8;
-        r[0] = cmbv[0]; r[1] = cmbv[1]; r[2] = cmbv[2]; r[3] = zstar; r[4] = rs; r[5] = dm;
-        r[6] = rd_out; r[7] = 100 * (rs / dm);
-      } else {
-        // the raw block sums leave as they are: k_finalize does the scalar algebra (one thread per row there; here it was
-        // ~270 instructions with divisions, a square root and a logarithm on ONE thread whose warp the CTA then waited for at
-        // the next row's grid-pass barrier)
-        a.aux[AUX_BAO * a.B + b] = v[2];
-        a.aux[AUX_GL_DM * a.B + b] = v[0];
-        a.aux[AUX_GL_RS * a.B + b] = v[1];
-        a.aux[AUX_CC * a.B + b] = v[3];
-        a.aux[AUX_LOGPRIOR * a.B + b] = lp;
-        a.aux[AUX_FLAGS * a.B + b] = 0.0;
-        a.aux[AUX_SN_SMALL * a.B + b] = v[4];
-        a.aux[AUX_ZSTAR * a.B + b] = zstar;
+    if (mode == MODE_EVAL) {
+      // The raw block sums leave as they are, one aux plane per lane of warp 0: lanes 0-4 add the eight warp partials of one
+      // value each (warp order: deterministic), lanes 5-7 carry the log-prior, the flags and z*.  k_finalize does the scalar
+      // algebra on top (one thread per row there; here it was ~270 instructions with divisions, a square root and a
+      // logarithm on ONE thread - and every thread of the CTA adding all partials of all values - while the CTA's other
+      // warps waited at the next row's grid-pass barrier).
+      if (tid < 8) {
+        double val;
+        if (tid < 5) val = (need_red && ((mask >> tid) & 1u)) ? block_partials_sum(sm.red[tb], tid) : 0.0;
+        else val = tid == 5 ? lp : tid == 6 ? 0.0 : zstar;
+        // value order of v[]: GL D_M sum, GL r_s sum, BAO, chronometers, small SN block
+        const int slot = tid == 0 ? AUX_GL_DM : tid == 1 ? AUX_GL_RS : tid == 2 ? AUX_BAO : tid == 3 ? AUX_CC : tid == 4 ? AUX_SN_SMALL
+                       : tid == 5 ? AUX_LOGPRIOR : tid == 6 ? AUX_FLAGS : AUX_ZSTAR;
+        a.aux[slot * a.B + b] = val;
       }
+    } else if (tid == 0) {   // MODE_CMB helper (block_sum has left the sums in v)
+      double cmbv[3] = {0.0, 0.0, 0.0}, rs = 0.0, dm = 0.0;
+      cmb_vector(s, c, zstar, v[0], v[1], cmbv, rs, dm);
+      double* r = a.out + b * 8;
+      r[0] = cmbv[0]; r[1] = cmbv[1]; r[2] = cmbv[2]; r[3] = zstar; r[4] = rs; r[5] = dm;
+      r[6] = rd_out; r[7] = 100 * (rs / dm);
     }
     // (the barrier inside block_sum orders this iteration's shared-memory reads before the next row's writes)
   }
