@@ -40,7 +40,7 @@ I8_PEAK_TOPS = 4485.0
 FP64_PIPE_TFLOPS = 37.1
 #: algorithmic FP64 flops of stage 1+2 per evaluation: 9 per grid node + 40 per supernova
 S12_FLOPS_PER_EVAL = lambda n_sn, n_grid: 9.0 * n_grid + 40.0 * n_sn
-OZ_DRAM_BYTES = {(7, 1701, 65536): 0.916e9}   # profiles/r04_ncu_full_summary.txt: 0.884e9 read + 0.032e9 written
+OZ_DRAM_BYTES = {(7, 1701, 65536): 0.916e9}   # profiles/r05_ncu_full_summary.txt: 0.884e9 read + 0.031e9 written
 
 
 def build_spec(n_sn):
@@ -479,8 +479,8 @@ def main():
                                  "avg_kernel_ms": s12_ms, "algorithmic_flops_per_eval": S12_FLOPS_PER_EVAL(N, int(spec.z_grid.size)),
                                  "hbm_gbs": s12_bytes / (s12_ms * 1e-3) / 1e9, "hbm_frac": s12_bytes / (s12_ms * 1e-3) / 1e9 / hbm_peak,
                                  "note": "FP64-ALU / issue bound, not HBM bound (SURVEY.md T5): algorithmic FP64 flops (9 G + 40 N, SURVEY.md 8(d)) against the "
-                                         "FP64 pipe (64 DFMA/clk/SM = 37.1 TFLOP/s, profiles/r01_ubench_fp64.log); ncu: FP64 pipe 38 % of cycles, "
-                                         "issue slots 56 % (profiles/r04_ncu_full_summary.txt); HBM traffic = theta in + 7 digit planes out"},
+                                         "FP64 pipe (64 DFMA/clk/SM = 37.1 TFLOP/s, profiles/r01_ubench_fp64.log); ncu: FP64 pipe 39 % of cycles, "
+                                         "issue slots 57 % (profiles/r05_ncu_full_summary.txt); HBM traffic = theta in + 7 digit planes out"},
             "stage_ms": {"stage12": s12_ms, "stage3_planes": planes_ms, "stage3_contraction": gemm_ms, "finalize": float(np.mean(hist[:, 2])),
                          "total": float(np.mean(hist[:, 3]))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
