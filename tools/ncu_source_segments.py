@@ -1,3 +1,8 @@
+#!/usr/bin/env python3
+"""Split an `ncu --page source --csv` export of the stage-1+2 kernel at its BAR.SYNC instructions: executed warp-instructions
+per row, stall samples and the opcode mix of every barrier-to-barrier segment, plus the eight hottest SASS lines - "who waits
+for whom" (a segment with few instructions and many samples is a wait for the slowest warp of the segment before it).
+Usage: ncu_source_segments.py file.src.csv   (B = 65536 rows per launch assumed)"""
 import csv, sys
 rows=list(csv.reader(open(sys.argv[1])))
 for hi,r in enumerate(rows):
