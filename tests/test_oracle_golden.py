@@ -171,3 +171,52 @@ def test_generic_log_probability(name):
     assert np.array_equal(np.isneginf(lp), np.isneginf(g["logp"])) and np.isneginf(g["logp"]).sum() == 2
     fin = np.isfinite(g["logp"])
     assert np.max(np.abs(lp[fin] - g["logp"][fin])) < CHI2_ATOL
+
+
+def test_pchip_on_equal_intervals_in_units_of_the_node_spacing():
+    """The CUDA path evaluates interp_pchip (interpolator.py:5-68,111-114) on the np.linspace grid in units of the node
+    spacing (csrc/friedmann.cuh: pchip_dh): slope x h = harmonic mean of the neighbouring differences, (3 d0 - d1) / 2 with the
+    end rules at the two boundary nodes - two divisions per query instead of eleven.  Restated here in numpy and held to the
+    oracle's literal transcription of the reference: monotone data (the dh grid of a real fit is), data with sign changes and
+    flat runs, queries in the first and last interval and on nodes."""
+    import oracle.oracle as O
+    rng = np.random.default_rng(5)
+
+    def fast(xq, x, y):
+        n, step = len(x), x[1] - x[0]
+        out = np.empty_like(xq)
+        sgn = np.sign
+        def end_slope(d0, d1):
+            v = 0.5 * (3.0 * d0 - d1)
+            if d0 == 0.0 or sgn(v) != sgn(d0):
+                return 0.0
+            if sgn(d0) != sgn(d1) and abs(v) > abs(3.0 * d0):
+                return 3.0 * d0
+            return v
+        def mid_slope(dm, dp):
+            return 2.0 * dm * dp / (dm + dp) if (dm != 0.0 and dp != 0.0 and dm * dp > 0.0) else 0.0
+        for k, q in enumerate(xq):
+            if q <= x[0]:
+                out[k] = y[0]; continue
+            if q >= x[-1]:
+                out[k] = y[-1]; continue
+            i = int(np.searchsorted(x, q) - 1)
+            t = (q - x[i]) / step
+            dc = y[i + 1] - y[i]
+            m0 = end_slope(dc, y[2] - y[1]) if i == 0 else mid_slope(y[i] - y[i - 1], dc)
+            m1 = end_slope(dc, y[n - 2] - y[n - 3]) if i == n - 2 else mid_slope(dc, y[i + 2] - y[i + 1])
+            t2, t3 = t * t, t * t * t
+            out[k] = (2 * t3 - 3 * t2 + 1) * y[i] + (t3 - 2 * t2 + t) * m0 + (-2 * t3 + 3 * t2) * y[i + 1] + (t3 - t2) * m1
+        return out
+
+    x = np.linspace(0.0, 2.4, 401)
+    cases = [1.0 / np.sqrt(0.3 * (1 + x) ** 3 + 0.7),                 # dh-like: smooth, decreasing
+             np.cumsum(rng.uniform(0.0, 1.0, x.size)),                # increasing, rough
+             rng.standard_normal(x.size),                             # sign changes everywhere
+             np.repeat(rng.standard_normal(x.size // 4 + 1), 4)[:x.size]]   # flat runs
+    xq = np.concatenate([rng.uniform(-0.1, 2.5, 500), x[:3] + 1e-4, x[-3:] - 1e-4, x[5:8], [x[0], x[-1]]])
+    for y in cases:
+        want = O.interp_pchip(xq, x, y)
+        got = fast(xq, x, np.asarray(y, dtype=np.float64))
+        scale = np.max(np.abs(y))
+        assert np.max(np.abs(got - want)) <= 1e-13 * scale, np.max(np.abs(got - want)) / scale
