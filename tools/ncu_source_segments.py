@@ -29,4 +29,5 @@ for k,s in enumerate(seg):
     top=sorted(s[3].items(), key=lambda kv:-kv[1])[:7]
     print(f"seg {k}: {s[0]/B:8.1f} inst/row ({100*s[0]/tot:4.1f}%), samples {s[1]:6.0f} ({100*s[1]/tots:4.1f}%), ends at BAR {s[4]}  top: "+", ".join(f"{o} {v/B:.0f}" for o,v in top))
 lines=sorted(data,key=lambda r:-float(r[ismp]))[:8]
-for r in lines: print(r[ismp], r[ia][-5:], r[isrc][:80])
+for r in lines:
+    print(r[ismp], r[ia][-5:], r[isrc][:80])
