@@ -439,7 +439,7 @@ k_friedmann_residuals(const __grid_constant__ DevSpec s, const __grid_constant__
   // nodes while the other warps waited at the barrier (30 % of the stall samples of bao/desi_cmb_union3.py).  Now: BAO and
   // chronometers from the top down (pt: warp 7), the small SN block below them (st: threads 223, 222, ...: warp 6 and down),
   // the 200 Gauss-Legendre nodes from the bottom up (gt: warps 0-6; from the top down in the small-probe instantiation, whose
-  // low warps carry the second supernova trip), the scalar tail on thread 0.
+  // low warps carry the second supernova trip); the block sums leave through eight lanes of warp 0 (one aux plane each).
   const int pt = kS12Threads - 1 - tid;
   const int st = kS12Threads - 33 - tid;
   const int gt = LEAN == 2 ? pt : tid;
